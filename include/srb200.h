@@ -1,0 +1,215 @@
+/*
+ * srb200 — C ABI of the B200-native (sm_100a) kernels behind subspace-reg's incremental-session path.
+ *
+ * The reference (feyzaakyurek/subspace-reg) has no FFI layer: its "operator interface" is the set of
+ * PyTorch library calls made from models/resnet_language.py and eval/language_eval.py.  Each entry
+ * point below replaces one group of those calls; the cited file:line is the reference call site.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless stated;
+ *   - the caller owns all memory (including workspaces); the library never allocates device memory,
+ *     never frees and never keeps a pointer past the call;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*), no host synchronisation
+ *     unless stated;
+ *   - return 0 on success, a negative SR_E_* code otherwise; sr_last_error() returns a thread-local
+ *     human readable message for the last failure on the calling thread;
+ *   - sm_100a only: any other device is refused with SR_E_DEVICE (there is no fallback path).
+ */
+#ifndef SRB200_H_
+#define SRB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SR_OK 0
+#define SR_E_ARG (-1)     /* bad argument / unsupported shape */
+#define SR_E_DEVICE (-2)  /* not an sm_100 device, or driver entry point missing */
+#define SR_E_CUDA (-3)    /* CUDA runtime error (message in sr_last_error) */
+#define SR_E_SMALLWS (-4) /* workspace too small */
+
+const char* sr_last_error(void);
+/* version = major*10000 + minor*100 + patch */
+int32_t sr_version(void);
+/* 0 if device `dev` can run this library (compute capability 10.x), SR_E_DEVICE otherwise. */
+int32_t sr_check_device(int32_t dev);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backbone: data-layout kernels
+ * ---------------------------------------------------------------------------------------------- */
+
+/* NCHW fp32 images -> NHWC bf16 with the channel dimension zero-padded to `cpad` (multiple of 16).
+ * Replaces the implicit layout PyTorch's conv2d consumes (resnet_language.py:170-171). */
+int32_t sr_pack_input(const float* x_nchw, void* y_nhwc_bf16, int32_t batch, int32_t channels, int32_t height,
+                      int32_t width, int32_t cpad, void* stream);
+
+/* BatchNorm eval-mode fold (resnet_language.py:250-255,148; nn.BatchNorm2d eval semantics):
+ *   scale[c] = gamma[c] / sqrt(running_var[c] + eps),  shift[c] = beta[c] - running_mean[c] * scale[c]. */
+int32_t sr_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                   float eps, float* scale, float* shift, int32_t channels, void* stream);
+
+/* Conv weight repack: OIHW fp32 [cout,cin,kh,kw] -> bf16 [cout][kh*kw][cin_pad] (zero padded), each output
+ * channel optionally multiplied by scale[cout] (NULL = 1) before rounding (folded BN scale). */
+int32_t sr_pack_weight(const float* w_oihw, const float* scale, void* w_packed_bf16, int32_t cout, int32_t cin,
+                       int32_t kh, int32_t kw, int32_t cin_pad, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backbone: implicit-GEMM convolution on tcgen05 / TMEM fed by TMA
+ * Replaces nn.Conv2d + nn.BatchNorm2d(eval) + LeakyReLU + residual add + MaxPool2d / AdaptiveAvgPool2d
+ * of BasicBlock.forward (resnet_language.py:268-301) and ResNet.forward (:170-181).
+ * ---------------------------------------------------------------------------------------------- */
+#define SR_EPI_ACT 0       /* y = lrelu(acc + shift [+ residual])            -> bf16 NHWC [B,H,W,cout]       */
+#define SR_EPI_ACT_POOL2 1 /* ... then MaxPool2d(2) (floor)                  -> bf16 NHWC [B,H/2,W/2,cout]   */
+#define SR_EPI_ACT_AVG 2   /* ... then mean over H x W (AdaptiveAvgPool2d(1)) -> fp32 [B,cout]               */
+#define SR_EPI_RAW_STATS 3 /* raw accumulator -> fp32 NHWC [B,H,W,cout]; per-channel sum / sum of squares    */
+                           /*   are ADDED to stats[0..cout) / stats[cout..2cout) (fp64, caller zeroes them)  */
+
+typedef struct sr_conv_panel {
+    const void* act;  /* bf16 NHWC [batch,height,width,cin_pad]                                   */
+    const void* wgt;  /* bf16 [cout][taps][cin_pad] from sr_pack_weight                           */
+    int32_t cin_pad;  /* channel pitch, multiple of 16                                            */
+    int32_t taps;     /* 9 = 3x3 stride 1 pad 1,  1 = 1x1 stride 1                                */
+} sr_conv_panel;
+
+typedef struct sr_conv_args {
+    int32_t batch, height, width, cout;
+    int32_t n_panels;        /* 1, or 2 when the 1x1 downsample conv accumulates into the same tile     */
+    sr_conv_panel panel[2];
+    const float* shift;      /* [cout] fp32 added to the accumulator (folded BN shift); NULL = 0        */
+    const void* residual;    /* bf16 NHWC [batch,height,width,cout] added before the activation; or NULL */
+    float slope;             /* LeakyReLU negative slope (0.1 in the reference)                          */
+    int32_t epilogue;        /* SR_EPI_*                                                                 */
+    void* out;               /* see SR_EPI_*                                                             */
+    double* stats;           /* SR_EPI_RAW_STATS only                                                    */
+} sr_conv_args;
+
+int32_t sr_conv(const sr_conv_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Backbone: train-mode BatchNorm (epoch 1 of every session, language_eval.py:211,252,257)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* From fp64 sums over `count` = B*H*W values per channel: batch mean, invstd = 1/sqrt(biased var + eps);
+ * running_mean/var updated in place with `momentum` (unbiased variance), nn.BatchNorm2d train semantics. */
+int32_t sr_bn_finalize(const double* stats, int64_t count, float eps, float momentum, float* running_mean,
+                       float* running_var, float* mean, float* invstd, int32_t channels, void* stream);
+
+typedef struct sr_bn_apply_args {
+    int32_t batch, height, width, channels;
+    const float* raw;       /* fp32 NHWC conv output (SR_EPI_RAW_STATS)                                  */
+    const float *mean, *invstd, *gamma, *beta;
+    const float* res_raw;   /* optional: fp32 NHWC raw output of the 1x1 downsample conv ...             */
+    const float *res_mean, *res_invstd, *res_gamma, *res_beta; /* ... with its own batch-norm            */
+    const void* res_act;    /* optional: bf16 NHWC identity residual                                     */
+    int32_t lrelu;          /* apply LeakyReLU(slope) after the (optional) residual add                  */
+    float slope;
+    int32_t pool;           /* 0 none, 2 = MaxPool2d(2), -1 = global average (-> fp32 [B,C] in `out`)    */
+    const uint8_t* keep;    /* optional NCHW uint8 [B,C,Ho,Wo] keep-mask applied AFTER pooling           */
+    float keep_scale;       /* multiplier for kept elements (1/(1-p) for dropout, numel/kept for DropBlock) */
+    void* out;              /* bf16 NHWC [B,Ho,Wo,C], or fp32 [B,C] when pool == -1                      */
+} sr_bn_apply_args;
+
+int32_t sr_bn_apply(const sr_bn_apply_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Subspace regulariser: orthonormal factor of span(base weights)
+ * Replaces torch.qr(base_weight^T, some=True) in LangPuller.get_projected_weight
+ * (resnet_language.py:92-97).  Factors the Gram matrix of the smaller side.
+ * ---------------------------------------------------------------------------------------------- */
+/* base [n_base, dim] row-major fp32.  Writes an orthonormal row basis qt [rank_rows, dim] of span(rows of base)
+ * where rank_rows = min(n_base, dim); info[0..3]: info[0] = rank_rows, info[1] = 1 when the span is all of R^dim
+ * (projection == identity, n_base >= dim), info[2] = index of the first non-positive pivot + 1, else 0.
+ * workspace: sr_subspace_factor_workspace_bytes(n_base, dim) bytes. */
+int64_t sr_subspace_factor_workspace_bytes(int32_t n_base, int32_t dim);
+int32_t sr_subspace_factor(const float* base, int32_t n_base, int32_t dim, float* qt, int32_t* info, void* workspace,
+                           int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused classifier-head fine-tuning (language_eval.py:242-318)
+ * One "epoch" = CE(support) + CE(memory) + lmbd_b*||W[:nb]-W0|| + lmbd_n*||W[nb:nb+np]-Wres|| +
+ * gamma*||pull - W[new]||^2, its gradient w.r.t. W, and the SGD-momentum / Adam update of W
+ * (eval/util.py:92-102), all on cached 640-d features.
+ * ---------------------------------------------------------------------------------------------- */
+#define SR_PULL_NONE 0    /* no label_pull term                                                        */
+#define SR_PULL_FIXED 1   /* pullers constant (semantic / linear-mapping modes, resnet_language.py:75-87) */
+#define SR_PULL_PROJECT 2 /* pullers = projection of W[new] on span(base), differentiable (:92-97)      */
+#define SR_OPT_SGD 0
+#define SR_OPT_ADAM 1
+#define SR_TRACE_COLS 8
+
+typedef struct sr_head_args {
+    /* data */
+    const float* feat;        /* feature cache, row-major [*, dim]                                       */
+    int32_t dim;
+    int32_t n_support;        /* rows [support_row0, support_row0+n_support) are the support batch        */
+    int32_t support_row0;
+    int32_t n_memory;         /* rows [memory_row0, ...) are the replay batch (0 = none)                  */
+    int32_t memory_row0;
+    const int64_t* labels_support; /* [n_support] class ids                                              */
+    const int64_t* labels_memory;  /* [n_memory]                                                         */
+    /* parameters / state (updated in place) */
+    float* weight;            /* [n_classes, dim] classifier.weight                                       */
+    int32_t n_classes;
+    float* opt_state;         /* SGD: momentum buffer [n_classes*dim]; Adam: exp_avg then exp_avg_sq      */
+    /* regularisers */
+    const float* base_weight; /* W0 [n_base, dim] or NULL (no lmbd_reg_transform_w)                       */
+    int32_t n_base;
+    const float* reserve_weight; /* [n_prev_novel, dim] or NULL                                          */
+    int32_t n_prev_novel;
+    int32_t n_new;            /* rows [n_classes-n_new, n_classes) are this session's classes             */
+    int32_t pull_mode;        /* SR_PULL_*                                                                */
+    const float* pull;        /* FIXED: pullers [n_new, dim]; PROJECT: qt [q_rows, dim] from sr_subspace_factor */
+    int32_t q_rows;
+    float lmbd_base, lmbd_novel, gamma;
+    /* optimiser */
+    int32_t optimizer;        /* SR_OPT_*                                                                 */
+    float lr, momentum, weight_decay, beta1, beta2, adam_eps;
+    int32_t step0;            /* optimiser steps already taken on this state (0 for a fresh session)      */
+    /* stopping rule (language_eval.py:298-318) */
+    int32_t max_epochs;       /* run at most this many epochs in this call                                */
+    int32_t epoch0;           /* epochs already run in this session (for min/max_novel_epochs)            */
+    int32_t stable;           /* opt.stable: use the |dloss| < eps rule                                   */
+    int32_t stable_epochs;
+    int32_t stable_count0;    /* carry-over of the stable-epoch counter                                   */
+    int32_t min_novel_epochs, max_novel_epochs;
+    double convergence_epsilon;
+    double target_train_loss;
+    float prev_loss;          /* train_loss carried in (15 at session start)                              */
+    /* outputs */
+    float* loss_trace;        /* [max_epochs][SR_TRACE_COLS]: total, ce_support, ce_memory, reg_base,     */
+                              /*   reg_novel, pull, support top-1 hits, support top-5 hits (pre-update W) */
+    int32_t* status;          /* [4]: epochs run in this call, stopped flag, stable counter, reserved      */
+    float* logits_support;    /* optional [n_support, n_classes]: logits of the LAST epoch (pre-update W)  */
+    void* workspace;
+    int64_t workspace_bytes;
+} sr_head_args;
+
+int64_t sr_head_workspace_bytes(const sr_head_args* a);
+/* Persistent kernel: loops epochs on the device until the stopping rule fires or max_epochs is reached. */
+int32_t sr_head_run(const sr_head_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Query / base scoring on cached features (validate / eval_base / accuracy:
+ * language_eval.py:18-69, eval/util.py:26-40)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sr_eval_args {
+    const float* feat;      /* [n, dim]                                                                  */
+    const float* weight;    /* [n_classes, dim]                                                          */
+    const int64_t* labels;  /* [n]                                                                       */
+    int32_t n, dim, n_classes;
+    float* logits;          /* optional [n, n_classes]                                                   */
+    int32_t* pred;          /* [n] argmax (lowest index wins ties, as torch.argmax)                      */
+    int32_t* counts;        /* [2]: += top-1 hits, += top-5 hits                                         */
+    float* loss_sum;        /* [1]: += sum over rows of (logsumexp - z_y)                                */
+    int64_t* confusion;     /* optional [conf_dim, conf_dim] += 1 at (label, pred)                       */
+    int32_t conf_dim;
+} sr_eval_args;
+
+int32_t sr_eval_logits(const sr_eval_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRB200_H_ */

@@ -1,0 +1,562 @@
+// Implicit-GEMM convolution for the RFS ResNet backbone on sm_100a.
+//
+// Replaces nn.Conv2d(3x3 s1 p1 | 1x1) + eval BatchNorm2d + LeakyReLU(0.1) + residual + MaxPool2d(2) /
+// AdaptiveAvgPool2d(1) of BasicBlock.forward / ResNet.forward (reference models/resnet_language.py:268-301,
+// 170-181).  Design (B200-first, nothing shared with the reference's cuDNN path):
+//
+//   GEMM view        D[m, co] = sum_{panel, tap, ci} A_panel[pixel(m) + tap offset, ci] * B_panel[co, tap, ci]
+//   M (pixels)       one CTA owns TWO 128-row sub-tiles; a sub-tile is ONE 4-D TMA box (KC ch, TW, TH, TN) of the
+//                    NHWC bf16 activation tensor, so the nine 3x3 taps are the same box shifted by (dh, dw) and the
+//                    zero padding is TMA out-of-bounds fill.  Box shapes are chosen per feature-map size so that
+//                    >= 93 % of the 128 UMMA rows are real pixels and 2x2 pooling windows never leave the CTA.
+//   N (out channels) <= 256 per CTA, both sub-tiles share every B (weight) stage.
+//   K                one pipeline stage = one tap x one KC-channel block (KC = 64/32/16 <-> 128/64/32-byte swizzle).
+//   accumulators     2 x N fp32 columns of TMEM, written by tcgen05.mma (cta_group::1, M = 128).
+//   warps            0: TMA producer (one lane)   1: TMEM alloc + MMA issue (one lane)   2-5: epilogue
+//   epilogue         TMEM -> registers -> (+shift, +residual, LeakyReLU) -> bf16 NHWC, optionally through a shared
+//                    staging tile for MaxPool2d(2) / global average; or raw fp32 + per-channel sum / sum-of-squares
+//                    for train-mode BatchNorm.
+//   fused downsample the 1x1 conv of the residual branch is a second K "panel" accumulating into the same tile
+//                    (BN scales are folded into both weight sets, the shifts are summed on the host).
+#include <cuda_bf16.h>
+#include <algorithm>
+#include <mutex>
+#include "common.h"
+#include "ptx.cuh"
+
+namespace {
+
+using namespace srb;
+
+constexpr int kThreads = 192;       // 6 warps
+constexpr int kEpiThreads = 128;    // warps 2..5
+constexpr int kSubRows = 128;       // UMMA M
+constexpr int kStagePitchBf16 = 80; // bytes per staged row (32 bf16 + pad, conflict-free 16-byte accesses)
+constexpr int kStagePitchF32 = 33;  // floats per staged row (32 fp32 + 1)
+
+struct PanelDev {
+    CUtensorMap tmA;  // rank 4: (C, W, H, N), box (KC, TW, TH, TN)
+    CUtensorMap tmB;  // rank 2: (taps*cin_pad, cout), box (KC, n_cta)
+    int taps;
+    int ncb;       // channel blocks per tap
+    int kc_bytes;  // bytes per operand row per stage == swizzle span (32/64/128)
+    int cin_pad;
+};
+
+struct ConvParams {
+    PanelDev panel[2];
+    int n_panels;
+    int B, H, W, Cout;
+    int TW, TH, TN, stack_h;
+    int tiles_w, tiles_h;
+    int n_cta;
+    int rows_sub;
+    int stages, stage_bytes, a_slot;
+    int tmem_cols;
+    int epi;
+    float slope;
+    int Ho, Wo;
+    const float* shift;
+    const __nv_bfloat16* residual;
+    void* out;
+    double* stats;
+};
+
+__device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a);
+    __nv_bfloat162 y = *reinterpret_cast<__nv_bfloat162*>(&b);
+    __nv_bfloat162 r = __hmax2(x, y);
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+
+// After the call, lane l holds the sum over the 32 lanes of element l of v[] (v is clobbered).
+__device__ __forceinline__ float warp_transpose_sum(float* v, int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < off; ++k) {
+            const float send = upper ? v[k] : v[k + off];
+            const float keep = upper ? v[k + off] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // Dynamic shared memory is only guaranteed 16-byte aligned; swizzle-128B tiles need 1024.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    __shared__ uint64_t full_bar[16];
+    __shared__ uint64_t empty_bar[16];
+    __shared__ uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_shift[256];
+    __shared__ float s_sum[256];
+    __shared__ float s_sq[256];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // ---- tile coordinates ----
+    int t = blockIdx.x;
+    const int tw = t % p.tiles_w;
+    t /= p.tiles_w;
+    const int th = t % p.tiles_h;
+    const int tn = t / p.tiles_h;
+    const int w0 = tw * p.TW;
+    const int h0 = th * (p.stack_h ? 2 * p.TH : p.TH);
+    const int n0 = tn * (p.stack_h ? p.TN : 2 * p.TN);
+    const int sub_dh = p.stack_h ? p.TH : 0;
+    const int sub_dn = p.stack_h ? 0 : p.TN;
+    const int co0 = blockIdx.y * p.n_cta;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(&tmem_full_bar, 1);
+        mbar_fence_init();
+        for (int i = 0; i < p.n_panels; ++i) {
+            tma_prefetch_desc(&p.panel[i].tmA);
+            tma_prefetch_desc(&p.panel[i].tmB);
+        }
+    }
+    if (warp == 1) {
+        tmem_alloc_dyn(&tmem_slot, (uint32_t)p.tmem_cols);
+        tmem_relinquish();
+    }
+    if (threadIdx.x >= 64) {
+        const int et = threadIdx.x - 64;
+        for (int i = et; i < p.n_cta; i += kEpiThreads) {
+            s_shift[i] = p.shift ? p.shift[co0 + i] : 0.f;
+            s_sum[i] = 0.f;
+            s_sq[i] = 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int it = 0;
+            for (int pi = 0; pi < p.n_panels; ++pi) {
+                const PanelDev& pn = p.panel[pi];
+                const int kc = pn.kc_bytes >> 1;
+                const uint32_t tx = (uint32_t)(2 * p.rows_sub + p.n_cta) * (uint32_t)pn.kc_bytes;
+                for (int tap = 0; tap < pn.taps; ++tap) {
+                    const int dh = pn.taps == 9 ? tap / 3 - 1 : 0;
+                    const int dw = pn.taps == 9 ? tap % 3 - 1 : 0;
+                    for (int cb = 0; cb < pn.ncb; ++cb, ++it) {
+                        const int s = it % p.stages;
+                        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                        mbar_wait(&empty_bar[s], ph ^ 1u);
+                        uint8_t* st = smem + (size_t)s * p.stage_bytes;
+                        mbar_expect_tx(&full_bar[s], tx);
+                        tma_load_4d(st, &pn.tmA, &full_bar[s], cb * kc, w0 + dw, h0 + dh, n0);
+                        tma_load_4d(st + p.a_slot, &pn.tmA, &full_bar[s], cb * kc, w0 + dw, h0 + dh + sub_dh,
+                                    n0 + sub_dn);
+                        tma_load_2d(st + 2 * p.a_slot, &pn.tmB, &full_bar[s], tap * pn.cin_pad + cb * kc, co0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(kSubRows, (uint32_t)p.n_cta);
+            int it = 0;
+            for (int pi = 0; pi < p.n_panels; ++pi) {
+                const PanelDev& pn = p.panel[pi];
+                const int ksteps = pn.kc_bytes >> 5;  // UMMA K = 16 bf16 = 32 bytes
+                const int nk = pn.taps * pn.ncb;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
+                    for (int sub = 0; sub < 2; ++sub) {
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t da = umma_smem_desc(st + sub * p.a_slot + ks * 32, (uint32_t)pn.kc_bytes);
+                            const uint64_t db = umma_smem_desc(st + 2 * p.a_slot + ks * 32, (uint32_t)pn.kc_bytes);
+                            umma_f16(tmem_base + (uint32_t)(sub * p.n_cta), da, db, idesc,
+                                     (it > 0 || ks > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+                }
+            }
+            umma_commit(&tmem_full_bar);
+        }
+    } else {
+        // ================= epilogue (warps 2..5) =================
+        const int et = threadIdx.x - 64;
+        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const int m = q * 32 + lane;
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+
+        const int hw_sub = p.TH * p.TW;
+        const int nl = m / hw_sub;
+        const int rem = m - nl * hw_sub;
+        const int hl = rem / p.TW;
+        const int wl = rem - hl * p.TW;
+        const int nchunks = p.n_cta >> 5;
+
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int cbase = co0 + ch * 32;
+#pragma unroll 1
+            for (int sub = 0; sub < 2; ++sub) {
+                const int n = n0 + nl + sub * sub_dn;
+                const int h = h0 + hl + sub * sub_dh;
+                const int w = w0 + wl;
+                const bool valid = (m < p.rows_sub) && (n < p.B) && (h < p.H);
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * p.n_cta + ch * 32), v);
+                tmem_ld_wait();
+                const size_t pix = ((size_t)n * p.H + h) * p.W + w;
+
+                if (p.epi == SR_EPI_RAW_STATS) {
+                    if (valid) {
+                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Cout + cbase);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                    }
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+                    const float tsum = warp_transpose_sum(v, lane);
+                    const float tsq = warp_transpose_sum(sq, lane);
+                    atomicAdd(&s_sum[ch * 32 + lane], tsum);
+                    atomicAdd(&s_sq[ch * 32 + lane], tsq);
+                    continue;
+                }
+
+                // shift (+ residual) + LeakyReLU
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += s_shift[ch * 32 + j];
+                if (p.residual != nullptr && valid) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + cbase);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 r = __ldg(rp + j);
+                        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[k]);
+                            v[8 * j + 2 * k] += __bfloat162float(b2.x);
+                            v[8 * j + 2 * k + 1] += __bfloat162float(b2.y);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = lrelu(v[j], p.slope);
+
+                if (p.epi == SR_EPI_ACT) {
+                    if (valid) {
+                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + cbase);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                    }
+                } else if (p.epi == SR_EPI_ACT_POOL2) {
+                    uint4* dst = reinterpret_cast<uint4*>(smem + (size_t)(sub * kSubRows + m) * kStagePitchBf16);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                } else {  // SR_EPI_ACT_AVG
+                    float* dst = reinterpret_cast<float*>(smem) + (size_t)(sub * kSubRows + m) * kStagePitchF32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dst[j] = v[j];
+                }
+            }
+
+            if (p.epi == SR_EPI_ACT_POOL2) {
+                named_bar_sync(1, kEpiThreads);
+                const int Wp = p.TW >> 1;
+                const int Hp = p.stack_h ? p.TH : (p.TH >> 1);
+                const int imgs = p.stack_h ? 1 : 2 * p.TN;
+                const int items = imgs * Hp * Wp * 4;
+                for (int item = et; item < items; item += kEpiThreads) {
+                    const int g = item & 3;
+                    int pp = item >> 2;
+                    const int pw = pp % Wp;
+                    pp /= Wp;
+                    const int ph = pp % Hp;
+                    const int img = pp / Hp;
+                    const int n = n0 + img;
+                    const int hp = (h0 >> 1) + ph;
+                    const int wp = (w0 >> 1) + pw;
+                    if (n >= p.B || hp >= p.Ho || wp >= p.Wo) continue;
+                    uint4 acc = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+                        for (int dx = 0; dx < 2; ++dx) {
+                            const int hh = 2 * ph + dy;
+                            const int ww = 2 * pw + dx;
+                            int sub, hloc, nloc;
+                            if (p.stack_h) {
+                                sub = hh >= p.TH ? 1 : 0;
+                                hloc = hh - sub * p.TH;
+                                nloc = 0;
+                            } else {
+                                sub = img >= p.TN ? 1 : 0;
+                                nloc = img - sub * p.TN;
+                                hloc = hh;
+                            }
+                            const int mrow = sub * kSubRows + (nloc * p.TH + hloc) * p.TW + ww;
+                            const uint4 x = *reinterpret_cast<const uint4*>(smem + (size_t)mrow * kStagePitchBf16 + g * 16);
+                            if (dy == 0 && dx == 0) {
+                                acc = x;
+                            } else {
+                                acc.x = max_bf16x2(acc.x, x.x);
+                                acc.y = max_bf16x2(acc.y, x.y);
+                                acc.z = max_bf16x2(acc.z, x.z);
+                                acc.w = max_bf16x2(acc.w, x.w);
+                            }
+                        }
+                    }
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                       (((size_t)n * p.Ho + hp) * p.Wo + wp) * p.Cout + cbase + g * 8;
+                    *reinterpret_cast<uint4*>(o) = acc;
+                }
+                named_bar_sync(1, kEpiThreads);
+            } else if (p.epi == SR_EPI_ACT_AVG) {
+                named_bar_sync(1, kEpiThreads);
+                const int imgs = 2 * p.TN;
+                const float* stg = reinterpret_cast<const float*>(smem);
+                for (int item = et; item < imgs * 32; item += kEpiThreads) {
+                    const int j = item & 31;
+                    const int img = item >> 5;
+                    const int n = n0 + img;
+                    if (n >= p.B) continue;
+                    const int sub = img >= p.TN ? 1 : 0;
+                    const int nloc = img - sub * p.TN;
+                    const float* src = stg + (size_t)(sub * kSubRows + nloc * hw_sub) * kStagePitchF32 + j;
+                    float acc = 0.f;
+                    for (int r = 0; r < hw_sub; ++r) acc += src[(size_t)r * kStagePitchF32];
+                    reinterpret_cast<float*>(p.out)[(size_t)n * p.Cout + cbase + j] = acc / (float)hw_sub;
+                }
+                named_bar_sync(1, kEpiThreads);
+            }
+        }
+
+        if (p.epi == SR_EPI_RAW_STATS) {
+            named_bar_sync(1, kEpiThreads);
+            for (int i = et; i < p.n_cta; i += kEpiThreads) {
+                atomicAdd(&p.stats[co0 + i], (double)s_sum[i]);
+                atomicAdd(&p.stats[p.Cout + co0 + i], (double)s_sq[i]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc_dyn(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+CUtensorMapSwizzle swizzle_for(int kc_bytes) {
+    return kc_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                           : (kc_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+struct Tile {
+    int TW, TH, TN, stack_h, tiles_w, tiles_h;
+};
+
+// Choose the TMA box (TW, TH, TN) of one 128-row sub-tile and how the CTA's two sub-tiles are stacked.
+bool pick_tile(int H, int W, int epi, Tile* out) {
+    const bool pooled = epi == SR_EPI_ACT_POOL2;
+    const bool avg = epi == SR_EPI_ACT_AVG;
+    const int Heff = pooled ? (H & ~1) : H;  // MaxPool2d(2) floors: an odd last row is never needed
+    long best_key = -1;
+    for (int tiles_w = 1; tiles_w <= W; ++tiles_w) {
+        if (W % tiles_w) continue;
+        const int TW = W / tiles_w;
+        if (TW > 128) continue;
+        if (pooled && tiles_w > 1 && (TW & 1)) continue;  // pooling windows must not straddle CTAs
+        if (avg && tiles_w != 1) continue;
+        for (int TH = 1; TH <= Heff && TW * TH <= 128; ++TH) {
+            if (avg && TH != H) continue;
+            for (int stack_h = 0; stack_h < 2; ++stack_h) {
+                int TN, th_cnt;
+                double util;
+                if (!stack_h) {  // the CTA's two sub-tiles are consecutive groups of TN images
+                    if (pooled && (TH & 1)) continue;
+                    TN = 128 / (TW * TH);
+                    th_cnt = (Heff + TH - 1) / TH;
+                    util = (double)(TW * TH * TN) / 128.0 * (double)Heff / (double)(TH * th_cnt);
+                } else {  // one image, the two sub-tiles are consecutive groups of TH rows
+                    if (avg) continue;
+                    TN = 1;
+                    th_cnt = (Heff + 2 * TH - 1) / (2 * TH);
+                    util = (double)(TW * TH) / 128.0 * (double)Heff / (double)(2 * TH * th_cnt);
+                }
+                // most useful UMMA rows first; ties: row stacking (halo locality), then taller boxes
+                const long key = (long)(util * 10000.0 + 0.5) * 1000 + stack_h * 500 + TH;
+                if (key > best_key) {
+                    best_key = key;
+                    *out = Tile{TW, TH, TN, stack_h, tiles_w, th_cnt};
+                }
+            }
+        }
+    }
+    return best_key >= 0;
+}
+
+int kc_bytes_for(int cin_pad) { return (cin_pad % 64 == 0) ? 128 : ((cin_pad % 32 == 0) ? 64 : 32); }
+
+}  // namespace
+
+extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (!a) return fail(SR_E_ARG, "sr_conv: null args");
+    if (a->n_panels < 1 || a->n_panels > 2) return fail(SR_E_ARG, "sr_conv: n_panels must be 1 or 2");
+    if (a->batch < 1 || a->height < 1 || a->width < 1) return fail(SR_E_ARG, "sr_conv: empty input");
+    if (a->epilogue < SR_EPI_ACT || a->epilogue > SR_EPI_RAW_STATS) return fail(SR_E_ARG, "sr_conv: bad epilogue");
+    if (a->epilogue == SR_EPI_RAW_STATS && !a->stats) return fail(SR_E_ARG, "sr_conv: RAW_STATS needs stats");
+    if (!a->out) return fail(SR_E_ARG, "sr_conv: null out");
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) return fail(SR_E_DEVICE, "sr_conv: cuTensorMapEncodeTiled not available from the driver");
+
+    // N split
+    int ns = 0;
+    for (int c = 1; c <= 16; ++c) {
+        if (a->cout % c) continue;
+        const int n = a->cout / c;
+        if (n % 32 == 0 && n <= 256) {
+            ns = c;
+            break;
+        }
+    }
+    if (!ns) return fail(SR_E_ARG, "sr_conv: cout=%d cannot be split into multiples of 32 <= 256", a->cout);
+
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    Tile tile;
+    if (!pick_tile(a->height, a->width, a->epilogue, &tile))
+        return fail(SR_E_ARG, "sr_conv: no tile for %dx%d epilogue %d", a->height, a->width, a->epilogue);
+    p.n_panels = a->n_panels;
+    p.B = a->batch;
+    p.H = a->height;
+    p.W = a->width;
+    p.Cout = a->cout;
+    p.TW = tile.TW;
+    p.TH = tile.TH;
+    p.TN = tile.TN;
+    p.stack_h = tile.stack_h;
+    p.tiles_w = tile.tiles_w;
+    p.tiles_h = tile.tiles_h;
+    p.n_cta = a->cout / ns;
+    p.rows_sub = tile.TW * tile.TH * tile.TN;
+    p.epi = a->epilogue;
+    p.slope = a->slope;
+    p.Ho = a->epilogue == SR_EPI_ACT_POOL2 ? a->height / 2 : a->height;
+    p.Wo = a->epilogue == SR_EPI_ACT_POOL2 ? a->width / 2 : a->width;
+    p.shift = a->shift;
+    p.residual = static_cast<const __nv_bfloat16*>(a->residual);
+    p.out = a->out;
+    p.stats = a->stats;
+    int tm = 32;
+    while (tm < 2 * p.n_cta) tm <<= 1;
+    if (tm > 512) return fail(SR_E_ARG, "sr_conv: accumulators need %d TMEM columns", tm);
+    p.tmem_cols = tm;
+
+    int kc_max = 0;
+    for (int i = 0; i < a->n_panels; ++i) {
+        const sr_conv_panel& sp = a->panel[i];
+        if (!sp.act || !sp.wgt) return fail(SR_E_ARG, "sr_conv: null panel pointer");
+        if (sp.cin_pad < 16 || sp.cin_pad % 16) return fail(SR_E_ARG, "sr_conv: cin_pad must be a multiple of 16");
+        if (sp.taps != 9 && sp.taps != 1) return fail(SR_E_ARG, "sr_conv: taps must be 9 or 1");
+        if ((reinterpret_cast<uintptr_t>(sp.act) | reinterpret_cast<uintptr_t>(sp.wgt)) & 15)
+            return fail(SR_E_ARG, "sr_conv: operand pointers must be 16-byte aligned");
+        PanelDev& pd = p.panel[i];
+        pd.taps = sp.taps;
+        pd.cin_pad = sp.cin_pad;
+        pd.kc_bytes = kc_bytes_for(sp.cin_pad);
+        pd.ncb = sp.cin_pad * 2 / pd.kc_bytes;
+        kc_max = std::max(kc_max, pd.kc_bytes);
+        const int kc = pd.kc_bytes / 2;
+        {
+            cuuint64_t gdim[4] = {(cuuint64_t)sp.cin_pad, (cuuint64_t)a->width, (cuuint64_t)a->height, (cuuint64_t)a->batch};
+            cuuint64_t gstr[3] = {(cuuint64_t)sp.cin_pad * 2, (cuuint64_t)sp.cin_pad * 2 * a->width,
+                                  (cuuint64_t)sp.cin_pad * 2 * a->width * a->height};
+            cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)tile.TW, (cuuint32_t)tile.TH, (cuuint32_t)tile.TN};
+            cuuint32_t est[4] = {1, 1, 1, 1};
+            CUresult r = encode(&pd.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(sp.act), gdim, gstr, box,
+                                est, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(pd.kc_bytes),
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(SR_E_CUDA, "sr_conv: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+        }
+        {
+            cuuint64_t gdim[2] = {(cuuint64_t)sp.taps * sp.cin_pad, (cuuint64_t)a->cout};
+            cuuint64_t gstr[1] = {(cuuint64_t)sp.taps * sp.cin_pad * 2};
+            cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)p.n_cta};
+            cuuint32_t est[2] = {1, 1};
+            CUresult r = encode(&pd.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(sp.wgt), gdim, gstr, box,
+                                est, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(pd.kc_bytes),
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(SR_E_CUDA, "sr_conv: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+        }
+    }
+    p.a_slot = kSubRows * kc_max;
+    const int b_slot = (int)align_up((int64_t)p.n_cta * kc_max, 1024);
+    p.stage_bytes = 2 * p.a_slot + b_slot;
+    p.stages = std::min(12, (200 * 1024) / p.stage_bytes);
+    if (p.stages < 2) return fail(SR_E_ARG, "sr_conv: pipeline does not fit in shared memory");
+    const int staging = 2 * kSubRows * std::max(kStagePitchBf16, kStagePitchF32 * 4);
+    const int dyn_smem = std::max(p.stages * p.stage_bytes, staging) + 1024;
+
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_err != cudaSuccess)
+        return fail(SR_E_CUDA, "sr_conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+
+    const int tiles_n = tile.stack_h ? a->batch : (a->batch + 2 * tile.TN - 1) / (2 * tile.TN);
+    dim3 grid((unsigned)(tile.tiles_w * tile.tiles_h * tiles_n), (unsigned)ns, 1);
+    conv_umma_kernel<<<grid, kThreads, dyn_smem, stream>>>(p);
+    SR_CUDA_OK(cudaGetLastError());
+    return SR_OK;
+}

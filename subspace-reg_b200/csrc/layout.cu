@@ -1,0 +1,273 @@
+// Data-layout and train-mode BatchNorm kernels around the tcgen05 convolution (HBM-bound elementwise work:
+// coalesced 128-bit accesses, grids sized from the element count).
+#include <cuda_bf16.h>
+#include "common.h"
+
+namespace {
+
+using namespace srb;
+
+__device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
+
+// ---- NCHW fp32 -> NHWC bf16, channels zero-padded to cpad ----------------------------------------------------
+__global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t npix_total,
+                                  int C, int HW, int cpad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // pixel index over (n, h, w)
+    if (i >= npix_total) return;
+    const int64_t n = i / HW;
+    const int64_t hw = i - n * HW;
+    const float* src = x + n * C * HW + hw;
+    __nv_bfloat16* dst = y + i * cpad;
+    for (int c0 = 0; c0 < cpad; c0 += 8) {
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            v[j] = __float2bfloat16_rn(c < C ? src[(int64_t)c * HW] : 0.f);
+        }
+        *reinterpret_cast<uint4*>(dst + c0) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
+__global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                               float* scale, float* shift, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float s = gamma[c] / sqrtf(rv[c] + eps);
+    scale[c] = s;
+    shift[c] = beta[c] - rm[c] * s;
+}
+
+// ---- OIHW fp32 -> [cout][taps][cin_pad] bf16 (optionally scaled per output channel) ---------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
+                                   __nv_bfloat16* __restrict__ out, int cout, int cin, int taps, int cin_pad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)cout * taps * cin_pad;
+    if (i >= total) return;
+    const int ci = (int)(i % cin_pad);
+    const int tap = (int)((i / cin_pad) % taps);
+    const int co = (int)(i / ((int64_t)cin_pad * taps));
+    float v = 0.f;
+    if (ci < cin) {
+        v = w[((int64_t)co * cin + ci) * taps + tap];
+        if (scale) v *= scale[co];
+    }
+    out[i] = __float2bfloat16_rn(v);
+}
+
+// ---- train-mode BN statistics -> mean / invstd, running-stat EMA ---------------------------------------------
+__global__ void bn_finalize_kernel(const double* stats, double count, float eps, float momentum, float* rm, float* rv,
+                                   float* mean, float* invstd, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mu = stats[c] / count;
+    double var = stats[C + c] / count - mu * mu;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)mu;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    rm[c] = momentum * (float)mu + (1.f - momentum) * rm[c];
+    rv[c] = momentum * (float)unbiased + (1.f - momentum) * rv[c];
+}
+
+struct BnApplyParams {
+    sr_bn_apply_args a;
+    int Ho, Wo;
+};
+
+__device__ __forceinline__ void load8(const float* p, float* v) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// y = lrelu(bn(raw) [+ bn(res_raw) | + res_act]) at one pixel, 8 consecutive channels starting at c0.
+__device__ __forceinline__ void bn_pixel(const sr_bn_apply_args& a, int64_t pix, int c0, const float* al, const float* be,
+                                         const float* ral, const float* rbe, float* y) {
+    float x[8];
+    load8(a.raw + pix * a.channels + c0, x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) y[j] = x[j] * al[j] + be[j];
+    if (a.res_raw) {
+        load8(a.res_raw + pix * a.channels + c0, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] += x[j] * ral[j] + rbe[j];
+    } else if (a.res_act) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.res_act) +
+                                                              pix * a.channels + c0));
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[k]);
+            y[2 * k] += __bfloat162float(b2.x);
+            y[2 * k + 1] += __bfloat162float(b2.y);
+        }
+    }
+    if (a.lrelu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = lrelu(y[j], a.slope);
+    }
+}
+
+__device__ __forceinline__ void bn_coeffs(const float* mean, const float* invstd, const float* gamma, const float* beta,
+                                          int c0, float* al, float* be) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float s = invstd[c0 + j] * gamma[c0 + j];
+        al[j] = s;
+        be[j] = beta[c0 + j] - mean[c0 + j] * s;
+    }
+}
+
+// pool 0 / 2: one thread per (n, ho, wo, 8-channel group) -> bf16 NHWC
+__global__ void bn_apply_kernel(const BnApplyParams p) {
+    const sr_bn_apply_args& a = p.a;
+    const int cg = a.channels >> 3;
+    const int64_t total = (int64_t)a.batch * p.Ho * p.Wo * cg;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % cg);
+    int64_t r = i / cg;
+    const int wo = (int)(r % p.Wo);
+    r /= p.Wo;
+    const int ho = (int)(r % p.Ho);
+    const int n = (int)(r / p.Ho);
+    const int c0 = g * 8;
+    float al[8], be[8], ral[8], rbe[8];
+    bn_coeffs(a.mean, a.invstd, a.gamma, a.beta, c0, al, be);
+    if (a.res_raw) bn_coeffs(a.res_mean, a.res_invstd, a.res_gamma, a.res_beta, c0, ral, rbe);
+    float y[8];
+    if (a.pool == 2) {
+        float t[8];
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const int64_t pix = ((int64_t)n * a.height + (2 * ho + dy)) * a.width + (2 * wo + dx);
+                bn_pixel(a, pix, c0, al, be, ral, rbe, t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y[j] = (dy == 0 && dx == 0) ? t[j] : fmaxf(y[j], t[j]);
+            }
+    } else {
+        const int64_t pix = ((int64_t)n * a.height + ho) * a.width + wo;
+        bn_pixel(a, pix, c0, al, be, ral, rbe, y);
+    }
+    if (a.keep) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint8_t k = a.keep[(((int64_t)n * a.channels + c0 + j) * p.Ho + ho) * p.Wo + wo];
+            y[j] = k ? y[j] * a.keep_scale : 0.f;
+        }
+    }
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(y[j]);
+    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out) + (((int64_t)n * p.Ho + ho) * p.Wo + wo) * a.channels + c0) =
+        *reinterpret_cast<const uint4*>(o);
+}
+
+// pool -1: one thread per (n, 8-channel group): mask, then mean over H x W -> fp32 [B, C]
+__global__ void bn_apply_avg_kernel(const BnApplyParams p) {
+    const sr_bn_apply_args& a = p.a;
+    const int cg = a.channels >> 3;
+    const int64_t total = (int64_t)a.batch * cg;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int g = (int)(i % cg);
+    const int n = (int)(i / cg);
+    const int c0 = g * 8;
+    float al[8], be[8], ral[8], rbe[8];
+    bn_coeffs(a.mean, a.invstd, a.gamma, a.beta, c0, al, be);
+    if (a.res_raw) bn_coeffs(a.res_mean, a.res_invstd, a.res_gamma, a.res_beta, c0, ral, rbe);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int HW = a.height * a.width;
+    for (int q = 0; q < HW; ++q) {
+        float y[8];
+        bn_pixel(a, (int64_t)n * HW + q, c0, al, be, ral, rbe, y);
+        if (a.keep) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint8_t k = a.keep[((int64_t)n * a.channels + c0 + j) * HW + q];
+                y[j] = k ? y[j] * a.keep_scale : 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += y[j];
+    }
+    float* o = static_cast<float*>(a.out) + (int64_t)n * a.channels + c0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = acc[j] / (float)HW;
+}
+
+}  // namespace
+
+extern "C" int32_t sr_pack_input(const float* x, void* y, int32_t batch, int32_t channels, int32_t height, int32_t width,
+                                 int32_t cpad, void* stream_v) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (!x || !y || batch < 1 || channels < 1 || cpad < channels || cpad % 8)
+        return fail(SR_E_ARG, "sr_pack_input: bad arguments");
+    const int64_t npix = (int64_t)batch * height * width;
+    const int threads = 256;
+    pack_input_kernel<<<(unsigned)((npix + threads - 1) / threads), threads, 0, stream>>>(
+        x, static_cast<__nv_bfloat16*>(y), npix, channels, height * width, cpad);
+    SR_CUDA_OK(cudaGetLastError());
+    return SR_OK;
+}
+
+extern "C" int32_t sr_bn_fold(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                              float* scale, float* shift, int32_t channels, void* stream_v) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (!gamma || !beta || !rm || !rv || !scale || !shift || channels < 1) return fail(SR_E_ARG, "sr_bn_fold: bad arguments");
+    bn_fold_kernel<<<(channels + 127) / 128, 128, 0, stream>>>(gamma, beta, rm, rv, eps, scale, shift, channels);
+    SR_CUDA_OK(cudaGetLastError());
+    return SR_OK;
+}
+
+extern "C" int32_t sr_pack_weight(const float* w, const float* scale, void* out, int32_t cout, int32_t cin, int32_t kh,
+                                  int32_t kw, int32_t cin_pad, void* stream_v) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (!w || !out || cout < 1 || cin < 1 || cin_pad < cin || kh != kw || (kh != 1 && kh != 3))
+        return fail(SR_E_ARG, "sr_pack_weight: bad arguments");
+    const int64_t total = (int64_t)cout * kh * kw * cin_pad;
+    const int threads = 256;
+    pack_weight_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
+        w, scale, static_cast<__nv_bfloat16*>(out), cout, cin, kh * kw, cin_pad);
+    SR_CUDA_OK(cudaGetLastError());
+    return SR_OK;
+}
+
+extern "C" int32_t sr_bn_finalize(const double* stats, int64_t count, float eps, float momentum, float* rm, float* rv,
+                                  float* mean, float* invstd, int32_t channels, void* stream_v) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (!stats || !rm || !rv || !mean || !invstd || channels < 1 || count < 1)
+        return fail(SR_E_ARG, "sr_bn_finalize: bad arguments");
+    bn_finalize_kernel<<<(channels + 127) / 128, 128, 0, stream>>>(stats, (double)count, eps, momentum, rm, rv, mean,
+                                                                    invstd, channels);
+    SR_CUDA_OK(cudaGetLastError());
+    return SR_OK;
+}
+
+extern "C" int32_t sr_bn_apply(const sr_bn_apply_args* a, void* stream_v) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (!a || !a->raw || !a->mean || !a->invstd || !a->gamma || !a->beta || !a->out)
+        return fail(SR_E_ARG, "sr_bn_apply: null pointer");
+    if (a->channels % 8) return fail(SR_E_ARG, "sr_bn_apply: channels must be a multiple of 8");
+    if (a->pool != 0 && a->pool != 2 && a->pool != -1) return fail(SR_E_ARG, "sr_bn_apply: pool must be 0, 2 or -1");
+    if (a->res_raw && (!a->res_mean || !a->res_invstd || !a->res_gamma || !a->res_beta))
+        return fail(SR_E_ARG, "sr_bn_apply: res_raw needs its BN parameters");
+    BnApplyParams p;
+    p.a = *a;
+    p.Ho = a->pool == 2 ? a->height / 2 : a->height;
+    p.Wo = a->pool == 2 ? a->width / 2 : a->width;
+    const int threads = 256;
+    if (a->pool == -1) {
+        const int64_t total = (int64_t)a->batch * (a->channels / 8);
+        bn_apply_avg_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(p);
+    } else {
+        const int64_t total = (int64_t)a->batch * p.Ho * p.Wo * (a->channels / 8);
+        bn_apply_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(p);
+    }
+    SR_CUDA_OK(cudaGetLastError());
+    return SR_OK;
+}

@@ -1,0 +1,122 @@
+"""ctypes binding of libsrb200.so (the C ABI declared in include/srb200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` / ``csrc/Makefile``.  There is no
+fallback: if the library is missing, or the device is not sm_100, every op raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsrb200.so")
+
+SR_EPI_ACT, SR_EPI_ACT_POOL2, SR_EPI_ACT_AVG, SR_EPI_RAW_STATS = 0, 1, 2, 3
+SR_PULL_NONE, SR_PULL_FIXED, SR_PULL_PROJECT = 0, 1, 2
+SR_OPT_SGD, SR_OPT_ADAM = 0, 1
+SR_TRACE_COLS = 8
+
+EXPORTS = [
+    "sr_last_error", "sr_version", "sr_check_device", "sr_pack_input", "sr_bn_fold", "sr_pack_weight", "sr_conv",
+    "sr_bn_finalize", "sr_bn_apply", "sr_subspace_factor_workspace_bytes", "sr_subspace_factor",
+    "sr_head_workspace_bytes", "sr_head_run", "sr_eval_logits",
+]
+
+
+class ConvPanel(C.Structure):
+    _fields_ = [("act", C.c_void_p), ("wgt", C.c_void_p), ("cin_pad", C.c_int32), ("taps", C.c_int32)]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("cout", C.c_int32),
+        ("n_panels", C.c_int32), ("panel", ConvPanel * 2),
+        ("shift", C.c_void_p), ("residual", C.c_void_p), ("slope", C.c_float), ("epilogue", C.c_int32),
+        ("out", C.c_void_p), ("stats", C.c_void_p),
+    ]
+
+
+class BnApplyArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("channels", C.c_int32),
+        ("raw", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("res_raw", C.c_void_p), ("res_mean", C.c_void_p), ("res_invstd", C.c_void_p), ("res_gamma", C.c_void_p),
+        ("res_beta", C.c_void_p), ("res_act", C.c_void_p), ("lrelu", C.c_int32), ("slope", C.c_float),
+        ("pool", C.c_int32), ("keep", C.c_void_p), ("keep_scale", C.c_float), ("out", C.c_void_p),
+    ]
+
+
+class HeadArgs(C.Structure):
+    _fields_ = [
+        ("feat", C.c_void_p), ("dim", C.c_int32), ("n_support", C.c_int32), ("support_row0", C.c_int32),
+        ("n_memory", C.c_int32), ("memory_row0", C.c_int32), ("labels_support", C.c_void_p),
+        ("labels_memory", C.c_void_p), ("weight", C.c_void_p), ("n_classes", C.c_int32), ("opt_state", C.c_void_p),
+        ("base_weight", C.c_void_p), ("n_base", C.c_int32), ("reserve_weight", C.c_void_p),
+        ("n_prev_novel", C.c_int32), ("n_new", C.c_int32), ("pull_mode", C.c_int32), ("pull", C.c_void_p),
+        ("q_rows", C.c_int32), ("lmbd_base", C.c_float), ("lmbd_novel", C.c_float), ("gamma", C.c_float),
+        ("optimizer", C.c_int32), ("lr", C.c_float), ("momentum", C.c_float), ("weight_decay", C.c_float),
+        ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float), ("step0", C.c_int32),
+        ("max_epochs", C.c_int32), ("epoch0", C.c_int32), ("stable", C.c_int32), ("stable_epochs", C.c_int32),
+        ("stable_count0", C.c_int32), ("min_novel_epochs", C.c_int32), ("max_novel_epochs", C.c_int32),
+        ("convergence_epsilon", C.c_double), ("target_train_loss", C.c_double), ("prev_loss", C.c_float),
+        ("loss_trace", C.c_void_p), ("status", C.c_void_p), ("logits_support", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+    ]
+
+
+class EvalArgs(C.Structure):
+    _fields_ = [
+        ("feat", C.c_void_p), ("weight", C.c_void_p), ("labels", C.c_void_p),
+        ("n", C.c_int32), ("dim", C.c_int32), ("n_classes", C.c_int32),
+        ("logits", C.c_void_p), ("pred", C.c_void_p), ("counts", C.c_void_p), ("loss_sum", C.c_void_p),
+        ("confusion", C.c_void_p), ("conf_dim", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """dlopen libsrb200.so (once) and declare signatures.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "srb200: %s is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU / PyTorch fallback for this path)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    lib.sr_last_error.restype = C.c_char_p
+    lib.sr_last_error.argtypes = []
+    lib.sr_version.restype = i32
+    lib.sr_check_device.restype = i32
+    lib.sr_check_device.argtypes = [i32]
+    lib.sr_pack_input.restype = i32
+    lib.sr_pack_input.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.sr_bn_fold.restype = i32
+    lib.sr_bn_fold.argtypes = [vp, vp, vp, vp, f32, vp, vp, i32, vp]
+    lib.sr_pack_weight.restype = i32
+    lib.sr_pack_weight.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.sr_conv.restype = i32
+    lib.sr_conv.argtypes = [C.POINTER(ConvArgs), vp]
+    lib.sr_bn_finalize.restype = i32
+    lib.sr_bn_finalize.argtypes = [vp, i64, f32, f32, vp, vp, vp, vp, i32, vp]
+    lib.sr_bn_apply.restype = i32
+    lib.sr_bn_apply.argtypes = [C.POINTER(BnApplyArgs), vp]
+    lib.sr_subspace_factor_workspace_bytes.restype = i64
+    lib.sr_subspace_factor_workspace_bytes.argtypes = [i32, i32]
+    lib.sr_subspace_factor.restype = i32
+    lib.sr_subspace_factor.argtypes = [vp, i32, i32, vp, vp, vp, i64, vp]
+    lib.sr_head_workspace_bytes.restype = i64
+    lib.sr_head_workspace_bytes.argtypes = [C.POINTER(HeadArgs)]
+    lib.sr_head_run.restype = i32
+    lib.sr_head_run.argtypes = [C.POINTER(HeadArgs), vp]
+    lib.sr_eval_logits.restype = i32
+    lib.sr_eval_logits.argtypes = [C.POINTER(EvalArgs), vp]
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().sr_last_error()
+        raise RuntimeError("srb200 %s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))

@@ -1,0 +1,259 @@
+"""Torch-tensor front end of the srb200 C ABI.
+
+PyTorch is used here for device memory and streams only: every function checks its tensors (CUDA, contiguous,
+dtype), passes raw pointers + the current stream to libsrb200.so and returns torch tensors that own the outputs.
+No function in this module has a CPU or PyTorch-op fallback.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_checked_devices = set()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype=None, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("srb200: %s must be a CUDA tensor (no CPU fallback)" % name)
+    if not t.is_contiguous():
+        raise RuntimeError("srb200: %s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("srb200: %s must be %s, got %s" % (name, dtype, t.dtype))
+    dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if dev not in _checked_devices:
+        L.check(L.load().sr_check_device(dev), "sr_check_device")
+        _checked_devices.add(dev)
+    return C.c_void_p(t.data_ptr())
+
+
+def pack_input(x_nchw, cpad=16):
+    """NCHW fp32 -> NHWC bf16 with channels zero-padded to cpad."""
+    B, Cc, H, W = x_nchw.shape
+    y = torch.empty((B, H, W, cpad), dtype=torch.bfloat16, device=x_nchw.device)
+    rc = L.load().sr_pack_input(_ptr(x_nchw, torch.float32, "x"), _ptr(y), B, Cc, H, W, cpad, _stream())
+    L.check(rc, "sr_pack_input")
+    return y
+
+
+def bn_fold(gamma, beta, running_mean, running_var, eps=1e-5):
+    Cc = gamma.numel()
+    scale = torch.empty(Cc, dtype=torch.float32, device=gamma.device)
+    shift = torch.empty_like(scale)
+    rc = L.load().sr_bn_fold(_ptr(gamma, torch.float32), _ptr(beta, torch.float32), _ptr(running_mean, torch.float32),
+                             _ptr(running_var, torch.float32), eps, _ptr(scale), _ptr(shift), Cc, _stream())
+    L.check(rc, "sr_bn_fold")
+    return scale, shift
+
+
+def pack_weight(w_oihw, scale=None, cin_pad=None, out=None):
+    """OIHW fp32 -> bf16 [cout, kh*kw, cin_pad] (optionally scaled per output channel)."""
+    co, ci, kh, kw = w_oihw.shape
+    if cin_pad is None:
+        cin_pad = (ci + 15) // 16 * 16
+    if out is None:
+        out = torch.empty((co, kh * kw, cin_pad), dtype=torch.bfloat16, device=w_oihw.device)
+    rc = L.load().sr_pack_weight(_ptr(w_oihw, torch.float32, "w"), _ptr(scale, torch.float32, "scale"), _ptr(out), co, ci,
+                                 kh, kw, cin_pad, _stream())
+    L.check(rc, "sr_pack_weight")
+    return out
+
+
+def conv(panels, cout, shift=None, residual=None, slope=0.1, epilogue=L.SR_EPI_ACT, stats=None, out=None):
+    """panels: list of (act NHWC bf16 [B,H,W,cin_pad], packed weight bf16 [cout,taps,cin_pad])."""
+    act0 = panels[0][0]
+    B, H, W, _ = act0.shape
+    a = L.ConvArgs()
+    a.batch, a.height, a.width, a.cout = B, H, W, cout
+    a.n_panels = len(panels)
+    for i, (act, wgt) in enumerate(panels):
+        if act.shape[:3] != act0.shape[:3]:
+            raise RuntimeError("srb200: conv panels must share batch and spatial size")
+        if wgt.shape[0] != cout or wgt.shape[2] != act.shape[3]:
+            raise RuntimeError("srb200: packed weight %s does not match activation %s / cout %d" %
+                               (tuple(wgt.shape), tuple(act.shape), cout))
+        a.panel[i].act = _ptr(act, torch.bfloat16, "act")
+        a.panel[i].wgt = _ptr(wgt, torch.bfloat16, "wgt")
+        a.panel[i].cin_pad = act.shape[3]
+        a.panel[i].taps = wgt.shape[1]
+    a.shift = _ptr(shift, torch.float32, "shift")
+    a.residual = _ptr(residual, torch.bfloat16, "residual")
+    if residual is not None and tuple(residual.shape) != (B, H, W, cout):
+        raise RuntimeError("srb200: residual shape mismatch")
+    a.slope = slope
+    a.epilogue = epilogue
+    dev = act0.device
+    if out is None:
+        if epilogue == L.SR_EPI_ACT:
+            out = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=dev)
+        elif epilogue == L.SR_EPI_ACT_POOL2:
+            out = torch.empty((B, H // 2, W // 2, cout), dtype=torch.bfloat16, device=dev)
+        elif epilogue == L.SR_EPI_ACT_AVG:
+            out = torch.empty((B, cout), dtype=torch.float32, device=dev)
+        else:
+            out = torch.empty((B, H, W, cout), dtype=torch.float32, device=dev)
+    a.out = _ptr(out)
+    a.stats = _ptr(stats, torch.float64, "stats")
+    L.check(L.load().sr_conv(C.byref(a), _stream()), "sr_conv")
+    return out
+
+
+def bn_finalize(stats, count, running_mean, running_var, eps=1e-5, momentum=0.1):
+    Cc = running_mean.numel()
+    mean = torch.empty(Cc, dtype=torch.float32, device=stats.device)
+    invstd = torch.empty_like(mean)
+    rc = L.load().sr_bn_finalize(_ptr(stats, torch.float64), int(count), eps, momentum,
+                                 _ptr(running_mean, torch.float32), _ptr(running_var, torch.float32), _ptr(mean),
+                                 _ptr(invstd), Cc, _stream())
+    L.check(rc, "sr_bn_finalize")
+    return mean, invstd
+
+
+def bn_apply(raw, mean, invstd, gamma, beta, res_raw=None, res_bn=None, res_act=None, lrelu=True, slope=0.1, pool=0,
+             keep=None, keep_scale=1.0):
+    B, H, W, Cc = raw.shape
+    a = L.BnApplyArgs()
+    a.batch, a.height, a.width, a.channels = B, H, W, Cc
+    a.raw = _ptr(raw, torch.float32, "raw")
+    a.mean, a.invstd = _ptr(mean, torch.float32), _ptr(invstd, torch.float32)
+    a.gamma, a.beta = _ptr(gamma, torch.float32), _ptr(beta, torch.float32)
+    if res_raw is not None:
+        a.res_raw = _ptr(res_raw, torch.float32, "res_raw")
+        rm, ri, rg, rb = res_bn
+        a.res_mean, a.res_invstd = _ptr(rm, torch.float32), _ptr(ri, torch.float32)
+        a.res_gamma, a.res_beta = _ptr(rg, torch.float32), _ptr(rb, torch.float32)
+    a.res_act = _ptr(res_act, torch.bfloat16, "res_act")
+    a.lrelu = 1 if lrelu else 0
+    a.slope = slope
+    a.pool = pool
+    a.keep = _ptr(keep, torch.uint8, "keep")
+    a.keep_scale = keep_scale
+    if pool == -1:
+        out = torch.empty((B, Cc), dtype=torch.float32, device=raw.device)
+    elif pool == 2:
+        out = torch.empty((B, H // 2, W // 2, Cc), dtype=torch.bfloat16, device=raw.device)
+    else:
+        out = torch.empty((B, H, W, Cc), dtype=torch.bfloat16, device=raw.device)
+    a.out = _ptr(out)
+    L.check(L.load().sr_bn_apply(C.byref(a), _stream()), "sr_bn_apply")
+    return out
+
+
+def subspace_factor(base_weight):
+    """Orthonormal row basis Qt of span(rows of base_weight) -> (qt [q_rows, dim], q_rows, is_identity).
+
+    Replaces torch.qr(base_weight.T) of LangPuller.get_projected_weight (reference resnet_language.py:92-97)."""
+    n, d = base_weight.shape
+    lib = L.load()
+    ws_bytes = lib.sr_subspace_factor_workspace_bytes(n, d)
+    ws = torch.empty(max(int(ws_bytes), 256), dtype=torch.uint8, device=base_weight.device)
+    q = min(n, d)
+    qt = torch.zeros((q, d), dtype=torch.float32, device=base_weight.device)
+    info = torch.zeros(4, dtype=torch.int32, device=base_weight.device)
+    rc = lib.sr_subspace_factor(_ptr(base_weight, torch.float32, "base_weight"), n, d, _ptr(qt), _ptr(info), _ptr(ws),
+                                ws.numel(), _stream())
+    L.check(rc, "sr_subspace_factor")
+    info_h = info.cpu().tolist()
+    if info_h[2] != 0:
+        raise RuntimeError("srb200: base weights are rank deficient (Cholesky pivot %d <= 0)" % (info_h[2] - 1))
+    return qt, info_h[0], bool(info_h[1])
+
+
+class HeadSession(object):
+    """Device state of one session's fine-tuning (weight, optimiser state, counters) around sr_head_run."""
+
+    def __init__(self, feat, n_support, support_row0, labels_support, weight, n_base, n_new, *, n_memory=0,
+                 memory_row0=0, labels_memory=None, base_weight=None, reserve_weight=None, pull_mode=L.SR_PULL_NONE,
+                 pull=None, q_rows=0, lmbd_base=0.0, lmbd_novel=0.0, gamma=0.0, adam=False, lr=0.002, momentum=0.9,
+                 weight_decay=5e-4, stable=True, convergence_epsilon=1e-4, stable_epochs=10, target_train_loss=0.0,
+                 min_novel_epochs=20, max_novel_epochs=1000, want_logits=False):
+        dev = feat.device
+        self.feat, self.weight = feat, weight
+        self.labels_support, self.labels_memory = labels_support, labels_memory
+        self.base_weight, self.reserve_weight, self.pull = base_weight, reserve_weight, pull
+        Cn, d = weight.shape
+        self.opt_state = torch.zeros((2 if adam else 1, Cn, d), dtype=torch.float32, device=dev)
+        self.status = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.logits = torch.empty((n_support, Cn), dtype=torch.float32, device=dev) if want_logits else None
+        a = L.HeadArgs()
+        a.feat, a.dim = _ptr(feat, torch.float32, "feat"), d
+        a.n_support, a.support_row0 = n_support, support_row0
+        a.n_memory, a.memory_row0 = n_memory, memory_row0
+        a.labels_support = _ptr(labels_support, torch.int64, "labels_support")
+        a.labels_memory = _ptr(labels_memory, torch.int64, "labels_memory")
+        a.weight, a.n_classes = _ptr(weight, torch.float32, "weight"), Cn
+        a.opt_state = _ptr(self.opt_state)
+        a.base_weight, a.n_base = _ptr(base_weight, torch.float32, "base_weight"), n_base
+        a.reserve_weight = _ptr(reserve_weight, torch.float32, "reserve_weight")
+        a.n_prev_novel = 0 if reserve_weight is None else reserve_weight.shape[0]
+        a.n_new, a.pull_mode, a.pull, a.q_rows = n_new, pull_mode, _ptr(pull, torch.float32, "pull"), q_rows
+        a.lmbd_base, a.lmbd_novel, a.gamma = lmbd_base, lmbd_novel, gamma
+        a.optimizer = L.SR_OPT_ADAM if adam else L.SR_OPT_SGD
+        a.lr, a.momentum, a.weight_decay = lr, momentum, weight_decay
+        a.beta1, a.beta2, a.adam_eps = 0.9, 0.999, 1e-8
+        a.stable, a.stable_epochs = (1 if stable else 0), stable_epochs
+        a.min_novel_epochs, a.max_novel_epochs = min_novel_epochs, max_novel_epochs
+        a.convergence_epsilon, a.target_train_loss = convergence_epsilon, target_train_loss
+        a.status = _ptr(self.status)
+        a.logits_support = _ptr(self.logits)
+        ws_bytes = int(L.load().sr_head_workspace_bytes(C.byref(a)))
+        self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        a.workspace, a.workspace_bytes = _ptr(self.workspace), ws_bytes
+        self.args = a
+        self.epochs = 0
+        self.stable_count = 0
+        self.prev_loss = 15.0  # language_eval.py:234
+        self.stopped = False
+        self.traces = []
+
+    def run(self, max_epochs):
+        """Run up to max_epochs more epochs on the device; returns the [epochs, SR_TRACE_COLS] trace (host)."""
+        a = self.args
+        trace = torch.zeros((max_epochs, L.SR_TRACE_COLS), dtype=torch.float32, device=self.feat.device)
+        a.loss_trace = _ptr(trace)
+        a.max_epochs, a.epoch0, a.step0 = max_epochs, self.epochs, self.epochs
+        a.stable_count0, a.prev_loss = self.stable_count, self.prev_loss
+        L.check(L.load().sr_head_run(C.byref(a), _stream()), "sr_head_run")
+        st = self.status.cpu().tolist()  # the one host sync per call
+        if st[3] != 0:
+            raise RuntimeError("srb200: head kernel reported a grid-barrier timeout")
+        n = st[0]
+        tr = trace[:n].cpu()
+        self.epochs += n
+        self.stopped = bool(st[1])
+        self.stable_count = st[2]
+        if n > 0:
+            self.prev_loss = float(tr[-1, 0])
+        self.traces.append(tr)
+        return tr
+
+    def run_to_convergence(self, chunk=1 << 20):
+        while not self.stopped:
+            self.run(min(chunk, max(self.args.max_novel_epochs - self.epochs, 1)))
+        return torch.cat(self.traces, 0)
+
+
+def eval_logits(feat, weight, labels, confusion=None):
+    """-> dict(logits, pred, top1, top5, loss_sum) for rows of feat scored against weight."""
+    n, d = feat.shape
+    Cn = weight.shape[0]
+    dev = feat.device
+    logits = torch.empty((n, Cn), dtype=torch.float32, device=dev)
+    pred = torch.empty(n, dtype=torch.int32, device=dev)
+    counts = torch.zeros(2, dtype=torch.int32, device=dev)
+    loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+    a = L.EvalArgs()
+    a.feat, a.weight = _ptr(feat, torch.float32, "feat"), _ptr(weight, torch.float32, "weight")
+    a.labels = _ptr(labels, torch.int64, "labels")
+    a.n, a.dim, a.n_classes = n, d, Cn
+    a.logits, a.pred, a.counts, a.loss_sum = _ptr(logits), _ptr(pred), _ptr(counts), _ptr(loss_sum)
+    a.confusion = _ptr(confusion, torch.int64, "confusion")
+    a.conf_dim = 0 if confusion is None else confusion.shape[0]
+    L.check(L.load().sr_eval_logits(C.byref(a), _stream()), "sr_eval_logits")
+    return {"logits": logits, "pred": pred, "counts": counts, "loss_sum": loss_sum}
