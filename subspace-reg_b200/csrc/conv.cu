@@ -548,11 +548,17 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
 
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
+    static int max_dyn = 0;
     std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncAttributes fa;
+        attr_err = cudaFuncGetAttributes(&fa, conv_umma_kernel);
+        if (attr_err != cudaSuccess) return;
+        max_dyn = 227 * 1024 - (int)fa.sharedSizeBytes;  // static + dynamic <= 227 KB per CTA
+        attr_err = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
     });
     if (attr_err != cudaSuccess)
         return fail(SR_E_CUDA, "sr_conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+    if (dyn_smem > max_dyn) return fail(SR_E_ARG, "sr_conv: needs %d bytes of shared memory (> %d)", dyn_smem, max_dyn);
 
     const int tiles_n = tile.stack_h ? a->batch : (a->batch + 2 * tile.TN - 1) / (2 * tile.TN);
     dim3 grid((unsigned)(tile.tiles_w * tile.tiles_h * tiles_n), (unsigned)ns, 1);
