@@ -102,7 +102,7 @@ def make_world(seed=1, n_sessions=8, n_base_batch=1000, opt=None, **opt_over):
     # fixed base exemplars: one per base class, labels 0..59 (language_eval.py:112-116)
     bs_x = _images(gen, means, base)
     bs_y = torch.arange(len(base), dtype=torch.int64)
-    dummy = torch.zeros((1, 1, 3, 1, 1))
+    dummy = torch.zeros((1, 1, 3, IMG, IMG))   # drop_a_dim views the (unused) query slot too
     base_support_loader = ListLoader([(bs_x.unsqueeze(0), bs_y.unsqueeze(0), dummy, torch.zeros((1, 1), dtype=torch.int64))],
                                      _l2h(base))
     # fixed base evaluation batch (language_eval.py:121)
