@@ -199,7 +199,7 @@ typedef struct sr_eval_args {
     const float* weight;    /* [n_classes, dim]                                                          */
     const int64_t* labels;  /* [n]                                                                       */
     int32_t n, dim, n_classes;
-    float* logits;          /* optional [n, n_classes]                                                   */
+    float* logits;          /* required [n, n_classes]                                                   */
     int32_t* pred;          /* [n] argmax (lowest index wins ties, as torch.argmax)                      */
     int32_t* counts;        /* [2]: += top-1 hits, += top-5 hits                                         */
     float* loss_sum;        /* [1]: += sum over rows of (logsumexp - z_y)                                */
@@ -208,6 +208,33 @@ typedef struct sr_eval_args {
 } sr_eval_args;
 
 int32_t sr_eval_logits(const sr_eval_args* a, void* stream);
+/* Same scoring on logits the caller already has (feat / weight / dim ignored): eval/util.py accuracy :26-40. */
+int32_t sr_score_logits(const sr_eval_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-op surface (one launch per reference library call; used by the autograd wrappers behind the
+ * drop-in modules so the UNMODIFIED reference loop runs on the B200 modules)
+ * ---------------------------------------------------------------------------------------------- */
+/* LangPuller.forward, semantic mode (resnet_language.py:75-82):
+ * pullers = softmax(novel_embeds @ base_embeds^T / temperature, dim=1) @ base_weight. */
+int32_t sr_semantic_pullers(const float* novel_embeds, const float* base_embeds, const float* base_weight,
+                            int32_t n_novel, int32_t n_base, int32_t embed_dim, int32_t dim, float temperature,
+                            int32_t mask_diagonal, float* pullers, void* stream);
+/* nn.Linear forward / weight+bias backward (classifier :140,187; LinearMap :12-18):
+ * y[n,m] = x[n,k] w[m,k]^T + bias;  dw[m,k] = dy^T x, dbias[m] = column sums of dy (dbias may be NULL). */
+int32_t sr_linear_fwd(const float* x, const float* w, const float* bias, int32_t n, int32_t k, int32_t m, float* y,
+                      void* stream);
+int32_t sr_linear_bwd(const float* dy, const float* x, int32_t n, int32_t k, int32_t m, float* dw, float* dbias,
+                      void* stream);
+/* out[0] = sum((a-b)^2)  (torch.norm(a-b)**2, :90,232,239). */
+int32_t sr_sqdist(const float* a, const float* b, int64_t n, float* out, void* stream);
+/* out = (a-b) * scale * gout[0] * (sq ? 1/sqrt(sq[0]), 0 when sq[0]==0 : 1): backward of s*||a-b||^2 (sq NULL,
+ * scale = 2s) and of s*||a-b|| (sq = the forward's squared norm, scale = s; torch's zero-subgradient at 0). */
+int32_t sr_diff_scale(const float* a, const float* b, int64_t n, float scale, const float* gout, const float* sq,
+                      float* out, void* stream);
+/* out[n,dim] = (x qt^T) qt: projection of rows on span(base) (get_projected_weight :92-97); self-adjoint. */
+int32_t sr_project_rows(const float* x, const float* qt, int32_t n, int32_t q_rows, int32_t dim, float* out,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -57,13 +57,13 @@ __device__ __forceinline__ void gemm_nt_tile(const float* __restrict__ A, RowMap
         for (int idx = tid; idx < BM * (BK / 4); idx += kHeadThreads) {
             const int r = idx / (BK / 4), kq = (idx % (BK / 4)) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + r < M) v = *reinterpret_cast<const float4*>(A + rm(m0 + r) * K + k0 + kq);
+            if (m0 + r < M && k0 + kq < K) v = *reinterpret_cast<const float4*>(A + rm(m0 + r) * K + k0 + kq);
             s.a[kq][r] = v.x; s.a[kq + 1][r] = v.y; s.a[kq + 2][r] = v.z; s.a[kq + 3][r] = v.w;
         }
         for (int idx = tid; idx < BN * (BK / 4); idx += kHeadThreads) {
             const int r = idx / (BK / 4), kq = (idx % (BK / 4)) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n0 + r < N) v = *reinterpret_cast<const float4*>(Bm + (int64_t)(n0 + r) * K + k0 + kq);
+            if (n0 + r < N && k0 + kq < K) v = *reinterpret_cast<const float4*>(Bm + (int64_t)(n0 + r) * K + k0 + kq);
             s.b[kq][r] = v.x; s.b[kq + 1][r] = v.y; s.b[kq + 2][r] = v.z; s.b[kq + 3][r] = v.w;
         }
         __syncthreads();
@@ -665,7 +665,7 @@ extern "C" int32_t sr_head_run(const sr_head_args* a, void* stream_v) {
     if (!a) return fail(SR_E_ARG, "sr_head_run: null args");
     if (!a->feat || !a->weight || !a->opt_state || !a->labels_support || !a->loss_trace || !a->status || !a->workspace)
         return fail(SR_E_ARG, "sr_head_run: null pointer");
-    if (a->dim < 16 || a->dim % 16) return fail(SR_E_ARG, "sr_head_run: dim must be a multiple of 16");
+    if (a->dim < 4 || a->dim % 4) return fail(SR_E_ARG, "sr_head_run: dim must be a multiple of 4 (16-byte rows)");
     if (a->n_support < 1 || a->n_classes < 1 || a->max_epochs < 1) return fail(SR_E_ARG, "sr_head_run: empty problem");
     if (a->n_memory > 0 && !a->labels_memory) return fail(SR_E_ARG, "sr_head_run: memory rows without labels");
     if (a->n_new < 0 || a->n_new > a->n_classes) return fail(SR_E_ARG, "sr_head_run: bad n_new");
@@ -715,7 +715,7 @@ extern "C" int32_t sr_eval_logits(const sr_eval_args* a, void* stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     if (!a || !a->feat || !a->weight || !a->labels || !a->logits || !a->pred || !a->counts || !a->loss_sum)
         return fail(SR_E_ARG, "sr_eval_logits: null pointer");
-    if (a->n < 1 || a->n_classes < 1 || a->dim < 16 || a->dim % 16) return fail(SR_E_ARG, "sr_eval_logits: bad sizes");
+    if (a->n < 1 || a->n_classes < 1 || a->dim < 4 || a->dim % 4) return fail(SR_E_ARG, "sr_eval_logits: bad sizes");
     const int64_t t64 = ((int64_t)(a->n + 63) / 64) * ((a->n_classes + 63) / 64);
     if (t64 >= 2 * (int64_t)num_sms()) {
         logits_kernel<64><<<(unsigned)t64, kHeadThreads, 0, stream>>>(a->feat, a->weight, a->logits, a->n, a->n_classes, a->dim);
@@ -724,6 +724,16 @@ extern "C" int32_t sr_eval_logits(const sr_eval_args* a, void* stream_v) {
         logits_kernel<32><<<(unsigned)t32, kHeadThreads, 0, stream>>>(a->feat, a->weight, a->logits, a->n, a->n_classes, a->dim);
     }
     SR_CUDA_OK(cudaGetLastError());
+    score_rows_kernel<<<(a->n + 7) / 8, 256, 0, stream>>>(*a);
+    SR_CUDA_OK(cudaGetLastError());
+    return SR_OK;
+}
+
+extern "C" int32_t sr_score_logits(const sr_eval_args* a, void* stream_v) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (!a || !a->labels || !a->logits || !a->pred || !a->counts || !a->loss_sum)
+        return fail(SR_E_ARG, "sr_score_logits: null pointer");
+    if (a->n < 1 || a->n_classes < 1) return fail(SR_E_ARG, "sr_score_logits: bad sizes");
     score_rows_kernel<<<(a->n + 7) / 8, 256, 0, stream>>>(*a);
     SR_CUDA_OK(cudaGetLastError());
     return SR_OK;

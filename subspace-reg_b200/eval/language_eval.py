@@ -1,0 +1,300 @@
+"""Drop-in for reference eval/language_eval.py: validate (:18-43), eval_base (:46-69) and
+few_shot_finetune_incremental_test (:71-454) with the reference's signatures, prints and return values.
+
+B200-first restructuring of the session loop (same numbers, different schedule):
+  * epoch 1 of a session is the only train-mode backbone pass (batch-stat BN, running-stat update, dropout /
+    DropBlock with the CPU generator's masks) -> its features feed ONE head step;
+  * from epoch 2 on the backbone is in eval mode with fixed weights and statistics, so its outputs never change:
+    support, memory, every past session's queries and the base batch go through the tcgen05 backbone ONCE per
+    session into a feature cache;
+  * all remaining epochs run inside one persistent device kernel (sr_head_run) that applies the reference's
+    stopping rule on the device; the host reads back one status word and the loss trace;
+  * validate / eval_base score the cached features (sr_eval_logits) after the last epoch - the reference computes
+    them every epoch but only consumes the last (:370-376);
+  * BasicBlock.num_batches_tracked is advanced as if every skipped forward had happened (DropBlock's gamma).
+"""
+from __future__ import print_function
+
+import copy
+import itertools
+import time
+
+import numpy as np
+import torch
+
+from dataset.memory import Memory
+from models.resnet_language import LangPuller
+from srb200 import _lib as L
+from srb200 import ops
+from .util import AverageMeter, drop_a_dim, freeze_backbone_weights, get_vocabs, log_episode, percent
+
+
+def _score(net, feat, labels, confusion=None):
+    r = ops.eval_logits(feat, net.classifier.weight.detach().contiguous(), labels, confusion)
+    counts = r["counts"].cpu().tolist()
+    n = feat.shape[0]
+    return percent(counts[0], n), percent(counts[1], n), r["loss_sum"].item() / n, r["pred"].cpu().numpy().astype(np.int64), r
+
+
+def validate(query_xs, query_ys_id, net, criterion, opt, epoch):
+    """Per past session: top-1 / top-5 (percent, 1-element tensors), mean CE and argmax predictions.
+    Side effect kept from the reference: the network is left in eval mode."""
+    net.eval()
+    with torch.no_grad():
+        if isinstance(query_xs, list):
+            acc1, acc5, losses, preds = [], [], [], []
+            for i, item in enumerate(query_xs):
+                r = validate(item, query_ys_id[i], net, criterion, opt, epoch)
+                acc1.append(r[0])
+                acc5.append(r[1])
+                losses.append(r[2])
+                preds.append(r[3])
+            return acc1, acc5, losses, preds
+        feat = net.features(query_xs.cuda())
+        a1, a5, loss, pred, _ = _score(net, feat, query_ys_id.cuda())
+        return a1[0], a5[0], loss, pred
+
+
+def eval_base(net, base_batch, criterion, vocab_all=None, df=None, return_preds=False):
+    if df is not None:
+        raise NotImplementedError("the visualisation dataframe (vis=True) relies on DataFrame.append, removed in pandas 2")
+    net.eval()
+    with torch.no_grad():
+        input, target, *_ = base_batch
+        feat = net.features(input.squeeze(0).cuda())
+        a1, _, _, pred, _ = _score(net, feat, target.squeeze(0).cuda())
+    acc = np.mean([a1[0].item()])
+    if return_preds:
+        return acc, pred
+    return acc
+
+
+def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, base_val_loader, opt, vis=False,
+                                       base_support_loader=None):
+    if vis or opt.track_weights or opt.track_label_inspired_weights or opt.save_preds_0:
+        raise NotImplementedError("vis / track_weights / track_label_inspired_weights / save_preds_0 are the reference's "
+                                  "pandas dumps (broken under pandas >= 2); they are outside the B200 hot path")
+    if criterion is not None and not isinstance(criterion, torch.nn.CrossEntropyLoss):
+        raise NotImplementedError("the fused head implements nn.CrossEntropyLoss (mean reduction) only")
+    if net.classifier.bias is not None:
+        raise NotImplementedError("classifier bias: the reference's bias branches are dead code (--no_linear_bias)")
+    if opt.freeze_backbone_at != 1:
+        raise NotImplementedError("freeze_backbone_at != 1 trains the backbone, which is outside the incremental-session path")
+    record = dict(sessions=[], timers=dict(train_s=0.0, score_s=0.0, backbone_imgs=0, steps=0, images_scored=0))
+    few_shot_finetune_incremental_test.last_record = record
+    tm = record['timers']
+
+    acc_novel, acc_base = [AverageMeter() for _ in range(2)]
+    weighted_avg_l, acc_novel_list, acc_base_list = [[] for _ in range(3)]
+
+    torch.manual_seed(opt.set_seed)
+    np.random.seed(opt.set_seed)
+
+    basenet = copy.deepcopy(net).cuda()
+    base_weight, base_bias = basenet._get_base_weights()
+    base_weight = base_weight.contiguous()
+    dev = base_weight.device
+    n_base_cls = net.num_classes
+
+    base_valloader_it = itertools.cycle(iter(base_val_loader))
+    meta_valloader_it = itertools.cycle(iter(meta_valloader))
+    if base_support_loader is not None:
+        base_support_it = itertools.cycle(iter(base_support_loader))
+        base_support_xs, base_support_ys, *_ = drop_a_dim(next(base_support_it))
+
+    novel_query_collection = None
+    novel_query_collection_id = None
+    base_batch = next(base_valloader_it)
+    base_x = base_batch[0].squeeze(0).cuda(non_blocking=True)
+    base_y = base_batch[1].squeeze(0).cuda(non_blocking=True)
+
+    if opt.memory_replay:
+        memory = Memory()
+
+    # Initial validation on base samples.
+    t0 = time.perf_counter()
+    acc_base_ = eval_base(net, (base_x, base_y), criterion)
+    tm['score_s'] += time.perf_counter() - t0
+    tm['images_scored'] += base_x.shape[0]
+    weighted_avg_l.append(acc_base_)
+    record['base0'] = acc_base_
+
+    iter_num = opt.neval_episodes
+    if opt.continual:
+        iter_num = getattr(opt, 'n_sessions_override', 8)   # 8 sessions for miniImageNet (reference literal)
+        basec_map = ckpt['training_classes']
+
+    for idx in range(iter_num):
+        print("\n**** Iteration {}/{} ****\n".format(idx + 1, opt.neval_episodes))
+        support_xs, support_ys, query_xs, query_ys = drop_a_dim(next(meta_valloader_it))
+        if base_support_loader is not None:
+            support_xs = torch.cat([support_xs, base_support_xs], 0)
+
+        if idx > 0:
+            prev_vocab_base = vocab_base
+            prev_vocab_novel = vocab_novel
+        vocab_base, vocab_all, vocab_novel, orig2id = get_vocabs(base_val_loader, meta_valloader, query_ys)
+        print("Vocab base: ", vocab_base)
+        print("Vocab novel: ", vocab_novel)
+        if idx == 0:
+            orig_base_num = len(vocab_base)
+        if idx > 0:
+            vocab_base = prev_vocab_base + prev_vocab_novel
+
+        # Previous sessions' novel weights as they were when their session ended (reglossnovel anchors).
+        if idx == 1:
+            novel_weight_to_reserve = net.classifier.weight.clone().detach()[-opt.n_ways:, :].requires_grad_(False)
+            print(f"Novel weight to reserve is of shape {novel_weight_to_reserve.shape} at session {idx+1}.")
+        if idx > 1:
+            new_novel_set = net.classifier.weight.clone().detach()[-opt.n_ways:, :].requires_grad_(False)
+            novel_weight_to_reserve = torch.cat((novel_weight_to_reserve, new_novel_set), 0)
+            print(f"Novel weight to reserve is of shape {novel_weight_to_reserve.shape} at session {idx+1}.")
+
+        novel_labels = np.sort(np.unique(query_ys))
+        print("Novel labels: ", novel_labels)
+        for k, v in orig2id.items():
+            orig2id[k] = v + idx * opt.n_ways
+        query_ys_id = torch.LongTensor([orig2id[y] for y in query_ys])
+        support_ys_id = torch.LongTensor([orig2id[y] for y in support_ys])
+
+        query_xs_d = query_xs.cuda(non_blocking=True)
+        if novel_query_collection_id is None:
+            novel_query_collection = [query_xs_d]
+            novel_query_collection_id = [query_ys_id.cuda()]
+        else:
+            novel_query_collection.append(query_xs_d)
+            novel_query_collection_id.append(query_ys_id.cuda())
+
+        if base_support_loader is not None:
+            support_ys_id = torch.cat([support_ys_id, torch.from_numpy(base_support_ys)])
+
+        net.train()
+        net.augment_base_classifier_(len(novel_labels))
+
+        use_pull = opt.label_pull is not None and getattr(opt, 'pulling', None) == "regularize"
+        pull_mode, pull_t, q_rows = L.SR_PULL_NONE, None, 0
+        if use_pull:
+            if idx == 0:
+                lang_puller = LangPuller(opt, vocab_base, vocab_novel)
+            else:
+                lang_puller.update_novel_embeds(vocab_novel)
+            if opt.attraction_override == "mapping_linear_label2image":
+                lang_puller.create_pulling_mapping(ckpt[opt.attraction_override])
+            pullers = lang_puller(base_weight[:orig_base_num, :])
+            if opt.attraction_override == "distance2subspace":
+                qt, q_rows, _ = lang_puller.factor(base_weight)   # constant for the whole run (torch.qr every epoch in the reference)
+                pull_mode, pull_t = L.SR_PULL_PROJECT, qt
+            else:
+                pull_mode, pull_t = L.SR_PULL_FIXED, pullers.detach().contiguous()
+
+        opt.stable = True if opt.target_train_loss == 0 else False
+        freeze_backbone_weights(net, opt, 1, exclude=["classifier"])
+        t_train0 = time.perf_counter()
+        support_xs_d = support_xs.cuda(non_blocking=True)
+        support_ys_d = support_ys_id.cuda(non_blocking=True)
+        n_sup = support_xs_d.shape[0]
+        has_mem = bool(opt.memory_replay and len(memory) > 0)
+        n_mem = len(memory) if has_mem else 0
+        counters0 = next(iter(net.block_counters().values()))
+
+        # ---- epoch 1: the session's only train-mode forward(s); BN running statistics move here ----
+        f_train = net.features(support_xs_d)
+        if has_mem:
+            f_train = torch.cat([f_train, net.features(memory.data)], 0)
+        tm['backbone_imgs'] += n_sup + n_mem
+        W = net.classifier.weight.data
+        reserve = novel_weight_to_reserve.contiguous() if (opt.lmbd_reg_novel is not None and idx > 0) else None
+        head = ops.HeadSession(
+            f_train, n_sup, 0, support_ys_d, W, n_base_cls, len(novel_labels), n_memory=n_mem, memory_row0=n_sup,
+            labels_memory=memory.labels if has_mem else None,
+            base_weight=base_weight if opt.lmbd_reg_transform_w is not None else None, reserve_weight=reserve,
+            pull_mode=pull_mode, pull=pull_t, q_rows=q_rows,
+            lmbd_base=opt.lmbd_reg_transform_w or 0.0, lmbd_novel=opt.lmbd_reg_novel or 0.0,
+            gamma=opt.label_pull if use_pull else 0.0, adam=bool(opt.adam), lr=opt.learning_rate, momentum=opt.momentum,
+            weight_decay=opt.weight_decay, stable=opt.stable, convergence_epsilon=opt.convergence_epsilon,
+            stable_epochs=opt.stable_epochs, target_train_loss=opt.target_train_loss,
+            min_novel_epochs=opt.min_novel_epochs, max_novel_epochs=opt.max_novel_epochs)
+        head.run(1)
+        net.eval()                                  # validate()'s side effect after epoch 1
+
+        # ---- eval-mode feature cache: support | memory | queries of sessions 1..idx+1 | base batch ----
+        parts = [support_xs_d] + ([memory.data] if has_mem else []) + novel_query_collection + [base_x]
+        with torch.no_grad():
+            cache = net.engine().eval_features(torch.cat(parts, 0))
+        tm['backbone_imgs'] += cache.shape[0]
+        q_row0 = n_sup + n_mem
+        b_row0 = q_row0 + sum(q.shape[0] for q in novel_query_collection)
+
+        # ---- epochs 2.. on the device until the stopping rule fires ----
+        while not head.stopped:
+            head.run(max(opt.max_novel_epochs - head.epochs, 1), feat=cache, support_row0=0, memory_row0=n_sup)
+        trace = torch.cat(head.traces, 0).numpy()
+        epoch = head.epochs + 1
+        torch.cuda.synchronize()
+        tm['train_s'] += time.perf_counter() - t_train0
+        tm['steps'] += head.epochs
+        for e in range(10, head.epochs + 1, 10):
+            if use_pull:
+                print("PULL: ", float(trace[e - 1, 5]))
+            print('Novel Epoch {:4d}\tTrain Loss {:10.4f}\tAcc@1 {:10.3f}\tAcc@5 {:10.3f}'.format(
+                e, float(trace[e - 1, 0]), percent(trace[e - 1, 6], n_sup)[0], percent(trace[e - 1, 7], n_sup)[0]))
+
+        # ---- the reference's forward-call count, for DropBlock's schedule ----
+        n_calls = head.epochs * (1 + (1 if has_mem else 0) + len(novel_query_collection)) + 1
+        done = next(iter(net.block_counters().values())) - counters0
+        net.advance_block_counters(n_calls - done)
+
+        # ---- scoring of the last epoch: validate (:321-326) + eval_base (:362-367) on cached features ----
+        t0 = time.perf_counter()
+        test_acc, query_ys_pred, query_logits = [], [], []
+        r0 = q_row0
+        for qx, qy in zip(novel_query_collection, novel_query_collection_id):
+            a1, a5, loss_q, pred, raw = _score(net, cache[r0:r0 + qx.shape[0]], qy)
+            test_acc.append(a1[0])
+            query_ys_pred.append(pred)
+            query_logits.append(raw["logits"])
+            r0 += qx.shape[0]
+        a1, _, _, base_pred, _ = _score(net, cache[b_row0:b_row0 + base_x.shape[0]], base_y)
+        acc_base_ = np.mean([a1[0].item()])
+        tm['score_s'] += time.perf_counter() - t0
+        tm['images_scored'] += b_row0 - q_row0 + base_x.shape[0]
+
+        if opt.memory_replay:
+            inds = np.random.choice(opt.n_shots, opt.memory_replay)
+            margin = 5 * np.arange(5)
+            offset = np.arange(0, 125, 25)
+            inds = np.tile(margin + inds, (5, 1)) + (np.tile(offset, (5, 1))).T
+            inds = inds.flatten()
+            inds_d = torch.from_numpy(inds).to(dev)
+            memory.additems(support_xs_d[inds_d, :], support_ys_d[inds_d])
+
+        test_acc = [round(i.item(), 2) for i in test_acc]
+        print("Novel session accuracies: ", test_acc)
+        novel_session_acc = list(test_acc)
+        test_acc = np.array(test_acc).mean()
+
+        acc_base.update(acc_base_)
+        acc_novel.update(test_acc)
+        w1 = 60 if opt.dataset == "miniImageNet" else 200
+        w2 = len(vocab_base) + len(vocab_novel) - 60
+        weighted_avg = (w1 * acc_base_ + w2 * test_acc) / (w1 + w2)
+        weighted_avg_l.append(round(weighted_avg, 2))
+        acc_novel_list.append(round(test_acc, 2))
+        acc_base_list.append(round(acc_base_, 2))
+        print(f"***Running weighted avg: {weighted_avg}")
+        log_episode(novel_labels, vocab_novel, epoch, test_acc, acc_base_, acc_base.avg, acc_novel.avg)
+
+        record['sessions'].append(dict(
+            epochs=head.epochs, terms=trace.astype(np.float64), W=net.classifier.weight.detach().clone(),
+            novel_session_acc=novel_session_acc, query_pred=[torch.from_numpy(p) for p in query_ys_pred],
+            query_logits=query_logits, base_pred=torch.from_numpy(base_pred), acc_base=float(acc_base_),
+            memory_inds=inds.copy() if opt.memory_replay else None, vocab_novel=list(vocab_novel),
+            probe_feat=cache[:8].clone(), train_feat=f_train[:8].clone(),
+            bn={k: v.detach().clone() for k, v in net.state_dict().items() if 'running_' in k or 'num_batches_tracked' in k}))
+
+    record.update(weighted=weighted_avg_l, novel=acc_novel_list, base=acc_base_list, acc_novel_avg=acc_novel.avg,
+                  acc_base_avg=acc_base.avg, counters=net.block_counters())
+    print("Overall continual accuracies: ", weighted_avg_l)
+    print("Novel only incremental: ", acc_novel_list)
+    print("Base only incremental: ", acc_base_list)
+    return acc_novel.avg, acc_base.avg

@@ -17,7 +17,8 @@ SR_TRACE_COLS = 8
 EXPORTS = [
     "sr_last_error", "sr_version", "sr_check_device", "sr_pack_input", "sr_bn_fold", "sr_pack_weight", "sr_conv",
     "sr_bn_finalize", "sr_bn_apply", "sr_subspace_factor_workspace_bytes", "sr_subspace_factor",
-    "sr_head_workspace_bytes", "sr_head_run", "sr_eval_logits",
+    "sr_head_workspace_bytes", "sr_head_run", "sr_eval_logits", "sr_semantic_pullers", "sr_linear_fwd",
+    "sr_linear_bwd", "sr_sqdist", "sr_diff_scale", "sr_project_rows", "sr_score_logits",
 ]
 
 
@@ -112,6 +113,20 @@ def load():
     lib.sr_head_run.argtypes = [C.POINTER(HeadArgs), vp]
     lib.sr_eval_logits.restype = i32
     lib.sr_eval_logits.argtypes = [C.POINTER(EvalArgs), vp]
+    lib.sr_score_logits.restype = i32
+    lib.sr_score_logits.argtypes = [C.POINTER(EvalArgs), vp]
+    lib.sr_semantic_pullers.restype = i32
+    lib.sr_semantic_pullers.argtypes = [vp, vp, vp, i32, i32, i32, i32, f32, i32, vp, vp]
+    lib.sr_linear_fwd.restype = i32
+    lib.sr_linear_fwd.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.sr_linear_bwd.restype = i32
+    lib.sr_linear_bwd.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.sr_sqdist.restype = i32
+    lib.sr_sqdist.argtypes = [vp, vp, i64, vp, vp]
+    lib.sr_diff_scale.restype = i32
+    lib.sr_diff_scale.argtypes = [vp, vp, i64, f32, vp, vp, vp, vp]
+    lib.sr_project_rows.restype = i32
+    lib.sr_project_rows.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     _lib = lib
     return lib
 

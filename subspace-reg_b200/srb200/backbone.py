@@ -1,0 +1,192 @@
+"""Host-side sequencing of the backbone kernels (eval-mode folded-BN pass and the train-mode batch-stat pass).
+
+The arithmetic is in libsrb200.so (sr_pack_input / sr_pack_weight / sr_bn_fold / sr_conv / sr_bn_finalize /
+sr_bn_apply); this module only owns buffers and launch order.  Reference semantics: BasicBlock.forward
+(models/resnet_language.py:268-301), ResNet.forward (:170-181), nn.BatchNorm2d eval/train.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import ops
+
+SLOPE = 0.1
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+DROP_RATE = 0.1
+
+
+def _pad16(c):
+    return (c + 15) // 16 * 16
+
+
+class BackboneEngine(object):
+    """Packed (bf16, BN-folded) weights of one ResNet plus the two forward passes.
+
+    `blocks` is the module's list of block descriptors: dict(prefix, mod, cin, cout, pool, downsample, drop_block,
+    block_size) where `mod` carries conv1..3 / bn1..3 / downsample as parameter containers."""
+
+    def __init__(self, blocks, chunk=1024):
+        self.blocks = blocks
+        self.chunk = chunk
+        self._folded = None      # per block: dict(w1, s1, w2, s2, w3, s3[, wd])
+        self._raw = None         # per block: unscaled packed weights (train-mode pass)
+        self._fold_key = None
+
+    # ---------------------------------------------------------------- weight packing
+    def _bn_key(self):
+        key = []
+        for b in self.blocks:
+            m = b['mod']
+            bns = [m.bn1, m.bn2, m.bn3] + ([m.downsample[1]] if b['downsample'] else [])
+            convs = [m.conv1, m.conv2, m.conv3] + ([m.downsample[0]] if b['downsample'] else [])
+            for bn in bns:
+                key += [bn.running_mean._version, bn.running_var._version, bn.weight._version, bn.bias._version,
+                        bn.running_mean.data_ptr()]
+            for cv in convs:
+                key += [cv.weight._version, cv.weight.data_ptr()]
+        return tuple(key)
+
+    def invalidate(self):
+        self._fold_key = None
+
+    def _ensure_folded(self):
+        key = self._bn_key()
+        if self._folded is not None and key == self._fold_key:
+            return
+        folded = []
+        for b in self.blocks:
+            m = b['mod']
+            d = {}
+            for i, (cv, bn) in enumerate(((m.conv1, m.bn1), (m.conv2, m.bn2), (m.conv3, m.bn3))):
+                scale, shift = ops.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, BN_EPS)
+                d['w%d' % (i + 1)] = ops.pack_weight(cv.weight.detach(), scale, _pad16(cv.weight.shape[1]))
+                d['s%d' % (i + 1)] = shift
+            if b['downsample']:
+                cv, bn = m.downsample[0], m.downsample[1]
+                scale, shift = ops.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, BN_EPS)
+                d['wd'] = ops.pack_weight(cv.weight.detach(), scale, _pad16(cv.weight.shape[1]))
+                d['s3'] = d['s3'] + shift      # both branches land in one accumulator: shifts add
+            folded.append(d)
+        self._folded = folded
+        self._fold_key = key
+
+    def _ensure_raw(self):
+        key = tuple(cv.weight._version for b in self.blocks for cv in
+                    [b['mod'].conv1, b['mod'].conv2, b['mod'].conv3] + ([b['mod'].downsample[0]] if b['downsample'] else []))
+        if self._raw is not None and self._raw[0] == key:
+            return
+        raw = []
+        for b in self.blocks:
+            m = b['mod']
+            d = {('w%d' % (i + 1)): ops.pack_weight(cv.weight.detach(), None, _pad16(cv.weight.shape[1]))
+                 for i, cv in enumerate((m.conv1, m.conv2, m.conv3))}
+            if b['downsample']:
+                d['wd'] = ops.pack_weight(m.downsample[0].weight.detach(), None, _pad16(m.downsample[0].weight.shape[1]))
+            raw.append(d)
+        self._raw = (key, raw)
+
+    # ---------------------------------------------------------------- eval-mode pass
+    def eval_features(self, x, taps=None):
+        """x: CUDA fp32 NCHW [B,3,84,84] -> fp32 [B,640].  `taps`: optional list that receives the four stage
+        outputs (NHWC bf16) for ResNet.forward(is_feat=True)."""
+        self._ensure_folded()
+        outs = []
+        for i0 in range(0, x.shape[0], self.chunk):
+            outs.append(self._eval_chunk(x[i0:i0 + self.chunk].contiguous(), taps))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+    def _eval_chunk(self, x, taps):
+        h = ops.pack_input(x, 16)
+        nb = len(self.blocks)
+        for bi, (b, w) in enumerate(zip(self.blocks, self._folded)):
+            cout = b['cout']
+            last = bi == nb - 1
+            h1 = ops.conv([(h, w['w1'])], cout, shift=w['s1'], slope=SLOPE, epilogue=L.SR_EPI_ACT)
+            h2 = ops.conv([(h1, w['w2'])], cout, shift=w['s2'], slope=SLOPE, epilogue=L.SR_EPI_ACT)
+            if b['downsample']:
+                epi = L.SR_EPI_ACT_POOL2 if b['pool'] == 2 else L.SR_EPI_ACT
+                out = ops.conv([(h2, w['w3']), (h, w['wd'])], cout, shift=w['s3'], slope=SLOPE, epilogue=epi)
+                if last:
+                    raise RuntimeError("srb200: a pooled last block needs the separate average kernel (resnet12) - "
+                                       "not built in this round")
+            else:
+                epi = L.SR_EPI_ACT_AVG if last else L.SR_EPI_ACT
+                out = ops.conv([(h2, w['w3'])], cout, shift=w['s3'], residual=h, slope=SLOPE, epilogue=epi)
+            if taps is not None and not last:
+                if bi + 1 == nb or self.blocks[bi + 1]['prefix'].endswith('.0'):
+                    taps.append(out)
+            h = out
+        return h
+
+    # ---------------------------------------------------------------- train-mode pass (epoch 1 of a session)
+    def draw_masks(self, batch, counters):
+        """CPU-generator draws of one train-mode forward, in the reference's order (dropout after layerX.0,
+        DropBlock after layer3.1 / layer4.1; resnet_language.py:292-299, 311-325).  Returns per block
+        (keep uint8 NCHW [CUDA], scale) or None."""
+        masks = []
+        size = 84
+        for b in self.blocks:
+            size = size // b['pool']
+            shape = (batch, b['cout'], size, size)
+            if b['drop_block']:
+                bs = b['block_size']
+                nbt = counters[b['prefix']]
+                keep_rate = max(1.0 - DROP_RATE / (20 * 2000) * nbt, 1.0 - DROP_RATE)
+                gamma = (1 - keep_rate) / bs ** 2 * size ** 2 / (size - bs + 1) ** 2
+                seeds = torch.distributions.Bernoulli(gamma).sample((batch, b['cout'], size - (bs - 1), size - (bs - 1)))
+                left, right = int((bs - 1) / 2), int(bs / 2)
+                padded = F.pad(seeds, (left, right, left, right))
+                if bs > 1 and bool(seeds.any()):
+                    Hm, Wm = seeds.shape[2], seeds.shape[3]
+                    for i in range(bs):
+                        for j in range(bs):
+                            padded[:, :, i:i + Hm, j:j + Wm] = torch.maximum(padded[:, :, i:i + Hm, j:j + Wm], seeds)
+                bm = 1 - padded
+                scale = float(bm.numel() / bm.sum())     # fp32 tensor in the reference (countM / count_ones)
+                masks.append(((bm != 0).to(torch.uint8), scale))
+            else:
+                m = F.dropout(torch.ones(shape), p=DROP_RATE, training=True)
+                masks.append(((m != 0).to(torch.uint8), float(m.max())))
+        return masks
+
+    def train_features(self, x, counters):
+        """One train-mode forward (batch-stat BN, running-stat EMA in place, dropout / DropBlock) -> fp32 [B,640]."""
+        self._ensure_raw()
+        raw_w = self._raw[1]
+        B = x.shape[0]
+        masks = self.draw_masks(B, counters)
+        dev = x.device
+        h = ops.pack_input(x.contiguous(), 16)
+        nb = len(self.blocks)
+
+        def conv_bn(act, wgt, bn, cout):
+            stats = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
+            raw = ops.conv([(act, wgt)], cout, epilogue=L.SR_EPI_RAW_STATS, stats=stats)
+            count = raw.shape[0] * raw.shape[1] * raw.shape[2]
+            mean, invstd = ops.bn_finalize(stats, count, bn.running_mean, bn.running_var, BN_EPS, BN_MOMENTUM)
+            bn.num_batches_tracked += 1
+            return raw, mean, invstd
+
+        for bi, (b, w) in enumerate(zip(self.blocks, raw_w)):
+            m, cout = b['mod'], b['cout']
+            last = bi == nb - 1
+            r1, mu1, is1 = conv_bn(h, w['w1'], m.bn1, cout)
+            h1 = ops.bn_apply(r1, mu1, is1, m.bn1.weight.detach(), m.bn1.bias.detach(), lrelu=True, slope=SLOPE)
+            r2, mu2, is2 = conv_bn(h1, w['w2'], m.bn2, cout)
+            h2 = ops.bn_apply(r2, mu2, is2, m.bn2.weight.detach(), m.bn2.bias.detach(), lrelu=True, slope=SLOPE)
+            r3, mu3, is3 = conv_bn(h2, w['w3'], m.bn3, cout)
+            keep, scale = masks[bi]
+            keep = keep.to(dev, non_blocking=True)
+            pool = -1 if last and b['pool'] == 1 else (2 if b['pool'] == 2 else 0)
+            if b['downsample']:
+                bnd = m.downsample[1]
+                rd, mud, isd = conv_bn(h, w['wd'], bnd, cout)
+                h = ops.bn_apply(r3, mu3, is3, m.bn3.weight.detach(), m.bn3.bias.detach(), res_raw=rd,
+                                 res_bn=(mud, isd, bnd.weight.detach(), bnd.bias.detach()), lrelu=True, slope=SLOPE,
+                                 pool=pool, keep=keep, keep_scale=scale)
+            else:
+                h = ops.bn_apply(r3, mu3, is3, m.bn3.weight.detach(), m.bn3.bias.detach(), res_act=h, lrelu=True,
+                                 slope=SLOPE, pool=pool, keep=keep, keep_scale=scale)
+        self.invalidate()   # running statistics moved: the folded weights are stale
+        return h

@@ -212,9 +212,21 @@ class HeadSession(object):
         self.stopped = False
         self.traces = []
 
-    def run(self, max_epochs):
-        """Run up to max_epochs more epochs on the device; returns the [epochs, SR_TRACE_COLS] trace (host)."""
+    def run(self, max_epochs, feat=None, support_row0=None, memory_row0=None):
+        """Run up to max_epochs more epochs on the device; returns the [epochs, SR_TRACE_COLS] trace (host).
+
+        `feat` / row offsets may change between calls (epoch 1 uses the train-mode features, later epochs the
+        eval-mode cache); labels, weight and optimiser state carry over."""
         a = self.args
+        if feat is not None:
+            self.feat = feat
+            a.feat = _ptr(feat, torch.float32, "feat")
+            if feat.shape[1] != a.dim:
+                raise RuntimeError("srb200: feature width changed")
+        if support_row0 is not None:
+            a.support_row0 = support_row0
+        if memory_row0 is not None:
+            a.memory_row0 = memory_row0
         trace = torch.zeros((max_epochs, L.SR_TRACE_COLS), dtype=torch.float32, device=self.feat.device)
         a.loss_trace = _ptr(trace)
         a.max_epochs, a.epoch0, a.step0 = max_epochs, self.epochs, self.epochs
@@ -257,3 +269,79 @@ def eval_logits(feat, weight, labels, confusion=None):
     a.conf_dim = 0 if confusion is None else confusion.shape[0]
     L.check(L.load().sr_eval_logits(C.byref(a), _stream()), "sr_eval_logits")
     return {"logits": logits, "pred": pred, "counts": counts, "loss_sum": loss_sum}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# per-op surface (used by srb200.autograd behind the drop-in modules)
+# ---------------------------------------------------------------------------------------------------------------
+def semantic_pullers(novel_embeds, base_embeds, base_weight, temperature, mask=False):
+    n, e = novel_embeds.shape
+    b, d = base_weight.shape
+    if base_embeds.shape != (b, e):
+        raise RuntimeError("srb200: base_embeds %s does not match base_weight %s" % (tuple(base_embeds.shape), tuple(base_weight.shape)))
+    out = torch.empty((n, d), dtype=torch.float32, device=base_weight.device)
+    rc = L.load().sr_semantic_pullers(_ptr(novel_embeds, torch.float32, "novel_embeds"), _ptr(base_embeds, torch.float32, "base_embeds"),
+                                      _ptr(base_weight, torch.float32, "base_weight"), n, b, e, d, temperature, 1 if mask else 0,
+                                      _ptr(out), _stream())
+    L.check(rc, "sr_semantic_pullers")
+    return out
+
+
+def linear_fwd(x, w, bias=None):
+    n, k = x.shape
+    m = w.shape[0]
+    y = torch.empty((n, m), dtype=torch.float32, device=x.device)
+    rc = L.load().sr_linear_fwd(_ptr(x, torch.float32, "x"), _ptr(w, torch.float32, "w"), _ptr(bias, torch.float32, "bias"), n, k, m,
+                                _ptr(y), _stream())
+    L.check(rc, "sr_linear_fwd")
+    return y
+
+
+def linear_bwd(dy, x, want_bias):
+    n, m = dy.shape
+    k = x.shape[1]
+    dw = torch.empty((m, k), dtype=torch.float32, device=x.device)
+    db = torch.empty(m, dtype=torch.float32, device=x.device) if want_bias else None
+    rc = L.load().sr_linear_bwd(_ptr(dy, torch.float32, "dy"), _ptr(x, torch.float32, "x"), n, k, m, _ptr(dw), _ptr(db), _stream())
+    L.check(rc, "sr_linear_bwd")
+    return dw, db
+
+
+def sqdist(a, b):
+    out = torch.empty(1, dtype=torch.float32, device=a.device)
+    rc = L.load().sr_sqdist(_ptr(a, torch.float32, "a"), _ptr(b, torch.float32, "b"), a.numel(), _ptr(out), _stream())
+    L.check(rc, "sr_sqdist")
+    return out
+
+
+def diff_scale(a, b, scale, gout=None, sq=None):
+    out = torch.empty_like(a)
+    rc = L.load().sr_diff_scale(_ptr(a, torch.float32, "a"), _ptr(b, torch.float32, "b"), a.numel(), scale,
+                                _ptr(gout, torch.float32, "gout"), _ptr(sq, torch.float32, "sq"), _ptr(out), _stream())
+    L.check(rc, "sr_diff_scale")
+    return out
+
+
+def project_rows(x, qt, q_rows):
+    n, d = x.shape
+    out = torch.empty_like(x)
+    rc = L.load().sr_project_rows(_ptr(x, torch.float32, "x"), _ptr(qt, torch.float32, "qt"), n, q_rows, d, _ptr(out), _stream())
+    L.check(rc, "sr_project_rows")
+    return out
+
+
+def score_logits(logits, labels, confusion=None):
+    """Top-1 / top-5 hit counts, argmax and summed CE of logits the caller already has."""
+    n, Cn = logits.shape
+    dev = logits.device
+    pred = torch.empty(n, dtype=torch.int32, device=dev)
+    counts = torch.zeros(2, dtype=torch.int32, device=dev)
+    loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+    a = L.EvalArgs()
+    a.labels = _ptr(labels, torch.int64, "labels")
+    a.n, a.dim, a.n_classes = n, 0, Cn
+    a.logits, a.pred, a.counts, a.loss_sum = _ptr(logits, torch.float32, "logits"), _ptr(pred), _ptr(counts), _ptr(loss_sum)
+    a.confusion = _ptr(confusion, torch.int64, "confusion")
+    a.conf_dim = 0 if confusion is None else confusion.shape[0]
+    L.check(L.load().sr_score_logits(C.byref(a), _stream()), "sr_score_logits")
+    return {"pred": pred, "counts": counts, "loss_sum": loss_sum}

@@ -1,0 +1,95 @@
+"""CPU-side checks of the C-ABI boundary: the in-tree library loads, exports every symbol include/srb200.h declares,
+the ctypes mirrors have the C structs' sizes, and the product path refuses CPU tensors (no fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "srb200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from srb200 import _lib
+    return _lib.load()
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    from srb200 import _lib
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libsrb200.so does not export %s" % n
+    assert sorted(_lib.EXPORTS) == names, "srb200._lib.EXPORTS is out of sync with include/srb200.h"
+
+
+def test_version_and_error_string(lib):
+    assert lib.sr_version() >= 100
+    assert isinstance(lib.sr_last_error(), bytes)
+
+
+def test_struct_layouts_match_c(tmp_path):
+    from srb200 import _lib
+    prog = tmp_path / "sizes.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "srb200.h"\nint main(void){'
+                    'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(sr_conv_panel), sizeof(sr_conv_args), sizeof(sr_bn_apply_args),'
+                    'sizeof(sr_head_args), sizeof(sr_eval_args), offsetof(sr_head_args, convergence_epsilon),'
+                    'offsetof(sr_head_args, workspace_bytes)); return 0;}\n')
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(_lib.ConvPanel)
+    assert out[1] == ctypes.sizeof(_lib.ConvArgs)
+    assert out[2] == ctypes.sizeof(_lib.BnApplyArgs)
+    assert out[3] == ctypes.sizeof(_lib.HeadArgs)
+    assert out[4] == ctypes.sizeof(_lib.EvalArgs)
+    assert out[5] == _lib.HeadArgs.convergence_epsilon.offset
+    assert out[6] == _lib.HeadArgs.workspace_bytes.offset
+
+
+def test_argument_validation_without_gpu(lib):
+    """Bad arguments are rejected on the host before anything touches a device."""
+    from srb200 import _lib
+    a = _lib.ConvArgs()
+    a.n_panels = 3
+    assert lib.sr_conv(ctypes.byref(a), None) == -1
+    assert b"n_panels" in lib.sr_last_error()
+    h = _lib.HeadArgs()
+    assert lib.sr_head_run(ctypes.byref(h), None) == -1
+    assert lib.sr_pack_input(None, None, 1, 3, 84, 84, 16, None) == -1
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are refused loudly everywhere on the product path."""
+    from models.util import create_model
+    from srb200 import ops, synthetic
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.pack_input(torch.zeros(1, 3, 84, 84))
+    opt = synthetic.default_opt(1)
+    net = synthetic.init_model(create_model, opt, 1).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(2, 3, 84, 84))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.subspace_factor(torch.zeros(60, 640))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "subspace-reg_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)
