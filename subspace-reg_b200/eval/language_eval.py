@@ -80,7 +80,13 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         raise NotImplementedError("classifier bias: the reference's bias branches are dead code (--no_linear_bias)")
     if opt.freeze_backbone_at != 1:
         raise NotImplementedError("freeze_backbone_at != 1 trains the backbone, which is outside the incremental-session path")
-    record = dict(sessions=[], timers=dict(train_s=0.0, score_s=0.0, backbone_imgs=0, steps=0, images_scored=0))
+    record = dict(sessions=[], timers=dict(train_s=0.0, score_s=0.0, backbone_imgs=0, steps=0, images_scored=0),
+                  phases=dict(setup=0.0, train_pass=0.0, head1=0.0, cache=0.0, head=0.0, score=0.0, memory=0.0))
+    ph = record['phases']
+
+    def _tick():
+        torch.cuda.synchronize()
+        return time.perf_counter()
     few_shot_finetune_incremental_test.last_record = record
     tm = record['timers']
 
@@ -198,10 +204,14 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         counters0 = next(iter(net.block_counters().values()))
 
         # ---- epoch 1: the session's only train-mode forward(s); BN running statistics move here ----
+        tp0 = _tick()
+        ph['setup'] += tp0 - t_train0
         f_train = net.features(support_xs_d)
         if has_mem:
             f_train = torch.cat([f_train, net.features(memory.data)], 0)
         tm['backbone_imgs'] += n_sup + n_mem
+        tp1 = _tick()
+        ph['train_pass'] += tp1 - tp0
         W = net.classifier.weight.data
         reserve = novel_weight_to_reserve.contiguous() if (opt.lmbd_reg_novel is not None and idx > 0) else None
         head = ops.HeadSession(
@@ -216,18 +226,23 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
             min_novel_epochs=opt.min_novel_epochs, max_novel_epochs=opt.max_novel_epochs)
         head.run(1)
         net.eval()                                  # validate()'s side effect after epoch 1
+        tp2 = _tick()
+        ph['head1'] += tp2 - tp1
 
         # ---- eval-mode feature cache: support | memory | queries of sessions 1..idx+1 | base batch ----
         parts = [support_xs_d] + ([memory.data] if has_mem else []) + novel_query_collection + [base_x]
         with torch.no_grad():
             cache = net.engine().eval_features(torch.cat(parts, 0))
         tm['backbone_imgs'] += cache.shape[0]
+        tp3 = _tick()
+        ph['cache'] += tp3 - tp2
         q_row0 = n_sup + n_mem
         b_row0 = q_row0 + sum(q.shape[0] for q in novel_query_collection)
 
         # ---- epochs 2.. on the device until the stopping rule fires ----
         while not head.stopped:
             head.run(max(opt.max_novel_epochs - head.epochs, 1), feat=cache, support_row0=0, memory_row0=n_sup)
+        ph['head'] += _tick() - tp3
         trace = torch.cat(head.traces, 0).numpy()
         epoch = head.epochs + 1
         torch.cuda.synchronize()
@@ -247,16 +262,19 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         # ---- scoring of the last epoch: validate (:321-326) + eval_base (:362-367) on cached features ----
         t0 = time.perf_counter()
         test_acc, query_ys_pred, query_logits = [], [], []
+        confusion = torch.zeros((100, 100), dtype=torch.int64, device=dev)   # (gold id, predicted id) of this session
         r0 = q_row0
         for qx, qy in zip(novel_query_collection, novel_query_collection_id):
-            a1, a5, loss_q, pred, raw = _score(net, cache[r0:r0 + qx.shape[0]], qy)
+            a1, a5, loss_q, pred, raw = _score(net, cache[r0:r0 + qx.shape[0]], qy, confusion)
             test_acc.append(a1[0])
             query_ys_pred.append(pred)
             query_logits.append(raw["logits"])
             r0 += qx.shape[0]
-        a1, _, _, base_pred, _ = _score(net, cache[b_row0:b_row0 + base_x.shape[0]], base_y)
+        a1, _, _, base_pred, _ = _score(net, cache[b_row0:b_row0 + base_x.shape[0]], base_y, confusion)
         acc_base_ = np.mean([a1[0].item()])
+        record['confusion'] = confusion
         tm['score_s'] += time.perf_counter() - t0
+        ph['score'] += time.perf_counter() - t0
         tm['images_scored'] += b_row0 - q_row0 + base_x.shape[0]
 
         if opt.memory_replay:

@@ -8,6 +8,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib as L
+from . import host_rng
 from . import ops
 
 SLOPE = 0.1
@@ -32,6 +33,7 @@ class BackboneEngine(object):
         self._folded = None      # per block: dict(w1, s1, w2, s2, w3, s3[, wd])
         self._raw = None         # per block: unscaled packed weights (train-mode pass)
         self._fold_key = None
+        self._staging = {}
 
     # ---------------------------------------------------------------- weight packing
     def _bn_key(self):
@@ -120,43 +122,67 @@ class BackboneEngine(object):
         return h
 
     # ---------------------------------------------------------------- train-mode pass (epoch 1 of a session)
-    def draw_masks(self, batch, counters):
-        """CPU-generator draws of one train-mode forward, in the reference's order (dropout after layerX.0,
-        DropBlock after layer3.1 / layer4.1; resnet_language.py:292-299, 311-325).  Returns per block
-        (keep uint8 NCHW [CUDA], scale) or None."""
-        masks = []
-        size = 84
-        for b in self.blocks:
-            size = size // b['pool']
-            shape = (batch, b['cout'], size, size)
-            if b['drop_block']:
-                bs = b['block_size']
-                nbt = counters[b['prefix']]
-                keep_rate = max(1.0 - DROP_RATE / (20 * 2000) * nbt, 1.0 - DROP_RATE)
-                gamma = (1 - keep_rate) / bs ** 2 * size ** 2 / (size - bs + 1) ** 2
-                seeds = torch.distributions.Bernoulli(gamma).sample((batch, b['cout'], size - (bs - 1), size - (bs - 1)))
+    def _pinned(self, key, shape):
+        """Reusable pinned staging buffer (uint8) + the event of its last H2D copy."""
+        n = 1
+        for d in shape:
+            n *= int(d)
+        ent = self._staging.get(key)
+        if ent is None or ent[2].numel() < n:
+            flat = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=True)
+            ent = [None, None, flat]
+            self._staging[key] = ent
+        if ent[1] is not None:
+            ent[1].synchronize()     # the previous copy out of this buffer must have finished before it is rewritten
+        ent[0] = ent[2][:n].view(shape)
+        return ent
+
+    def draw_mask(self, bi, batch, size, counters, device):
+        """Keep-mask of block `bi` for one train-mode forward, drawn from torch's CPU generator exactly like the
+        reference does at this point of the forward (F.dropout after layerX.0, DropBlock after layer3.1 / layer4.1;
+        resnet_language.py:292-299, 311-325).  -> (keep uint8 NCHW on `device`, scale)."""
+        b = self.blocks[bi]
+        shape = (batch, b['cout'], size, size)
+        if not b['drop_block']:
+            ent = self._pinned(('m', bi), shape)
+            host_rng.bernoulli_u8(shape, 1 - DROP_RATE, 0, out=ent[0])       # noise.bernoulli_(1 - p)
+            scale = float(torch.ones(1).div_(1 - DROP_RATE))                   # noise.div_(1 - p)
+        else:
+            bs = b['block_size']
+            nbt = counters[b['prefix']]
+            keep_rate = max(1.0 - DROP_RATE / (20 * 2000) * nbt, 1.0 - DROP_RATE)
+            gamma = (1 - keep_rate) / bs ** 2 * size ** 2 / (size - bs + 1) ** 2
+            seed_shape = (batch, b['cout'], size - (bs - 1), size - (bs - 1))
+            seeds, n_seed = host_rng.bernoulli_u8(seed_shape, gamma, 1)        # Bernoulli(gamma).sample(...)
+            ent = self._pinned(('m', bi), shape)
+            if bs == 1:
+                ent[0].copy_(1 - seeds)
+                kept = seeds.numel() - n_seed
+            else:
                 left, right = int((bs - 1) / 2), int(bs / 2)
                 padded = F.pad(seeds, (left, right, left, right))
-                if bs > 1 and bool(seeds.any()):
+                if n_seed > 0:
                     Hm, Wm = seeds.shape[2], seeds.shape[3]
                     for i in range(bs):
                         for j in range(bs):
                             padded[:, :, i:i + Hm, j:j + Wm] = torch.maximum(padded[:, :, i:i + Hm, j:j + Wm], seeds)
-                bm = 1 - padded
-                scale = float(bm.numel() / bm.sum())     # fp32 tensor in the reference (countM / count_ones)
-                masks.append(((bm != 0).to(torch.uint8), scale))
-            else:
-                m = F.dropout(torch.ones(shape), p=DROP_RATE, training=True)
-                masks.append(((m != 0).to(torch.uint8), float(m.max())))
-        return masks
+                ent[0].copy_(1 - padded)
+                kept = int(ent[0].sum())
+            # countM / count_ones: python int over an fp32 0-d tensor -> fp32 division
+            scale = float(torch.tensor(float(ent[0].numel()), dtype=torch.float32) / torch.tensor(float(kept), dtype=torch.float32))
+        keep = ent[0].to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        ent[1] = ev
+        return keep, scale
 
     def train_features(self, x, counters):
         """One train-mode forward (batch-stat BN, running-stat EMA in place, dropout / DropBlock) -> fp32 [B,640]."""
         self._ensure_raw()
         raw_w = self._raw[1]
         B = x.shape[0]
-        masks = self.draw_masks(B, counters)
         dev = x.device
+        size = x.shape[2]
         h = ops.pack_input(x.contiguous(), 16)
         nb = len(self.blocks)
 
@@ -176,12 +202,14 @@ class BackboneEngine(object):
             r2, mu2, is2 = conv_bn(h1, w['w2'], m.bn2, cout)
             h2 = ops.bn_apply(r2, mu2, is2, m.bn2.weight.detach(), m.bn2.bias.detach(), lrelu=True, slope=SLOPE)
             r3, mu3, is3 = conv_bn(h2, w['w3'], m.bn3, cout)
-            keep, scale = masks[bi]
-            keep = keep.to(dev, non_blocking=True)
-            pool = -1 if last and b['pool'] == 1 else (2 if b['pool'] == 2 else 0)
             if b['downsample']:
                 bnd = m.downsample[1]
                 rd, mud, isd = conv_bn(h, w['wd'], bnd, cout)
+            size = size // b['pool']
+            # drawn here, in forward order: the host RNG of block i overlaps the GPU work already queued for block i
+            keep, scale = self.draw_mask(bi, B, size, counters, dev)
+            pool = -1 if last and b['pool'] == 1 else (2 if b['pool'] == 2 else 0)
+            if b['downsample']:
                 h = ops.bn_apply(r3, mu3, is3, m.bn3.weight.detach(), m.bn3.bias.detach(), res_raw=rd,
                                  res_bn=(mud, isd, bnd.weight.detach(), bnd.bias.detach()), lrelu=True, slope=SLOPE,
                                  pool=pool, keep=keep, keep_scale=scale)

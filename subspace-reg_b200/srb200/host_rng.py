@@ -1,0 +1,76 @@
+"""Keep-masks of the train-mode epoch from PyTorch's CPU generator.
+
+The draws MUST be the ones the reference makes (F.dropout -> bernoulli_(1-p); Bernoulli(gamma).sample), in the same
+order, because the same generator later initialises the next session's classifier rows.  Two equivalent producers:
+torch itself (always correct, ~10 ns per element, serial) and sr_host_bernoulli (a vectorised replay of the same
+mt19937 stream from torch.get_rng_state()).  The replay is used only after it has reproduced torch on a sample that
+crosses several generator blocks; otherwise every call goes to torch.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_replay_ok = None
+
+
+def _torch_draw(shape, p, kind):
+    if kind == 0:
+        return torch.empty(shape, dtype=torch.uint8).bernoulli_(p)
+    probs = torch.tensor(p)                       # float32, like torch.distributions.Bernoulli(gamma).probs
+    return torch.bernoulli(probs.expand(shape)).to(torch.uint8)
+
+
+def _replay_draw(shape, p, kind, out=None):
+    n = 1
+    for s in shape:
+        n *= int(s)
+    state = torch.get_rng_state()
+    if out is None:
+        out = torch.empty(shape, dtype=torch.uint8)
+    ones = L.load().sr_host_bernoulli(C.c_void_p(state.data_ptr()), state.numel(), kind, float(p), n,
+                                      C.c_void_p(out.data_ptr()))
+    if ones < 0:
+        raise RuntimeError("srb200: unexpected torch CPU generator state layout")
+    torch.set_rng_state(state)
+    return out, int(ones)
+
+
+def _self_check():
+    saved = torch.get_rng_state()
+    ok = True
+    try:
+        for kind, p in ((0, 0.9), (1, 0.0123), (0, 0.5), (1, 0.5)):
+            torch.manual_seed(1234 + kind)
+            torch.rand(7)                          # start mid-block
+            s0 = torch.get_rng_state()
+            a = _torch_draw((3, 1777), p, kind)
+            sa = torch.get_rng_state()
+            torch.set_rng_state(s0)
+            b, ones = _replay_draw((3, 1777), p, kind)
+            sb = torch.get_rng_state()
+            ok = ok and torch.equal(a, b) and torch.equal(sa, sb) and ones == int(a.sum())
+    except Exception:
+        ok = False
+    torch.set_rng_state(saved)
+    return ok
+
+
+def replay_available():
+    global _replay_ok
+    if _replay_ok is None:
+        _replay_ok = _self_check()
+    return _replay_ok
+
+
+def bernoulli_u8(shape, p, kind, out=None):
+    """uint8 CPU tensor of draws (1 with probability p) + number of ones, consuming torch's CPU generator exactly like
+    kind 0: tensor.bernoulli_(p)   kind 1: torch.bernoulli(torch.tensor(p).expand(shape))."""
+    if replay_available():
+        return _replay_draw(shape, p, kind, out)
+    t = _torch_draw(shape, p, kind)
+    if out is not None:
+        out.copy_(t)
+        t = out
+    return t, int(t.sum())

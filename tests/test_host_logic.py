@@ -1,0 +1,137 @@
+"""Host-side logic that needs no GPU: drop-in module surface, RNG parity of model construction, synthetic world,
+label-embedding loader, session bookkeeping helpers."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+
+def test_model_surface_and_state_dict_keys():
+    """State-dict key set of the reference ResNet-18: 22 convs + 44 BN affine + classifier.weight, 66 BN
+    buffers; same RNG consumption as the oracle's restatement of ResNet.__init__."""
+    import models
+    from models.util import create_model
+    from oracle import init as oinit
+    from srb200 import synthetic
+    assert models.model_pool == ['resnet12', 'resnet18'] and set(models.model_dict) == set(models.model_pool)
+    opt = synthetic.default_opt(3)
+    net = synthetic.init_model(create_model, opt, 3)
+    sd = net.state_dict()
+    ref = oinit.init_state_dict(3)
+    assert list(sd.keys()) == list(ref.keys())
+    params = dict(net.named_parameters())
+    assert len(params) == 22 + 44 + 1 and 'classifier.weight' in params and 'classifier.bias' not in sd
+    assert sum(1 for k in sd if 'running_' in k or 'num_batches' in k) == 66
+    for k in sd:
+        assert torch.equal(sd[k], ref[k]), k
+    assert net.num_classes == 60 and net.classifier.weight.shape == (60, 640)
+
+
+def test_augment_and_base_weights_cpu():
+    from models.util import create_model
+    from srb200 import synthetic
+    opt = synthetic.default_opt(1)
+    net = synthetic.init_model(create_model, opt, 1)
+    w0, b0 = net._get_base_weights()
+    assert b0 is None and not w0.requires_grad and w0.data_ptr() != net.classifier.weight.data_ptr()
+    torch.manual_seed(7)
+    net.augment_base_classifier_(5)
+    torch.manual_seed(7)
+    expect = torch.nn.Linear(640, 5, bias=False).weight.detach()
+    W = net.classifier.weight
+    assert W.shape == (65, 640) and W.requires_grad and isinstance(W, torch.nn.Parameter)
+    assert torch.equal(W[:60].detach(), w0) and torch.equal(W[60:].detach(), expect)
+    assert net.num_classes == 60          # stays 60, as in the reference
+    assert [n for n, _ in net.named_parameters() if n.startswith('classifier')] == ['classifier.weight']
+    import copy
+    net2 = copy.deepcopy(net)
+    assert torch.equal(net2.classifier.weight, net.classifier.weight)
+    counters = net.block_counters()
+    assert list(counters) == ['layer1.0', 'layer2.0', 'layer3.0', 'layer3.1', 'layer4.0', 'layer4.1']
+    net.advance_block_counters(7)
+    assert set(net.block_counters().values()) == {7}
+
+
+def test_block_plan_matches_reference_quirks():
+    from models.util import create_model
+    from oracle import backbone as obb
+    from srb200 import synthetic
+    net = synthetic.init_model(create_model, synthetic.default_opt(1), 1)
+    plan = obb.block_plan('resnet18', True)
+    mine = net._blocks()
+    for a, b in zip(plan, mine):
+        for k in ('prefix', 'cin', 'cout', 'pool', 'downsample', 'drop_block', 'block_size'):
+            assert a[k] == b[k], (a['prefix'], k)
+    # layerX.0 of a two-block stage is plain dropout (use_se lands in the drop_block slot), the last block is DropBlock
+    assert [b['drop_block'] for b in plan] == [False, False, False, True, False, True]
+    opt5 = synthetic.default_opt(1, no_dropblock=False)
+    net5 = synthetic.init_model(create_model, opt5, 1)
+    assert [b['block_size'] for b in net5._blocks()] == [1, 1, 1, 5, 1, 5]
+
+
+def test_synthetic_world_contract():
+    from srb200 import synthetic
+    w = synthetic.make_world(4, n_sessions=3, n_base_batch=16)
+    base, sessions = synthetic.class_split(4)
+    assert len(base) == 60 and len(set(base)) == 60 and all(len(s) == 5 for s in sessions)
+    assert not (set(base) & set(np.concatenate(sessions)))
+    sx, sy, qx, qy = w.meta_valloader.batches[1]
+    assert sx.shape == (1, 125, 3, 84, 84) and qx.shape == (1, 125, 3, 84, 84)
+    assert np.array_equal(sy.view(-1).numpy(), np.tile(np.repeat(sessions[1], 5), 5))
+    assert np.array_equal(qy.view(-1).numpy(), np.repeat(sessions[1], 25))
+    l2h = w.base_val_loader.dataset.label2human
+    assert len(l2h) == 100 and sum(1 for n in l2h if n) == 60
+    w2 = synthetic.make_world(4, n_sessions=3, n_base_batch=16)
+    assert torch.equal(w2.meta_valloader.batches[2][0], w.meta_valloader.batches[2][0])      # deterministic
+    from eval.util import drop_a_dim, get_vocabs
+    a, b, c, d = drop_a_dim(w.meta_valloader.batches[0])
+    assert a.shape == (125, 3, 84, 84) and b.dtype == np.int64
+    vb, va, vn, o2i = get_vocabs(w.base_val_loader, w.meta_valloader, d)
+    assert len(vb) == 60 and len(vn) == 5 and sorted(o2i.values()) == [60, 61, 62, 63, 64]
+
+
+def test_get_embeds_matches_oracle(word_embed_dir):
+    from models.util import get_embeds
+    from oracle import regularizer as rg
+    from srb200 import synthetic
+    path = os.path.join(word_embed_dir, "miniImageNet_dim500.pickle")
+    a = get_embeds(path, synthetic.LABELS)
+    b = rg.get_embeds(path, synthetic.LABELS)
+    assert a.dtype == b.dtype == torch.float64 and torch.equal(a, b)
+    assert float(a[synthetic.LABELS.index('komondor')].abs().sum()) == 0.0
+
+
+def test_percent_rounding_like_reference():
+    from eval.util import percent
+    from oracle.session import accuracy
+    out = torch.zeros(125, 7)
+    out[:, 3] = 1.0
+    tgt = torch.full((125,), 3, dtype=torch.int64)
+    tgt[:38] = 2
+    ref = accuracy(out, tgt, (1,))[0]
+    assert torch.equal(percent(87, 125), ref)
+
+
+def test_memory_dropin():
+    from dataset.memory import Memory
+    m = Memory()
+    assert len(m) == 0
+    m.additems(torch.zeros(25, 3, 4, 4), torch.arange(25))
+    m.additems(torch.ones(25, 3, 4, 4), torch.arange(25))
+    assert len(m) == 50 and m.data.shape == (50, 3, 4, 4) and m[30][1].item() == 5
+
+
+def test_unsupported_options_fail_loudly():
+    from eval.language_eval import few_shot_finetune_incremental_test
+    from models.util import create_model
+    from srb200 import synthetic
+    w = synthetic.make_world(1, n_sessions=1, n_base_batch=4)
+    net = synthetic.init_model(create_model, w.opt, 1)
+    w.opt.track_weights = True
+    with pytest.raises(NotImplementedError):
+        few_shot_finetune_incremental_test(net, {}, None, w.meta_valloader, w.base_val_loader, w.opt)
+    w.opt.track_weights = False
+    w.opt.freeze_backbone_at = 3
+    with pytest.raises(NotImplementedError):
+        few_shot_finetune_incremental_test(net, {}, None, w.meta_valloader, w.base_val_loader, w.opt)
