@@ -1,0 +1,74 @@
+"""Kernel-level parity on the GPU through the C ABI (srb200.ops -> libsrb200.so): each case compares one kernel with a
+plain fp32 / fp64 PyTorch statement of the same op on the same device.  Tolerances: bf16-output convolutions 2^-8 of the
+output range (one bf16 rounding), fp32-output paths 2e-5, fp32 head / projection 1e-5 (north_star)."""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+@pytest.mark.parametrize("group", ["conv_basic", "conv_k", "conv_epi", "conv_train", "head", "factor"])
+def test_kernel_group(group):
+    import diag
+    assert getattr(diag, "group_" + group)()
+
+
+def test_head_stress_config5():
+    """BASELINE config 5 shapes: 1000 base + 100 novel classes, 100-shot, 512-d.  With 1000 base rows in 512-d the span
+    is everything: the projector is the identity and the regulariser vanishes; n_base = 256 is the
+    non-trivial projection."""
+    import diag
+    from srb200 import _lib as L
+    assert diag.head_case("config5 P=I", 10000, 0, 1000, 0, 100, 512, L.SR_PULL_PROJECT, epochs=3)
+    assert diag.head_case("config5 nb256", 10000, 0, 256, 0, 100, 512, L.SR_PULL_PROJECT, epochs=3)
+
+
+def test_eval_logits_properties():
+    """Scoring: predictions equal torch.argmax, hit counts / CE equal the reference's accuracy() + CrossEntropyLoss, the
+    confusion matrix sums to n and its trace equals the top-1 hits."""
+    from srb200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n, d, Cn = 16384, 512, 1100
+    X = torch.randn(n, d, device="cuda", generator=g)
+    W = torch.randn(Cn, d, device="cuda", generator=g) / d ** 0.5
+    y = torch.randint(0, Cn, (n,), device="cuda", generator=g)
+    conf = torch.zeros(Cn, Cn, dtype=torch.int64, device="cuda")
+    r = ops.eval_logits(X, W, y, conf)
+    Z = X.double() @ W.double().t()
+    assert (r["logits"].double() - Z).abs().max().item() < 1e-4
+    Zf = r["logits"]
+    assert (r["pred"].long() == Zf.argmax(1)).all()
+    top5 = Zf.topk(5, 1).indices
+    assert int(r["counts"][0]) == int((Zf.argmax(1) == y).sum())
+    assert int(r["counts"][1]) == int((top5 == y[:, None]).any(1).sum())
+    ce = torch.nn.functional.cross_entropy(Zf.double(), y, reduction="sum").item()
+    assert abs(r["loss_sum"].item() - ce) < 1e-4 * ce
+    assert int(conf.sum()) == n and int(conf.diag().sum()) == int(r["counts"][0])
+
+
+def test_backbone_linearity_in_last_residual():
+    """Size-independent property at full batch size: eval features are deterministic and independent of batch
+    composition (per-image independence of the eval-mode pass that the feature cache relies on)."""
+    from models.util import create_model
+    from srb200 import synthetic
+    net = synthetic.init_model(create_model, synthetic.default_opt(1), 1).cuda().eval()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(300, 3, 84, 84, device="cuda", generator=g)
+    with torch.no_grad():
+        f_all = net.features(x)
+        f_part = net.features(x[37:150].contiguous())
+        f_again = net.features(x)
+    assert torch.equal(f_all, f_again)
+    assert torch.equal(f_all[37:150], f_part)
