@@ -12,7 +12,9 @@
 //   N (out channels) <= 256 per CTA, both sub-tiles share every B (weight) stage.
 //   K                one pipeline stage = one tap x one KC-channel block (KC = 64/32/16 <-> 128/64/32-byte swizzle).
 //   accumulators     2 x N fp32 columns of TMEM, written by tcgen05.mma (cta_group::1, M = 128).
-//   warps            0: TMA producer (one lane)   1: TMEM alloc + MMA issue (one lane)   2-5: epilogue
+//   warps            0: TMA producer (one lane)   1: TMEM alloc + MMA issue (one lane)   2-9: epilogue
+//   schedule         persistent: one CTA per SM walks (pixel tile, channel split) items; the producer prefetches across
+//                    tile boundaries and up to four TMEM accumulator stages let epilogue(i) overlap mainloop(i+1)
 //   epilogue         TMEM -> registers -> (+shift, +residual, LeakyReLU) -> bf16 NHWC, optionally through a shared
 //                    staging tile for MaxPool2d(2) / global average; or raw fp32 + per-channel sum / sum-of-squares
 //                    for train-mode BatchNorm.
@@ -28,8 +30,9 @@ namespace {
 
 using namespace srb;
 
-constexpr int kThreads = 192;       // 6 warps
-constexpr int kEpiThreads = 128;    // warps 2..5
+constexpr int kThreads = 320;       // 10 warps
+constexpr int kEpiWarps = 8;        // warps 2..9
+constexpr int kEpiThreads = 256;
 constexpr int kSubRows = 128;       // UMMA M
 constexpr int kStagePitchBf16 = 80; // bytes per staged row (32 bf16 + pad, conflict-free 16-byte accesses)
 constexpr int kStagePitchF32 = 33;  // floats per staged row (32 fp32 + 1)
@@ -49,6 +52,8 @@ struct ConvParams {
     int B, H, W, Cout;
     int TW, TH, TN, stack_h;
     int tiles_w, tiles_h;
+    int n_splits, total_tiles;
+    int acc_stages;
     int n_cta;
     int rows_sub;
     int stages, stage_bytes, a_slot;
@@ -75,10 +80,13 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
     return *reinterpret_cast<uint32_t*>(&r);
 }
 
-// After the call, lane l holds the sum over the 32 lanes of element l of v[] (v is clobbered).
-__device__ __forceinline__ float warp_transpose_sum(float* v, int lane) {
+// 16-value variant: first fold lane pairs (l, l^16), then transpose-reduce over 16 lanes.
+// After the call lanes 0..15 (and their mirrors 16..31) hold the sum over the 32 lanes of element (lane & 15).
+__device__ __forceinline__ float warp_transpose_sum16(float* v, int lane) {
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
+    for (int k = 0; k < 16; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) {
         const bool upper = (lane & off) != 0;
 #pragma unroll
         for (int k = 0; k < off; ++k) {
@@ -90,41 +98,58 @@ __device__ __forceinline__ float warp_transpose_sum(float* v, int lane) {
     return v[0];
 }
 
+struct TileCoord {
+    int w0, h0, n0, co0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+    // n-split fastest: CTAs that run concurrently share the same activation tile in L2
+    const int nsp = tile % p.n_splits;
+    int t = tile / p.n_splits;
+    const int tw = t % p.tiles_w;
+    t /= p.tiles_w;
+    const int th = t % p.tiles_h;
+    const int tn = t / p.tiles_h;
+    TileCoord c;
+    c.w0 = tw * p.TW;
+    c.h0 = th * (p.stack_h ? 2 * p.TH : p.TH);
+    c.n0 = tn * (p.stack_h ? p.TN : 2 * p.TN);
+    c.co0 = nsp * p.n_cta;
+    return c;
+}
+
+// Persistent kernel: one CTA per SM loops over (pixel tile, channel split) work items.  The TMA producer runs ahead across
+// tile boundaries, the MMA warp only waits for a free TMEM accumulator stage, so the epilogue of tile i overlaps the
+// loads (and, when TMEM has room for a second accumulator, the MMAs) of tile i+1.
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // Dynamic shared memory is only guaranteed 16-byte aligned; swizzle-128B tiles need 1024.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* staging = smem + (size_t)p.stages * p.stage_bytes;
 
     __shared__ uint64_t full_bar[16];
     __shared__ uint64_t empty_bar[16];
-    __shared__ uint64_t tmem_full_bar;
+    __shared__ uint64_t tmem_full_bar[4];
+    __shared__ uint64_t tmem_empty_bar[4];
     __shared__ uint32_t tmem_slot;
-    __shared__ float s_shift[256];
     __shared__ float s_sum[256];
     __shared__ float s_sq[256];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    // ---- tile coordinates ----
-    int t = blockIdx.x;
-    const int tw = t % p.tiles_w;
-    t /= p.tiles_w;
-    const int th = t % p.tiles_h;
-    const int tn = t / p.tiles_h;
-    const int w0 = tw * p.TW;
-    const int h0 = th * (p.stack_h ? 2 * p.TH : p.TH);
-    const int n0 = tn * (p.stack_h ? p.TN : 2 * p.TN);
     const int sub_dh = p.stack_h ? p.TH : 0;
     const int sub_dn = p.stack_h ? 0 : p.TN;
-    const int co0 = blockIdx.y * p.n_cta;
+    const int acc_cols = 2 * p.n_cta;  // TMEM columns of one accumulator stage (two sub-tiles)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.stages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
-        mbar_init(&tmem_full_bar, 1);
+        for (int i = 0; i < p.acc_stages; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], kEpiWarps);
+        }
         mbar_fence_init();
         for (int i = 0; i < p.n_panels; ++i) {
             tma_prefetch_desc(&p.panel[i].tmA);
@@ -135,14 +160,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         tmem_alloc_dyn(&tmem_slot, (uint32_t)p.tmem_cols);
         tmem_relinquish();
     }
-    if (threadIdx.x >= 64) {
-        const int et = threadIdx.x - 64;
-        for (int i = et; i < p.n_cta; i += kEpiThreads) {
-            s_shift[i] = p.shift ? p.shift[co0 + i] : 0.f;
-            s_sum[i] = 0.f;
-            s_sq[i] = 0.f;
-        }
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -152,23 +169,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         // ================= TMA producer =================
         if (lane == 0) {
             int it = 0;
-            for (int pi = 0; pi < p.n_panels; ++pi) {
-                const PanelDev& pn = p.panel[pi];
-                const int kc = pn.kc_bytes >> 1;
-                const uint32_t tx = (uint32_t)(2 * p.rows_sub + p.n_cta) * (uint32_t)pn.kc_bytes;
-                for (int tap = 0; tap < pn.taps; ++tap) {
-                    const int dh = pn.taps == 9 ? tap / 3 - 1 : 0;
-                    const int dw = pn.taps == 9 ? tap % 3 - 1 : 0;
-                    for (int cb = 0; cb < pn.ncb; ++cb, ++it) {
-                        const int s = it % p.stages;
-                        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                        mbar_wait(&empty_bar[s], ph ^ 1u);
-                        uint8_t* st = smem + (size_t)s * p.stage_bytes;
-                        mbar_expect_tx(&full_bar[s], tx);
-                        tma_load_4d(st, &pn.tmA, &full_bar[s], cb * kc, w0 + dw, h0 + dh, n0);
-                        tma_load_4d(st + p.a_slot, &pn.tmA, &full_bar[s], cb * kc, w0 + dw, h0 + dh + sub_dh,
-                                    n0 + sub_dn);
-                        tma_load_2d(st + 2 * p.a_slot, &pn.tmB, &full_bar[s], tap * pn.cin_pad + cb * kc, co0);
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord tc = decode_tile(p, tile);
+                for (int pi = 0; pi < p.n_panels; ++pi) {
+                    const PanelDev& pn = p.panel[pi];
+                    const int kc = pn.kc_bytes >> 1;
+                    const uint32_t tx = (uint32_t)(2 * p.rows_sub + p.n_cta) * (uint32_t)pn.kc_bytes;
+                    for (int tap = 0; tap < pn.taps; ++tap) {
+                        const int dh = pn.taps == 9 ? tap / 3 - 1 : 0;
+                        const int dw = pn.taps == 9 ? tap % 3 - 1 : 0;
+                        for (int cb = 0; cb < pn.ncb; ++cb, ++it) {
+                            const int s = it % p.stages;
+                            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                            mbar_wait(&empty_bar[s], ph ^ 1u);
+                            uint8_t* st = smem + (size_t)s * p.stage_bytes;
+                            mbar_expect_tx(&full_bar[s], tx);
+                            tma_load_4d(st, &pn.tmA, &full_bar[s], cb * kc, tc.w0 + dw, tc.h0 + dh, tc.n0);
+                            tma_load_4d(st + p.a_slot, &pn.tmA, &full_bar[s], cb * kc, tc.w0 + dw, tc.h0 + dh + sub_dh,
+                                        tc.n0 + sub_dn);
+                            tma_load_2d(st + 2 * p.a_slot, &pn.tmB, &full_bar[s], tap * pn.cin_pad + cb * kc, tc.co0);
+                        }
                     }
                 }
             }
@@ -177,194 +197,231 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         // ================= MMA issuer =================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(kSubRows, (uint32_t)p.n_cta);
-            int it = 0;
-            for (int pi = 0; pi < p.n_panels; ++pi) {
-                const PanelDev& pn = p.panel[pi];
-                const int ksteps = pn.kc_bytes >> 5;  // UMMA K = 16 bf16 = 32 bytes
-                const int nk = pn.taps * pn.ncb;
-                for (int kb = 0; kb < nk; ++kb, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                    mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
-                    for (int sub = 0; sub < 2; ++sub) {
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t da = umma_smem_desc(st + sub * p.a_slot + ks * 32, (uint32_t)pn.kc_bytes);
-                            const uint64_t db = umma_smem_desc(st + 2 * p.a_slot + ks * 32, (uint32_t)pn.kc_bytes);
-                            umma_f16(tmem_base + (uint32_t)(sub * p.n_cta), da, db, idesc,
-                                     (it > 0 || ks > 0) ? 1u : 0u);
+            int it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+                const int as = t % p.acc_stages;
+                const uint32_t use = (uint32_t)(t / p.acc_stages);
+                mbar_wait(&tmem_empty_bar[as], (use & 1u) ^ 1u);  // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(as * acc_cols);
+                bool first = true;
+                for (int pi = 0; pi < p.n_panels; ++pi) {
+                    const PanelDev& pn = p.panel[pi];
+                    const int ksteps = pn.kc_bytes >> 5;  // UMMA K = 16 bf16 = 32 bytes
+                    const int nk = pn.taps * pn.ncb;
+                    for (int kb = 0; kb < nk; ++kb, ++it) {
+                        const int s = it % p.stages;
+                        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
+                        for (int sub = 0; sub < 2; ++sub) {
+                            for (int ks = 0; ks < ksteps; ++ks) {
+                                const uint64_t da = umma_smem_desc(st + sub * p.a_slot + ks * 32, (uint32_t)pn.kc_bytes);
+                                const uint64_t db = umma_smem_desc(st + 2 * p.a_slot + ks * 32, (uint32_t)pn.kc_bytes);
+                                umma_f16(acc + (uint32_t)(sub * p.n_cta), da, db, idesc, (first && ks == 0) ? 0u : 1u);
+                            }
                         }
+                        first = false;
+                        umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
                     }
-                    umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
                 }
+                umma_commit(&tmem_full_bar[as]);
             }
-            umma_commit(&tmem_full_bar);
         }
     } else {
-        // ================= epilogue (warps 2..5) =================
+        // ================= epilogue (warps 2..9): two warps per TMEM lane quarter, 16 columns each =================
         const int et = threadIdx.x - 64;
-        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;       // which 16 of the 32 columns of a chunk
         const int m = q * 32 + lane;
-        mbar_wait(&tmem_full_bar, 0);
-        tc_fence_after();
-
         const int hw_sub = p.TH * p.TW;
         const int nl = m / hw_sub;
         const int rem = m - nl * hw_sub;
         const int hl = rem / p.TW;
         const int wl = rem - hl * p.TW;
         const int nchunks = p.n_cta >> 5;
-
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int cbase = co0 + ch * 32;
-#pragma unroll 1
-            for (int sub = 0; sub < 2; ++sub) {
-                const int n = n0 + nl + sub * sub_dn;
-                const int h = h0 + hl + sub * sub_dh;
-                const int w = w0 + wl;
-                const bool valid = (m < p.rows_sub) && (n < p.B) && (h < p.H);
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * p.n_cta + ch * 32), v);
-                tmem_ld_wait();
-                const size_t pix = ((size_t)n * p.H + h) * p.W + w;
-
-                if (p.epi == SR_EPI_RAW_STATS) {
-                    if (valid) {
-                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Cout + cbase);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                    }
-                    float sq[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-                    const float tsum = warp_transpose_sum(v, lane);
-                    const float tsq = warp_transpose_sum(sq, lane);
-                    atomicAdd(&s_sum[ch * 32 + lane], tsum);
-                    atomicAdd(&s_sq[ch * 32 + lane], tsq);
-                    continue;
+        int t = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+            const TileCoord tc = decode_tile(p, tile);
+            const int as = t % p.acc_stages;
+            const uint32_t use = (uint32_t)(t / p.acc_stages);
+            if (p.epi == SR_EPI_RAW_STATS) {
+                for (int i = et; i < p.n_cta; i += kEpiThreads) {
+                    s_sum[i] = 0.f;
+                    s_sq[i] = 0.f;
                 }
+                named_bar_sync(1, kEpiThreads);
+            }
+            mbar_wait(&tmem_full_bar[as], use & 1u);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols);
 
-                // shift (+ residual) + LeakyReLU
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const int c16 = ch * 32 + half * 16;     // first of this thread's 16 channels inside the CTA's N range
+                const int cbase = tc.co0 + c16;
+#pragma unroll 1
+                for (int sub = 0; sub < 2; ++sub) {
+                    const int n = tc.n0 + nl + sub * sub_dn;
+                    const int h = tc.h0 + hl + sub * sub_dh;
+                    const int w = tc.w0 + wl;
+                    const bool valid = (m < p.rows_sub) && (n < p.B) && (h < p.H);
+                    float v[16];
+                    tmem_ld16(acc + (uint32_t)(sub * p.n_cta + c16), v);
+                    tmem_ld_wait();
+                    const size_t pix = ((size_t)n * p.H + h) * p.W + w;
+
+                    if (p.epi == SR_EPI_RAW_STATS) {
+                        if (valid) {
+                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Cout + cbase);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += s_shift[ch * 32 + j];
-                if (p.residual != nullptr && valid) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + cbase);
+                            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint4 r = __ldg(rp + j);
-                        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+                            for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                        }
+                        float sq[16];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[k]);
-                            v[8 * j + 2 * k] += __bfloat162float(b2.x);
-                            v[8 * j + 2 * k + 1] += __bfloat162float(b2.y);
+                        for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+                        const float tsum = warp_transpose_sum16(v, lane);
+                        const float tsq = warp_transpose_sum16(sq, lane);
+                        if (lane < 16) {
+                            atomicAdd(&s_sum[c16 + lane], tsum);
+                            atomicAdd(&s_sq[c16 + lane], tsq);
+                        }
+                        continue;
+                    }
+
+                    // shift (+ residual) + LeakyReLU
+                    if (p.shift != nullptr) {
+                        const float4* sp = reinterpret_cast<const float4*>(p.shift + cbase);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 s4 = __ldg(sp + j);
+                            v[4 * j] += s4.x; v[4 * j + 1] += s4.y; v[4 * j + 2] += s4.z; v[4 * j + 3] += s4.w;
                         }
                     }
-                }
+                    if (p.residual != nullptr && valid) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + cbase);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = lrelu(v[j], p.slope);
+                        for (int j = 0; j < 2; ++j) {
+                            const uint4 r = __ldg(rp + j);
+                            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[k]);
+                                v[8 * j + 2 * k] += __bfloat162float(b2.x);
+                                v[8 * j + 2 * k + 1] += __bfloat162float(b2.y);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j], p.slope);
 
-                if (p.epi == SR_EPI_ACT) {
-                    if (valid) {
-                        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + cbase);
+                    if (p.epi == SR_EPI_ACT) {
+                        if (valid) {
+                            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + cbase);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
+                            for (int j = 0; j < 2; ++j)
+                                dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                    pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                        }
+                    } else if (p.epi == SR_EPI_ACT_POOL2) {
+                        uint4* dst = reinterpret_cast<uint4*>(staging + (size_t)(sub * kSubRows + m) * kStagePitchBf16 + half * 32);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
                             dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                                                 pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                    } else {  // SR_EPI_ACT_AVG
+                        float* dst = reinterpret_cast<float*>(staging) + (size_t)(sub * kSubRows + m) * kStagePitchF32 + half * 16;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) dst[j] = v[j];
                     }
-                } else if (p.epi == SR_EPI_ACT_POOL2) {
-                    uint4* dst = reinterpret_cast<uint4*>(smem + (size_t)(sub * kSubRows + m) * kStagePitchBf16);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                } else {  // SR_EPI_ACT_AVG
-                    float* dst = reinterpret_cast<float*>(smem) + (size_t)(sub * kSubRows + m) * kStagePitchF32;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) dst[j] = v[j];
                 }
-            }
 
-            if (p.epi == SR_EPI_ACT_POOL2) {
-                named_bar_sync(1, kEpiThreads);
-                const int Wp = p.TW >> 1;
-                const int Hp = p.stack_h ? p.TH : (p.TH >> 1);
-                const int imgs = p.stack_h ? 1 : 2 * p.TN;
-                const int items = imgs * Hp * Wp * 4;
-                for (int item = et; item < items; item += kEpiThreads) {
-                    const int g = item & 3;
-                    int pp = item >> 2;
-                    const int pw = pp % Wp;
-                    pp /= Wp;
-                    const int ph = pp % Hp;
-                    const int img = pp / Hp;
-                    const int n = n0 + img;
-                    const int hp = (h0 >> 1) + ph;
-                    const int wp = (w0 >> 1) + pw;
-                    if (n >= p.B || hp >= p.Ho || wp >= p.Wo) continue;
-                    uint4 acc = make_uint4(0, 0, 0, 0);
+                if (p.epi == SR_EPI_ACT_POOL2) {
+                    named_bar_sync(1, kEpiThreads);
+                    const int Wp = p.TW >> 1;
+                    const int Hp = p.stack_h ? p.TH : (p.TH >> 1);
+                    const int imgs = p.stack_h ? 1 : 2 * p.TN;
+                    const int items = imgs * Hp * Wp * 4;
+                    for (int item = et; item < items; item += kEpiThreads) {
+                        const int g = item & 3;
+                        int pp = item >> 2;
+                        const int pw = pp % Wp;
+                        pp /= Wp;
+                        const int ph = pp % Hp;
+                        const int img = pp / Hp;
+                        const int n = tc.n0 + img;
+                        const int hp = (tc.h0 >> 1) + ph;
+                        const int wp = (tc.w0 >> 1) + pw;
+                        if (n >= p.B || hp >= p.Ho || wp >= p.Wo) continue;
+                        uint4 acc4 = make_uint4(0, 0, 0, 0);
 #pragma unroll
-                    for (int dy = 0; dy < 2; ++dy) {
+                        for (int dy = 0; dy < 2; ++dy) {
 #pragma unroll
-                        for (int dx = 0; dx < 2; ++dx) {
-                            const int hh = 2 * ph + dy;
-                            const int ww = 2 * pw + dx;
-                            int sub, hloc, nloc;
-                            if (p.stack_h) {
-                                sub = hh >= p.TH ? 1 : 0;
-                                hloc = hh - sub * p.TH;
-                                nloc = 0;
-                            } else {
-                                sub = img >= p.TN ? 1 : 0;
-                                nloc = img - sub * p.TN;
-                                hloc = hh;
-                            }
-                            const int mrow = sub * kSubRows + (nloc * p.TH + hloc) * p.TW + ww;
-                            const uint4 x = *reinterpret_cast<const uint4*>(smem + (size_t)mrow * kStagePitchBf16 + g * 16);
-                            if (dy == 0 && dx == 0) {
-                                acc = x;
-                            } else {
-                                acc.x = max_bf16x2(acc.x, x.x);
-                                acc.y = max_bf16x2(acc.y, x.y);
-                                acc.z = max_bf16x2(acc.z, x.z);
-                                acc.w = max_bf16x2(acc.w, x.w);
+                            for (int dx = 0; dx < 2; ++dx) {
+                                const int hh = 2 * ph + dy;
+                                const int ww = 2 * pw + dx;
+                                int sub, hloc, nloc;
+                                if (p.stack_h) {
+                                    sub = hh >= p.TH ? 1 : 0;
+                                    hloc = hh - sub * p.TH;
+                                    nloc = 0;
+                                } else {
+                                    sub = img >= p.TN ? 1 : 0;
+                                    nloc = img - sub * p.TN;
+                                    hloc = hh;
+                                }
+                                const int mrow = sub * kSubRows + (nloc * p.TH + hloc) * p.TW + ww;
+                                const uint4 x = *reinterpret_cast<const uint4*>(staging + (size_t)mrow * kStagePitchBf16 + g * 16);
+                                if (dy == 0 && dx == 0) {
+                                    acc4 = x;
+                                } else {
+                                    acc4.x = max_bf16x2(acc4.x, x.x);
+                                    acc4.y = max_bf16x2(acc4.y, x.y);
+                                    acc4.z = max_bf16x2(acc4.z, x.z);
+                                    acc4.w = max_bf16x2(acc4.w, x.w);
+                                }
                             }
                         }
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                           (((size_t)n * p.Ho + hp) * p.Wo + wp) * p.Cout + tc.co0 + ch * 32 + g * 8;
+                        *reinterpret_cast<uint4*>(o) = acc4;
                     }
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                       (((size_t)n * p.Ho + hp) * p.Wo + wp) * p.Cout + cbase + g * 8;
-                    *reinterpret_cast<uint4*>(o) = acc;
+                    named_bar_sync(1, kEpiThreads);
+                } else if (p.epi == SR_EPI_ACT_AVG) {
+                    named_bar_sync(1, kEpiThreads);
+                    const int imgs = 2 * p.TN;
+                    const float* stg = reinterpret_cast<const float*>(staging);
+                    for (int item = et; item < imgs * 32; item += kEpiThreads) {
+                        const int j = item & 31;
+                        const int img = item >> 5;
+                        const int n = tc.n0 + img;
+                        if (n >= p.B) continue;
+                        const int sub = img >= p.TN ? 1 : 0;
+                        const int nloc = img - sub * p.TN;
+                        const float* src = stg + (size_t)(sub * kSubRows + nloc * hw_sub) * kStagePitchF32 + j;
+                        float a = 0.f;
+                        for (int r = 0; r < hw_sub; ++r) a += src[(size_t)r * kStagePitchF32];
+                        reinterpret_cast<float*>(p.out)[(size_t)n * p.Cout + tc.co0 + ch * 32 + j] = a / (float)hw_sub;
+                    }
+                    named_bar_sync(1, kEpiThreads);
                 }
-                named_bar_sync(1, kEpiThreads);
-            } else if (p.epi == SR_EPI_ACT_AVG) {
-                named_bar_sync(1, kEpiThreads);
-                const int imgs = 2 * p.TN;
-                const float* stg = reinterpret_cast<const float*>(smem);
-                for (int item = et; item < imgs * 32; item += kEpiThreads) {
-                    const int j = item & 31;
-                    const int img = item >> 5;
-                    const int n = n0 + img;
-                    if (n >= p.B) continue;
-                    const int sub = img >= p.TN ? 1 : 0;
-                    const int nloc = img - sub * p.TN;
-                    const float* src = stg + (size_t)(sub * kSubRows + nloc * hw_sub) * kStagePitchF32 + j;
-                    float acc = 0.f;
-                    for (int r = 0; r < hw_sub; ++r) acc += src[(size_t)r * kStagePitchF32];
-                    reinterpret_cast<float*>(p.out)[(size_t)n * p.Cout + cbase + j] = acc / (float)hw_sub;
-                }
-                named_bar_sync(1, kEpiThreads);
             }
-        }
 
-        if (p.epi == SR_EPI_RAW_STATS) {
-            named_bar_sync(1, kEpiThreads);
-            for (int i = et; i < p.n_cta; i += kEpiThreads) {
-                atomicAdd(&p.stats[co0 + i], (double)s_sum[i]);
-                atomicAdd(&p.stats[p.Cout + co0 + i], (double)s_sq[i]);
+            // all of this warp's TMEM reads of the tile are complete: hand the accumulator back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+
+            if (p.epi == SR_EPI_RAW_STATS) {
+                named_bar_sync(1, kEpiThreads);
+                for (int i = et; i < p.n_cta; i += kEpiThreads) {
+                    atomicAdd(&p.stats[tc.co0 + i], (double)s_sum[i]);
+                    atomicAdd(&p.stats[p.Cout + tc.co0 + i], (double)s_sq[i]);
+                }
+                named_bar_sync(1, kEpiThreads);
             }
         }
     }
@@ -443,7 +500,10 @@ bool pick_tile(int H, int W, int epi, Tile* out) {
     return best_key >= 0;
 }
 
-int kc_bytes_for(int cin_pad) { return (cin_pad % 64 == 0) ? 128 : ((cin_pad % 32 == 0) ? 64 : 32); }
+// Channel block per pipeline stage.  128-byte rows whenever the tensor has at least 64 channels: a ragged last block
+// (160 = 64 + 64 + 32) is zero-filled by TMA (out-of-bounds channels of A are zeros, so whatever the B box picks up
+// there is multiplied by zero); 64-byte rows halve the bytes per L2 request and measured 25 % vs 43 % tensor-active.
+int kc_bytes_for(int cin_pad) { return cin_pad >= 64 ? 128 : (cin_pad >= 32 ? 64 : 32); }
 
 }  // namespace
 
@@ -496,10 +556,10 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
     p.residual = static_cast<const __nv_bfloat16*>(a->residual);
     p.out = a->out;
     p.stats = a->stats;
-    int tm = 32;
-    while (tm < 2 * p.n_cta) tm <<= 1;
-    if (tm > 512) return fail(SR_E_ARG, "sr_conv: accumulators need %d TMEM columns", tm);
-    p.tmem_cols = tm;
+    if (2 * p.n_cta > 512) return fail(SR_E_ARG, "sr_conv: accumulators need %d TMEM columns", 2 * p.n_cta);
+    p.acc_stages = std::min(4, 512 / (2 * p.n_cta));   // as many accumulator stages as TMEM holds
+    p.tmem_cols = 512;                                 // one persistent CTA per SM owns all of TMEM
+    p.n_splits = ns;
 
     int kc_max = 0;
     for (int i = 0; i < a->n_panels; ++i) {
@@ -513,7 +573,7 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
         pd.taps = sp.taps;
         pd.cin_pad = sp.cin_pad;
         pd.kc_bytes = kc_bytes_for(sp.cin_pad);
-        pd.ncb = sp.cin_pad * 2 / pd.kc_bytes;
+        pd.ncb = (sp.cin_pad * 2 + pd.kc_bytes - 1) / pd.kc_bytes;
         kc_max = std::max(kc_max, pd.kc_bytes);
         const int kc = pd.kc_bytes / 2;
         {
@@ -541,10 +601,9 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
     p.a_slot = kSubRows * kc_max;
     const int b_slot = (int)align_up((int64_t)p.n_cta * kc_max, 1024);
     p.stage_bytes = 2 * p.a_slot + b_slot;
-    p.stages = std::min(12, (200 * 1024) / p.stage_bytes);
-    if (p.stages < 2) return fail(SR_E_ARG, "sr_conv: pipeline does not fit in shared memory");
-    const int staging = 2 * kSubRows * std::max(kStagePitchBf16, kStagePitchF32 * 4);
-    const int dyn_smem = std::max(p.stages * p.stage_bytes, staging) + 1024;
+    int staging = 0;   // the producer prefetches the next tile during the epilogue: staging cannot alias the pipeline
+    if (a->epilogue == SR_EPI_ACT_POOL2) staging = 2 * kSubRows * kStagePitchBf16;
+    if (a->epilogue == SR_EPI_ACT_AVG) staging = 2 * kSubRows * kStagePitchF32 * 4;
 
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
@@ -558,10 +617,19 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
     });
     if (attr_err != cudaSuccess)
         return fail(SR_E_CUDA, "sr_conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
-    if (dyn_smem > max_dyn) return fail(SR_E_ARG, "sr_conv: needs %d bytes of shared memory (> %d)", dyn_smem, max_dyn);
+    p.stages = std::min(12, (max_dyn - 1024 - staging) / p.stage_bytes);
+    if (p.stages < 2) return fail(SR_E_ARG, "sr_conv: pipeline does not fit in shared memory");
+    const int dyn_smem = p.stages * p.stage_bytes + staging + 1024;
 
     const int tiles_n = tile.stack_h ? a->batch : (a->batch + 2 * tile.TN - 1) / (2 * tile.TN);
-    dim3 grid((unsigned)(tile.tiles_w * tile.tiles_h * tiles_n), (unsigned)ns, 1);
+    p.total_tiles = tile.tiles_w * tile.tiles_h * tiles_n * ns;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    dim3 grid((unsigned)std::min(p.total_tiles, num_sms), 1, 1);
     conv_umma_kernel<<<grid, kThreads, dyn_smem, stream>>>(p);
     SR_CUDA_OK(cudaGetLastError());
     return SR_OK;

@@ -17,6 +17,9 @@ BN_MOMENTUM = 0.1
 DROP_RATE = 0.1
 
 
+_PINNED_POOL = {}
+
+
 def _pad16(c):
     return (c + 15) // 16 * 16
 
@@ -127,11 +130,11 @@ class BackboneEngine(object):
         n = 1
         for d in shape:
             n *= int(d)
-        ent = self._staging.get(key)
+        ent = _PINNED_POOL.get(key)     # process-wide: cudaHostAlloc is far too slow to repeat per model instance
         if ent is None or ent[2].numel() < n:
             flat = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=True)
             ent = [None, None, flat]
-            self._staging[key] = ent
+            _PINNED_POOL[key] = ent
         if ent[1] is not None:
             ent[1].synchronize()     # the previous copy out of this buffer must have finished before it is rewritten
         ent[0] = ent[2][:n].view(shape)
