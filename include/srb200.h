@@ -240,7 +240,8 @@ int32_t sr_project_rows(const float* x, const float* qt, int32_t n, int32_t q_ro
  * Host helper (no device work): replay of PyTorch's CPU mt19937 Bernoulli stream for the dropout / DropBlock
  * keep-masks of the train-mode epoch (resnet_language.py:292-299, 311-325), bit-identical to
  * tensor.bernoulli_(p) (kind 0: double p, two 32-bit draws per element) and torch.bernoulli(float p tensor)
- * (kind 1: one draw per element).  `state_blob` = bytes of torch.get_rng_state(), advanced in place.
+ * (kind 1: one draw per element); kind 2 skips n 32-bit draws without output.  `state_blob` = bytes of
+ * torch.get_rng_state(), advanced in place.
  * out: HOST uint8[n] (1 = drawn one).  Returns the number of ones, or -1 on a malformed state.
  * ---------------------------------------------------------------------------------------------- */
 int64_t sr_host_bernoulli(void* state_blob, int64_t blob_bytes, int32_t kind, double p, int64_t n, uint8_t* out);

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <mutex>
 #include "common.h"
+#include "head_common.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -125,49 +126,9 @@ __device__ __forceinline__ void gemm_tn_tile(const float* __restrict__ DL, int l
     }
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-// Sum over the block (result valid in every thread). `red` = 32 doubles of shared memory.
-__device__ __forceinline__ double block_sum(double v, double* red) {
-    v = warp_sum(v);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    __syncthreads();
-    if (l == 0) red[w] = v;
-    __syncthreads();
-    double t = 0.0;
-    const int nw = blockDim.x >> 5;
-    for (int i = 0; i < nw; ++i) t += red[i];
-    return t;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Persistent head kernel
 // ------------------------------------------------------------------------------------------------
-struct HeadCtrl {          // lives at the start of the workspace (zeroed by the host before launch)
-    unsigned int barrier;  // monotonically increasing arrival counter
-    int stop;
-    int epochs_done;
-    int stable_count;
-    float prev_loss;
-    int error;
-    int pad[10];
-    double norm_base_sq;   // ||W[:nb] - W0||_F^2
-    double norm_prev_sq;   // ||W[nb:nb+np] - Wres||_F^2
-};
-
 struct HeadParams {
     sr_head_args a;
     int n_total;
@@ -178,27 +139,6 @@ struct HeadParams {
     float* gpull;     // [n_new, dim]
     float* Z;         // [n_total, n_classes]
 };
-
-__device__ __forceinline__ void grid_barrier(HeadCtrl* ctrl, unsigned int& target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        target += gridDim.x;
-        __threadfence();
-        atomicAdd(&ctrl->barrier, 1u);
-        const long long t0 = clock64();
-        while (true) {
-            unsigned int v;
-            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(&ctrl->barrier) : "memory");
-            if (v >= target) break;
-            if (clock64() - t0 > 8000000000LL) {  // never hang the device
-                ctrl->error = 1;
-                __trap();
-            }
-        }
-        __threadfence();
-    }
-    __syncthreads();
-}
 
 // Projection residual and gradient of gamma*||pull - w||^2 for new-class row `i` (one CTA).
 __device__ void pull_task(const HeadParams& p, int i, float* sw, float* sr, float* su, double* red) {
@@ -657,7 +597,9 @@ int32_t launch_head(const HeadParams& p, int grid, size_t dyn, cudaStream_t stre
 
 extern "C" int64_t sr_head_workspace_bytes(const sr_head_args* a) {
     if (!a) return 0;
-    return head_layout(a).total;
+    int64_t n = head_layout(a).total;
+    if (a->dim >= 32 && a->dim % 32 == 0) n = std::max<int64_t>(n, srb::head_small_workspace_bytes(a));
+    return n;
 }
 
 extern "C" int32_t sr_head_run(const sr_head_args* a, void* stream_v) {
@@ -675,10 +617,12 @@ extern "C" int32_t sr_head_run(const sr_head_args* a, void* stream_v) {
     if (a->reserve_weight && a->n_base + a->n_prev_novel > a->n_classes)
         return fail(SR_E_ARG, "sr_head_run: reserve rows exceed n_classes");
     if (a->optimizer != SR_OPT_SGD && a->optimizer != SR_OPT_ADAM) return fail(SR_E_ARG, "sr_head_run: bad optimizer");
+    if (reinterpret_cast<uintptr_t>(a->workspace) & 255) return fail(SR_E_ARG, "sr_head_run: workspace must be 256-byte aligned");
+    // Paper-sized problems: everything constant over the session stays in shared memory (head_small.cu).
+    if (srb::head_small_applicable(a)) return srb::head_small_run(a, stream);
     const HeadLayout L = head_layout(a);
     if (a->workspace_bytes < L.total) return fail(SR_E_SMALLWS, "sr_head_run: workspace %lld < %lld",
                                                   (long long)a->workspace_bytes, (long long)L.total);
-    if (reinterpret_cast<uintptr_t>(a->workspace) & 255) return fail(SR_E_ARG, "sr_head_run: workspace must be 256-byte aligned");
 
     HeadParams p;
     p.a = *a;

@@ -1,0 +1,533 @@
+// Latency-optimised persistent head kernel for the paper-sized problems (C <= 128 classes, a few hundred rows):
+// the step is ~1.5 MB / 30-90 MFLOP, far below what one kernel launch costs, so everything that does not change
+// between epochs stays in shared memory for the whole session and an epoch is TWO grid phases:
+//
+//   phase 1  row CTAs (R rows of X resident): stream W through a cp.async double buffer, logits, softmax,
+//            CE / top-k per row, dlogits -> DLt[c][n] (class-major);
+//            pull CTA (Q^T resident, 153 KB): u = W_new Q  (projection coefficients of the newest rows);
+//            CTA 0: assembles the loss of the PREVIOUS epoch and applies the stopping rule (language_eval.py:298-318)
+//   phase 2  column CTAs (8 feature columns of X, W, momentum, W0, reserve, Q^T resident): stream DLt, dW = dZ^T X,
+//            every regulariser gradient, weight decay, SGD-momentum / Adam, write W; partial sums of
+//            ||W - W0||^2, ||W_prev - W_res||^2 for the next epoch and ||P w - w||^2 for this one.
+//
+// Same arithmetic as head_kernel (head.cu) except that the projection gradient uses the closed form 2*gamma*(w - Pw)
+// (P is an orthogonal projector; the reference's autograd expression 2*gamma*(rP - r) differs by O(1e-8)).
+#include <algorithm>
+#include <mutex>
+#include "common.h"
+#include "head_common.cuh"
+
+namespace {
+using namespace srb;
+
+constexpr int kT = 256;
+constexpr int DC = 8;     // feature columns per column CTA
+constexpr int KC = 32;    // k-chunk of the W stream (phase 1) / n-chunk of the DLt stream (phase 2)
+constexpr int PITCH = 36; // floats per staged row: 16-byte aligned for cp.async, conflict-free LDS.128
+constexpr int NS = 6;     // cp.async stages of the W / DLt streams (one region, the two phases never overlap in a CTA)
+
+struct SmallParams {
+    sr_head_args a;
+    int n_total, ldn;      // ldn: row pitch of DLt (n_total rounded up to 32)
+    int R, GA, GC, G;      // rows per row CTA, #row CTAs, #column CTAs, grid (= max(GA, GC) + 1 pull CTA)
+    int CP;                // classes padded to 64 or 128 (thread mapping of phase 1)
+    HeadCtrl* ctrl;
+    float* DLt;            // [C][ldn]
+    float* rowloss;        // [2][n_total]
+    int* rowhit;           // [2][n_total]
+    double* nb_part;       // [2][GC]
+    double* nn_part;       // [2][GC]
+    double* pull_part;     // [GC]
+    float* u;              // [n_new][q_rows]
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ int64_t feat_row(const sr_head_args& a, int r) {
+    return r < a.n_support ? (int64_t)a.support_row0 + r : (int64_t)a.memory_row0 + (r - a.n_support);
+}
+
+// Loss of epoch `e` from the partial results in the workspace + the reference's stopping rule.  One CTA.
+__device__ void assemble_loss(const SmallParams& p, int e, double* red) {
+    const sr_head_args& a = p.a;
+    const int par = e & 1;
+    const int tid = threadIdx.x;
+    double ls = 0.0, lm = 0.0, h1 = 0.0, h5 = 0.0, nb = 0.0, nn = 0.0, ps = 0.0;
+    for (int r = tid; r < p.n_total; r += blockDim.x) {
+        const float l = p.rowloss[par * p.n_total + r];
+        const int h = p.rowhit[par * p.n_total + r];
+        if (r < a.n_support) { ls += (double)l; h1 += (double)(h & 1); h5 += (double)((h >> 1) & 1); }
+        else lm += (double)l;
+    }
+    for (int i = tid; i < p.GC; i += blockDim.x) {
+        nb += p.nb_part[par * p.GC + i];
+        nn += p.nn_part[par * p.GC + i];
+        ps += p.pull_part[i];
+    }
+    ls = block_sum(ls, red); lm = block_sum(lm, red); h1 = block_sum(h1, red); h5 = block_sum(h5, red);
+    nb = block_sum(nb, red); nn = block_sum(nn, red); ps = block_sum(ps, red);
+    if (tid == 0) {
+        const bool has_base = a.base_weight != nullptr;
+        const bool has_prev = a.reserve_weight != nullptr && a.n_prev_novel > 0;
+        const bool has_pull = a.pull_mode != SR_PULL_NONE;
+        const float ce_s = (float)(ls / (double)a.n_support);
+        const float ce_m = a.n_memory > 0 ? (float)(lm / (double)a.n_memory) : 0.f;
+        const float reg_b = has_base ? a.lmbd_base * (float)sqrt(nb) : 0.f;
+        const float reg_n = has_prev ? a.lmbd_novel * (float)sqrt(nn) : 0.f;
+        const float pull = has_pull ? a.gamma * (float)ps : 0.f;
+        float loss = ce_s;
+        if (a.n_memory > 0) loss += ce_m;
+        if (has_base) loss += reg_b;
+        if (has_prev) loss += reg_n;
+        if (has_pull) loss += pull;
+        float* tr = a.loss_trace + (int64_t)e * SR_TRACE_COLS;
+        tr[0] = loss; tr[1] = ce_s; tr[2] = ce_m; tr[3] = reg_b; tr[4] = reg_n; tr[5] = pull; tr[6] = (float)h1; tr[7] = (float)h5;
+        int stop = 0;
+        int sc = e == 0 ? a.stable_count0 : p.ctrl->stable_count;
+        const float prev = e == 0 ? a.prev_loss : p.ctrl->prev_loss;
+        if (a.stable) {
+            if (fabs((double)loss - (double)prev) < a.convergence_epsilon) sc += 1; else sc = 0;
+            if (sc == a.stable_epochs) stop = 1;
+        }
+        const int epoch = a.epoch0 + e + 1;
+        if (epoch >= a.max_novel_epochs || ((double)loss <= a.target_train_loss && epoch >= a.min_novel_epochs + 1)) stop = 1;
+        p.ctrl->stable_count = sc;
+        p.ctrl->prev_loss = loss;
+        p.ctrl->epochs_done = e + 1;
+        p.ctrl->stop = stop;
+    }
+    __syncthreads();
+}
+
+template <int R>
+__global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) {
+    extern __shared__ __align__(16) uint8_t dyn[];
+    __shared__ double red[32];
+    __shared__ int s_stop;
+    const sr_head_args& a = p.a;
+    const int C = a.n_classes, d = a.dim, NT = p.n_total, q = a.q_rows;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cta = blockIdx.x;
+    const bool is_row = cta < p.GA, is_col = cta < p.GC, is_pull = cta == p.G - 1;
+    const bool has_base = a.base_weight != nullptr;
+    const bool has_prev = a.reserve_weight != nullptr && a.n_prev_novel > 0;
+    const bool proj = a.pull_mode == SR_PULL_PROJECT && q < d;   // q >= d: P = I, the term vanishes
+    const bool fixed = a.pull_mode == SR_PULL_FIXED;
+    const int new0 = C - a.n_new;
+    const int n_opt = a.optimizer == SR_OPT_ADAM ? 2 : 1;
+
+    // ---- shared memory carve-up ----
+    float* sp = reinterpret_cast<float*>(dyn);
+    float* Xrow = sp;            sp += is_row ? R * d : 0;                 // [R][d]
+    float* Zs = sp;              sp += is_row ? R * (p.CP + 1) : 0;        // [R][CP+1] logits
+    const int xp = p.ldn + 4;    // pitch of the X column slice: +4 floats keeps the 8 rows on different banks
+    float* Xc = sp;              sp += is_col ? DC * xp : 0;               // [DC][xp]   (column-major slice of X)
+    float* Wc = sp;              sp += is_col ? C * DC : 0;                // [C][DC] master copy of this CTA's W columns
+    float* Vc = sp;              sp += is_col ? n_opt * C * DC : 0;        // optimiser state columns
+    float* W0c = sp;             sp += (is_col && has_base) ? a.n_base * DC : 0;
+    float* Rc = sp;              sp += (is_col && has_prev) ? a.n_prev_novel * DC : 0;
+    float* Pc = sp;              sp += (is_col && (proj || fixed)) ? (proj ? q : a.n_new) * DC : 0;  // Q^T or puller columns
+    float* Us = sp;              sp += (is_col && proj) ? ((a.n_new * q + 3) & ~3) : 0;      // [n_new][q] projection coefficients
+    float* Stg = sp;             sp += (is_row || is_col) ? NS * p.CP * PITCH : 0;   // NS x [CP][PITCH] stream stages
+    float* Qs = sp;              sp += (is_pull && proj) ? q * d : 0;      // [q][d]
+    float* wn = sp;              sp += (is_pull && proj) ? a.n_new * d : 0;
+
+    // ---- one-time loads of everything that is constant over the session ----
+    const int r0 = cta * R;
+    if (is_row) {
+        for (int i = tid; i < R * (d / 4); i += kT) {
+            const int r = i / (d / 4), k4 = i % (d / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r0 + r < NT) v = *reinterpret_cast<const float4*>(a.feat + feat_row(a, r0 + r) * d + k4 * 4);
+            *reinterpret_cast<float4*>(Xrow + r * d + k4 * 4) = v;
+        }
+    }
+    const int j0 = cta * DC;
+    if (is_col) {
+        for (int i = tid; i < p.ldn * DC; i += kT) {
+            const int n = i / DC, j = i % DC;
+            Xc[j * xp + n] = n < NT ? a.feat[feat_row(a, n) * d + j0 + j] : 0.f;
+        }
+        for (int i = tid; i < C * DC; i += kT) {
+            const int c = i / DC, j = i % DC;
+            Wc[i] = a.weight[(int64_t)c * d + j0 + j];
+            for (int s = 0; s < n_opt; ++s) Vc[s * C * DC + i] = a.opt_state[(int64_t)s * C * d + (int64_t)c * d + j0 + j];
+        }
+        if (has_base)
+            for (int i = tid; i < a.n_base * DC; i += kT) W0c[i] = a.base_weight[(int64_t)(i / DC) * d + j0 + i % DC];
+        if (has_prev)
+            for (int i = tid; i < a.n_prev_novel * DC; i += kT) Rc[i] = a.reserve_weight[(int64_t)(i / DC) * d + j0 + i % DC];
+        if (proj)
+            for (int i = tid; i < q * DC; i += kT) Pc[i] = a.pull[(int64_t)(i / DC) * d + j0 + i % DC];
+        if (fixed)
+            for (int i = tid; i < a.n_new * DC; i += kT) Pc[i] = a.pull[(int64_t)(i / DC) * d + j0 + i % DC];
+    }
+    if (is_pull && proj)
+        for (int i = tid; i < q * (d / 4); i += kT)
+            *reinterpret_cast<float4*>(Qs + i * 4) = *reinterpret_cast<const float4*>(a.pull + (int64_t)i * 4);
+    __syncthreads();
+    // norm partials of W_0 (buffer parity 0)
+    if (is_col) {
+        double nb = 0.0, nn = 0.0;
+        if (has_base)
+            for (int i = tid; i < a.n_base * DC; i += kT) { const float dl = Wc[i] - W0c[i]; nb += (double)dl * dl; }
+        if (has_prev)
+            for (int i = tid; i < a.n_prev_novel * DC; i += kT) { const float dl = Wc[a.n_base * DC + i] - Rc[i]; nn += (double)dl * dl; }
+        nb = block_sum(nb, red);
+        nn = block_sum(nn, red);
+        if (tid == 0) { p.nb_part[cta] = nb; p.nn_part[cta] = nn; p.pull_part[cta] = 0.0; }
+    }
+    unsigned int bar_target = 0;
+    grid_barrier(p.ctrl, bar_target);
+
+    const int CP = p.CP;
+    const int RG = kT / CP;          // row groups in phase 1 (2 or 4)
+    const int RPT = R / RG;          // rows per thread
+    const int c1 = tid % CP, rg = tid / CP;
+    int e = 0;
+    bool stopped = false;
+    for (; e < a.max_epochs; ++e) {
+        const int par = e & 1;
+        unsigned long long ts0 = 0, ts1 = 0, ts2 = 0, ts3 = 0;
+        if (cta == 0 && tid == 0) ts0 = global_ns();
+        // ======================= phase 1 =======================
+        if (cta == 0 && e > 0) assemble_loss(p, e - 1, red);
+        if (is_row) {
+            float acc[R / 2];
+#pragma unroll
+            for (int i = 0; i < R / 2; ++i) acc[i] = 0.f;
+            const int nchunk = d / KC;
+            auto issue = [&](int ck) {
+                float* dst = Stg + (ck % NS) * CP * PITCH;
+                for (int i = tid; i < C * (KC / 4); i += kT) {
+                    const int c = i / (KC / 4), k4 = i % (KC / 4);
+                    cp_async16(dst + c * PITCH + k4 * 4, a.weight + (int64_t)c * d + ck * KC + k4 * 4);
+                }
+            };
+            for (int s = 0; s < NS - 1; ++s) {
+                if (s < nchunk) issue(s);
+                cp_async_commit();
+            }
+            for (int ck = 0; ck < nchunk; ++ck) {
+                if (ck + NS - 1 < nchunk) issue(ck + NS - 1);
+                cp_async_commit();
+                cp_async_wait<NS - 1>();
+                __syncthreads();
+                const float* wsrc = Stg + (ck % NS) * CP * PITCH + c1 * PITCH;
+                if (c1 < C) {
+#pragma unroll
+                    for (int k4 = 0; k4 < KC / 4; ++k4) {
+                        const float4 w4 = *reinterpret_cast<const float4*>(wsrc + k4 * 4);
+#pragma unroll
+                        for (int i = 0; i < R / 2; ++i) {
+                            if (i < RPT) {
+                                const float4 x4 = *reinterpret_cast<const float4*>(Xrow + (rg * RPT + i) * d + ck * KC + k4 * 4);
+                                acc[i] = fmaf(x4.x, w4.x, acc[i]);
+                                acc[i] = fmaf(x4.y, w4.y, acc[i]);
+                                acc[i] = fmaf(x4.z, w4.z, acc[i]);
+                                acc[i] = fmaf(x4.w, w4.w, acc[i]);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            cp_async_wait<0>();
+#pragma unroll
+            for (int i = 0; i < R / 2; ++i)
+                if (i < RPT && c1 < C) Zs[(rg * RPT + i) * (CP + 1) + c1] = acc[i];
+            __syncthreads();
+            // softmax per row: warp w handles rows w, w + 8, ...
+            for (int r = warp; r < R; r += kT / 32) {
+                const int n = r0 + r;
+                if (n >= NT) continue;
+                const float* z = Zs + r * (CP + 1);
+                const bool is_sup = n < a.n_support;
+                const int y = (int)(is_sup ? a.labels_support[n] : a.labels_memory[n - a.n_support]);
+                const float inv_n = 1.f / (float)(is_sup ? a.n_support : a.n_memory);
+                float mx = -INFINITY;
+                for (int c = lane; c < C; c += 32) mx = fmaxf(mx, z[c]);
+                mx = warp_max(mx);
+                float se = 0.f;
+                for (int c = lane; c < C; c += 32) se += expf(z[c] - mx);
+                se = warp_sum(se);
+                const float lse = mx + logf(se);
+                const float zy = z[y];
+                int greater = 0, tie_before = 0;
+                for (int c = lane; c < C; c += 32) {
+                    const float zc = z[c];
+                    greater += zc > zy ? 1 : 0;
+                    tie_before += (zc == zy && c < y) ? 1 : 0;
+                }
+                greater = __reduce_add_sync(0xffffffffu, greater);
+                tie_before = __reduce_add_sync(0xffffffffu, tie_before);
+                for (int c = lane; c < C; c += 32) {
+                    const float pr = expf(z[c] - lse);
+                    p.DLt[(int64_t)c * p.ldn + n] = (pr - (c == y ? 1.f : 0.f)) * inv_n;
+                }
+                if (lane == 0) {
+                    p.rowloss[par * NT + n] = lse - zy;
+                    const int rank = greater + tie_before;
+                    p.rowhit[par * NT + n] = (rank == 0 ? 1 : 0) | (rank < 5 ? 2 : 0);
+                }
+            }
+        }
+        if (is_pull && proj) {   // u = W_new Q  ([n_new][q])
+            for (int i = tid; i < a.n_new * (d / 4); i += kT)
+                *reinterpret_cast<float4*>(wn + i * 4) = *reinterpret_cast<const float4*>(a.weight + (int64_t)new0 * d + (int64_t)i * 4);
+            __syncthreads();
+            for (int o = warp; o < a.n_new * q; o += kT / 32) {
+                const int i = o / q, jq = o % q;
+                float s = 0.f;
+                for (int k = lane; k < d; k += 32) s = fmaf(Qs[jq * d + k], wn[i * d + k], s);
+                s = warp_sum(s);
+                if (lane == 0) p.u[o] = s;
+            }
+        }
+        if (cta == 0 && tid == 0) ts1 = global_ns();
+        grid_barrier(p.ctrl, bar_target);
+        if (cta == 0 && tid == 0) ts2 = global_ns();
+        if (tid == 0) s_stop = p.ctrl->stop;
+        __syncthreads();
+        if (e > 0 && s_stop) { stopped = true; break; }
+
+        // ======================= phase 2 =======================
+        if (is_col) {
+            // norms of W_e - anchors (partials written at the end of the previous epoch / init): one load per thread
+            double nbs = 0.0, nns = 0.0;
+            for (int i = tid; i < p.GC; i += kT) { nbs += p.nb_part[par * p.GC + i]; nns += p.nn_part[par * p.GC + i]; }
+            nbs = block_sum(nbs, red);
+            nns = block_sum(nns, red);
+            if (proj) {   // projection coefficients of this epoch (written by the pull CTA in phase 1) -> shared memory
+                for (int i = tid; i < a.n_new * q; i += kT) Us[i] = p.u[i];
+            }
+            const float nb = has_base ? (float)sqrt(nbs) : 0.f, nn = has_prev ? (float)sqrt(nns) : 0.f;
+            const float sb = nb > 0.f ? a.lmbd_base / nb : 0.f;
+            const float sn = nn > 0.f ? a.lmbd_novel / nn : 0.f;
+            const int j = tid % DC, cg = tid / DC;          // cg in [0, 32): classes cg, cg + 32, cg + 64, cg + 96
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const int nchunk = p.ldn / KC;
+            auto issue = [&](int ck) {
+                float* dst = Stg + (ck % NS) * CP * PITCH;
+                for (int i = tid; i < C * (KC / 4); i += kT) {
+                    const int c = i / (KC / 4), n4 = i % (KC / 4);
+                    cp_async16(dst + c * PITCH + n4 * 4, p.DLt + (int64_t)c * p.ldn + ck * KC + n4 * 4);
+                }
+            };
+            for (int s = 0; s < NS - 1; ++s) {
+                if (s < nchunk) issue(s);
+                cp_async_commit();
+            }
+            for (int ck = 0; ck < nchunk; ++ck) {
+                if (ck + NS - 1 < nchunk) issue(ck + NS - 1);
+                cp_async_commit();
+                cp_async_wait<NS - 1>();
+                __syncthreads();
+                const float* dsrc = Stg + (ck % NS) * CP * PITCH;
+                const float* xsrc = Xc + j * xp + ck * KC;
+#pragma unroll
+                for (int n4 = 0; n4 < KC / 4; ++n4) {
+                    const float4 x4 = *reinterpret_cast<const float4*>(xsrc + n4 * 4);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = cg + 32 * i;
+                        if (c < C) {
+                            const float4 d4 = *reinterpret_cast<const float4*>(dsrc + c * PITCH + n4 * 4);
+                            acc[i] = fmaf(d4.x, x4.x, acc[i]);
+                            acc[i] = fmaf(d4.y, x4.y, acc[i]);
+                            acc[i] = fmaf(d4.z, x4.z, acc[i]);
+                            acc[i] = fmaf(d4.w, x4.w, acc[i]);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            cp_async_wait<0>();
+            const int step = a.step0 + e;
+            float bc1 = 1.f, bc2s = 1.f;
+            if (a.optimizer == SR_OPT_ADAM) {
+                bc1 = (float)(1.0 - pow((double)a.beta1, (double)(step + 1)));
+                bc2s = (float)sqrt(1.0 - pow((double)a.beta2, (double)(step + 1)));
+            }
+            double nbp = 0.0, nnp = 0.0, pp = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = cg + 32 * i;
+                if (c >= C) continue;
+                const int idx = c * DC + j;
+                const float w = Wc[idx];
+                float g = acc[i];
+                if (has_base && c < a.n_base) g += sb * (w - W0c[idx]);
+                if (has_prev && c >= a.n_base && c < a.n_base + a.n_prev_novel) g += sn * (w - Rc[idx - a.n_base * DC]);
+                if (c >= new0 && (proj || fixed)) {
+                    float r;
+                    if (proj) {
+                        float pw = 0.f;
+                        const float* ui = Us + (c - new0) * q;
+                        for (int jq = 0; jq < q; ++jq) pw = fmaf(ui[jq], Pc[jq * DC + j], pw);
+                        r = pw - w;
+                    } else {
+                        r = Pc[(c - new0) * DC + j] - w;
+                    }
+                    pp += (double)r * (double)r;
+                    g += -2.f * a.gamma * r;
+                }
+                g = fmaf(a.weight_decay, w, g);
+                float wnew;
+                if (a.optimizer == SR_OPT_SGD) {
+                    float v = Vc[idx];
+                    v = step == 0 ? g : fmaf(a.momentum, v, g);
+                    Vc[idx] = v;
+                    wnew = w - a.lr * v;
+                } else {
+                    float m1 = Vc[idx], m2 = Vc[C * DC + idx];
+                    m1 = m1 + (1.f - a.beta1) * (g - m1);
+                    m2 = a.beta2 * m2 + (1.f - a.beta2) * g * g;
+                    Vc[idx] = m1;
+                    Vc[C * DC + idx] = m2;
+                    wnew = w - (a.lr / bc1) * (m1 / (sqrtf(m2) / bc2s + a.adam_eps));
+                }
+                Wc[idx] = wnew;
+                a.weight[(int64_t)c * d + j0 + j] = wnew;
+                if (has_base && c < a.n_base) { const float dl = wnew - W0c[idx]; nbp += (double)dl * dl; }
+                if (has_prev && c >= a.n_base && c < a.n_base + a.n_prev_novel) {
+                    const float dl = wnew - Rc[idx - a.n_base * DC];
+                    nnp += (double)dl * dl;
+                }
+            }
+            nbp = block_sum(nbp, red);
+            nnp = block_sum(nnp, red);
+            pp = block_sum(pp, red);
+            if (tid == 0) {
+                p.nb_part[(par ^ 1) * p.GC + cta] = nbp;
+                p.nn_part[(par ^ 1) * p.GC + cta] = nnp;
+                p.pull_part[cta] = pp;
+            }
+        }
+        if (cta == 0 && tid == 0) ts3 = global_ns();
+        grid_barrier(p.ctrl, bar_target);
+        if (cta == 0 && tid == 0) {
+            p.ctrl->t_ns[0] += ts1 - ts0;
+            p.ctrl->t_ns[1] += ts2 - ts1;
+            p.ctrl->t_ns[2] += ts3 - ts2;
+            p.ctrl->t_ns[3] += global_ns() - ts3;
+        }
+    }
+    // ---- tail: loss of the last applied epoch when the loop ran out of epochs; write back optimiser state ----
+    if (!stopped && cta == 0 && e > 0) assemble_loss(p, e - 1, red);
+    if (is_col) {
+        for (int i = tid; i < C * DC; i += kT) {
+            const int c = i / DC, j = i % DC;
+            for (int s = 0; s < n_opt; ++s) a.opt_state[(int64_t)s * C * d + (int64_t)c * d + j0 + j] = Vc[s * C * DC + i];
+        }
+    }
+    if (cta == 0) {
+        __syncthreads();
+        if (tid == 0) {
+            a.status[0] = p.ctrl->epochs_done;
+            a.status[1] = p.ctrl->stop;
+            a.status[2] = p.ctrl->stable_count;
+            a.status[3] = p.ctrl->error;
+        }
+    }
+}
+
+struct SmallLayout {
+    int64_t ctrl, DLt, rowloss, rowhit, nb, nn, pull, u, total;
+};
+
+SmallLayout small_layout(const sr_head_args* a, int GC) {
+    SmallLayout L;
+    const int64_t nt = (int64_t)a->n_support + a->n_memory;
+    const int64_t ldn = align_up(nt, KC);
+    int64_t off = 0;
+    L.ctrl = off;    off += align_up(sizeof(HeadCtrl), 256);
+    L.DLt = off;     off += align_up((int64_t)a->n_classes * ldn * 4, 256);
+    L.rowloss = off; off += align_up(2 * nt * 4, 256);
+    L.rowhit = off;  off += align_up(2 * nt * 4, 256);
+    L.nb = off;      off += align_up(2 * (int64_t)GC * 8, 256);
+    L.nn = off;      off += align_up(2 * (int64_t)GC * 8, 256);
+    L.pull = off;    off += align_up((int64_t)GC * 8, 256);
+    L.u = off;       off += align_up((int64_t)std::max(a->n_new, 1) * std::max(a->q_rows, 1) * 4, 256);
+    L.total = off;
+    return L;
+}
+
+template <int R>
+int32_t launch_small(const SmallParams& p, size_t dyn, cudaStream_t stream) {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cudaFuncSetAttribute(head_small_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    });
+    void* args[] = {const_cast<SmallParams*>(&p)};
+    SR_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(head_small_kernel<R>), dim3(p.G), dim3(kT), args, dyn,
+                                           stream));
+    return SR_OK;
+}
+
+size_t small_smem_bytes(const sr_head_args* a, int R, int CP, int ldn, bool pull_cta) {
+    const int C = a->n_classes, d = a->dim;
+    const bool proj = a->pull_mode == SR_PULL_PROJECT && a->q_rows < d;
+    const bool fixed = a->pull_mode == SR_PULL_FIXED;
+    const int n_opt = a->optimizer == SR_OPT_ADAM ? 2 : 1;
+    size_t f = 0;
+    f += (size_t)R * d + (size_t)R * (CP + 1);                                       // row role
+    f += (size_t)NS * CP * PITCH;                                                    // stream stages (shared by both roles)
+    f += (size_t)DC * (ldn + 4) + (size_t)C * DC * (1 + n_opt) + (size_t)a->n_base * DC + (size_t)a->n_prev_novel * DC +
+         (size_t)(proj ? a->q_rows : (fixed ? a->n_new : 0)) * DC + (size_t)(proj ? a->n_new * a->q_rows : 0) + 8;   // column role
+    size_t g = pull_cta && proj ? (size_t)a->q_rows * d + (size_t)a->n_new * d : 0;    // pull role (its own CTA)
+    return std::max(f, g) * sizeof(float);
+}
+}  // namespace
+
+namespace srb {
+
+// Shapes the resident-operand kernel handles; anything else goes to the tiled head_kernel.
+bool head_small_applicable(const sr_head_args* a) {
+    const int nt = a->n_support + a->n_memory;
+    if (a->logits_support != nullptr) return false;
+    if (a->n_classes > 128 || a->dim % 32 != 0 || a->dim > 1024 || a->dim / DC > 147 || nt > 1024) return false;
+    if (a->pull_mode == SR_PULL_PROJECT && a->q_rows < a->dim && (a->q_rows > 256 || a->n_new > 16)) return false;
+    const int R = nt <= 200 ? 8 : 16;
+    const int CP = a->n_classes <= 64 ? 64 : 128;
+    const int ldn = (int)align_up(nt, KC);
+    if ((nt + R - 1) / R > 147) return false;
+    return small_smem_bytes(a, R, CP, ldn, true) <= 200 * 1024;
+}
+
+int64_t head_small_workspace_bytes(const sr_head_args* a) { return small_layout(a, a->dim / DC).total; }
+
+int32_t head_small_run(const sr_head_args* a, cudaStream_t stream) {
+    SmallParams p;
+    p.a = *a;
+    p.n_total = a->n_support + a->n_memory;
+    p.ldn = (int)align_up(p.n_total, KC);
+    p.R = p.n_total <= 200 ? 8 : 16;
+    p.GA = (p.n_total + p.R - 1) / p.R;
+    p.GC = a->dim / DC;
+    p.G = std::max(p.GA, p.GC) + 1;
+    p.CP = a->n_classes <= 64 ? 64 : 128;
+    const SmallLayout L = small_layout(a, p.GC);
+    if (a->workspace_bytes < L.total) return fail(SR_E_SMALLWS, "sr_head_run: workspace %lld < %lld",
+                                                  (long long)a->workspace_bytes, (long long)L.total);
+    uint8_t* ws = static_cast<uint8_t*>(a->workspace);
+    p.ctrl = reinterpret_cast<HeadCtrl*>(ws + L.ctrl);
+    p.DLt = reinterpret_cast<float*>(ws + L.DLt);
+    p.rowloss = reinterpret_cast<float*>(ws + L.rowloss);
+    p.rowhit = reinterpret_cast<int*>(ws + L.rowhit);
+    p.nb_part = reinterpret_cast<double*>(ws + L.nb);
+    p.nn_part = reinterpret_cast<double*>(ws + L.nn);
+    p.pull_part = reinterpret_cast<double*>(ws + L.pull);
+    p.u = reinterpret_cast<float*>(ws + L.u);
+    SR_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)L.total, stream));   // control block, DLt padding columns, partials
+    const size_t dyn = small_smem_bytes(a, p.R, p.CP, p.ldn, true);
+    return p.R == 8 ? launch_small<8>(p, dyn, stream) : launch_small<16>(p, dyn, stream);
+}
+
+}  // namespace srb

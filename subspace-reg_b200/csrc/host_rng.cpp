@@ -82,13 +82,31 @@ uint64_t threshold(double p, int bits) {  // ceil(p * 2^bits), clamped to [0, 2^
 
 // state_blob: the bytes of torch.get_rng_state() (updated in place).  Returns the number of ones written, or -1.
 extern "C" int64_t sr_host_bernoulli(void* state_blob, int64_t blob_bytes, int32_t kind, double p, int64_t n, uint8_t* out) {
-    if (!state_blob || !out || n < 0 || blob_bytes < (int64_t)sizeof(Blob) || (kind != 0 && kind != 1)) return -1;
+    if (!state_blob || n < 0 || blob_bytes < (int64_t)sizeof(Blob) || kind < 0 || kind > 2 || (kind != 2 && !out)) return -1;
     Blob* b = static_cast<Blob*>(state_blob);
     if (!b->seeded || b->left < 1 || b->left > N || b->next > (uint64_t)N) return -1;
     uint32_t s[N];
     for (int i = 0; i < N; ++i) s[i] = (uint32_t)b->state[i];
     int64_t remaining = b->left - 1;  // words left in the current block
     int64_t pos = (int64_t)b->next;
+    if (kind == 2) {  // skip n 32-bit draws (what a consumer with an as yet unknown probability will use up)
+        int64_t need = n;
+        while (need > 0) {
+            if (remaining == 0) {
+                regenerate(s);
+                pos = 0;
+                remaining = N;
+            }
+            const int64_t take = need < remaining ? need : remaining;
+            pos += take;
+            remaining -= take;
+            need -= take;
+        }
+        for (int i = 0; i < N; ++i) b->state[i] = s[i];
+        b->left = (int32_t)(remaining + 1);
+        b->next = (uint64_t)pos;
+        return 0;
+    }
     const int per = kind == 0 ? 2 : 1;
     constexpr int64_t kChunkElems = 1 << 16;
     std::vector<uint32_t> words((size_t)kChunkElems * 2 + N);

@@ -101,6 +101,7 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
     base_weight = base_weight.contiguous()
     dev = base_weight.device
     n_base_cls = net.num_classes
+    W_cols = base_weight.shape[1]
 
     base_valloader_it = itertools.cycle(iter(base_val_loader))
     meta_valloader_it = itertools.cycle(iter(meta_valloader))
@@ -210,6 +211,11 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         if has_mem:
             f_train = torch.cat([f_train, net.features(memory.data)], 0)
         tm['backbone_imgs'] += n_sup + n_mem
+        if idx + 1 < iter_num:
+            # the next session's dropout masks are drawn on a host thread while the GPU runs this session's cache build
+            # and head loop (verified against the live generator when they are consumed)
+            nxt = [n_sup] + ([n_mem + 25] if (opt.memory_replay == 1) else [])
+            net.engine().start_mask_prefetch(nxt, skip_words_first=opt.n_ways * W_cols)
         tp1 = _tick()
         ph['train_pass'] += tp1 - tp0
         W = net.classifier.weight.data

@@ -37,6 +37,8 @@ class BackboneEngine(object):
         self._raw = None         # per block: unscaled packed weights (train-mode pass)
         self._fold_key = None
         self._staging = {}
+        self._prefetch = None     # host_rng.MaskPrefetch for upcoming train-mode forwards
+        self._pf_fwd = 0          # index of the next train-mode forward relative to the prefetch plan
 
     # ---------------------------------------------------------------- weight packing
     def _bn_key(self):
@@ -125,17 +127,37 @@ class BackboneEngine(object):
         return h
 
     # ---------------------------------------------------------------- train-mode pass (epoch 1 of a session)
-    def _pinned(self, key, shape):
+    def start_mask_prefetch(self, batches, skip_words_first=0):
+        """Begin drawing, on a host thread, the dropout masks of the next len(batches) train-mode forwards (batch sizes
+        given), assuming `skip_words_first` generator draws happen before them (the next session's nn.Linear init).
+        DropBlock draws are skipped over (their gamma is not known yet) and made later from the live generator."""
+        steps = [('skip', skip_words_first)] if skip_words_first else []
+        for f, batch in enumerate(batches):
+            size = 84
+            for bi, b in enumerate(self.blocks):
+                size = size // b['pool']
+                if b['drop_block']:
+                    bs = b['block_size']
+                    steps.append(('skip', batch * b['cout'] * (size - (bs - 1)) ** 2))
+                else:
+                    shape = (batch, b['cout'], size, size)
+                    ent = self._pinned(('pf', f, bi), shape)      # waits for the last H2D out of this buffer
+                    steps.append(('draw', (f, bi), ent[0], 1 - DROP_RATE))
+        self._prefetch = host_rng.MaskPrefetch(steps)
+        self._pf_fwd = 0
+
+    def _pinned(self, key, shape, sync=True):
         """Reusable pinned staging buffer (uint8) + the event of its last H2D copy."""
         n = 1
         for d in shape:
             n *= int(d)
         ent = _PINNED_POOL.get(key)     # process-wide: cudaHostAlloc is far too slow to repeat per model instance
         if ent is None or ent[2].numel() < n:
-            flat = torch.empty(max(n, 1), dtype=torch.uint8, pin_memory=True)
+            cap = 1 << max(int(n - 1).bit_length(), 12)          # power-of-two capacity: batches grow session by session
+            flat = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
             ent = [None, None, flat]
             _PINNED_POOL[key] = ent
-        if ent[1] is not None:
+        if sync and ent[1] is not None:
             ent[1].synchronize()     # the previous copy out of this buffer must have finished before it is rewritten
         ent[0] = ent[2][:n].view(shape)
         return ent
@@ -147,9 +169,13 @@ class BackboneEngine(object):
         b = self.blocks[bi]
         shape = (batch, b['cout'], size, size)
         if not b['drop_block']:
-            ent = self._pinned(('m', bi), shape)
-            host_rng.bernoulli_u8(shape, 1 - DROP_RATE, 0, out=ent[0])       # noise.bernoulli_(1 - p)
             scale = float(torch.ones(1).div_(1 - DROP_RATE))                   # noise.div_(1 - p)
+            got = self._prefetch.take((self._cur_fwd, bi), shape) if self._prefetch is not None else None
+            if got is not None:                                                # drawn ahead of time on the host thread
+                ent = self._pinned(('pf', self._cur_fwd, bi), shape, sync=False)
+            else:
+                ent = self._pinned(('m', bi), shape)
+                host_rng.bernoulli_u8(shape, 1 - DROP_RATE, 0, out=ent[0])    # noise.bernoulli_(1 - p)
         else:
             bs = b['block_size']
             nbt = counters[b['prefix']]
@@ -186,6 +212,8 @@ class BackboneEngine(object):
         B = x.shape[0]
         dev = x.device
         size = x.shape[2]
+        self._cur_fwd = self._pf_fwd
+        self._pf_fwd += 1
         h = ops.pack_input(x.contiguous(), 16)
         nb = len(self.blocks)
 

@@ -7,6 +7,7 @@ mt19937 stream from torch.get_rng_state()).  The replay is used only after it ha
 crosses several generator blocks; otherwise every call goes to torch.
 """
 import ctypes as C
+import threading
 
 import torch
 
@@ -74,3 +75,67 @@ def bernoulli_u8(shape, p, kind, out=None):
         out.copy_(t)
         t = out
     return t, int(t.sum())
+
+
+def _numel(shape):
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n
+
+
+class MaskPrefetch(object):
+    """Pre-draws, on a host thread, the dropout masks of FUTURE train-mode forwards while the GPU is busy.
+
+    The thread replays torch's stream on a private copy of the generator state taken now.  Consumers whose probability
+    is not known yet (DropBlock's gamma depends on how many epochs the running session will take) and the next
+    session's nn.Linear init only need to be SKIPPED: they use a fixed number of 32-bit draws.  Every pre-drawn mask
+    remembers the generator state before and after it; `take` hands it out only if the live generator is exactly in
+    the `before` state (then moves it to `after`), so a wrong guess about what happens in between costs nothing but
+    the prefetch."""
+
+    def __init__(self, steps):
+        """steps: list of ('skip', n_words) | ('draw', key, uint8 CPU buffer [shape], p)."""
+        self.ok = replay_available()
+        self.results = {}
+        self.thread = None
+        if not self.ok:
+            return
+        self._state = torch.get_rng_state().clone()
+        self._steps = steps
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        lib = L.load()
+        blob = self._state
+        try:
+            for st in self._steps:
+                if st[0] == 'skip':
+                    if lib.sr_host_bernoulli(C.c_void_p(blob.data_ptr()), blob.numel(), 2, 0.0, int(st[1]), None) < 0:
+                        raise RuntimeError("skip failed")
+                else:
+                    _, key, buf, p = st
+                    before = blob.clone()
+                    ones = lib.sr_host_bernoulli(C.c_void_p(blob.data_ptr()), blob.numel(), 0, float(p), buf.numel(),
+                                                 C.c_void_p(buf.data_ptr()))
+                    if ones < 0:
+                        raise RuntimeError("draw failed")
+                    self.results[key] = (before, blob.clone(), buf, int(ones))
+        except Exception:
+            self.results = {}
+
+    def take(self, key, shape):
+        """-> (uint8 buffer, ones) or None.  Advances torch's live generator exactly as the draw would have."""
+        if self.thread is None:
+            return None
+        self.thread.join()
+        ent = self.results.pop(key, None)
+        if ent is None:
+            return None
+        before, after, buf, ones = ent
+        if tuple(buf.shape) != tuple(shape) or not torch.equal(torch.get_rng_state(), before):
+            self.results = {}          # the stream went somewhere else: everything drawn after this point is void too
+            return None
+        torch.set_rng_state(after)
+        return buf, ones

@@ -1,0 +1,86 @@
+"""The host replay of PyTorch's CPU Bernoulli stream (sr_host_bernoulli) and the mask prefetcher built on it."""
+import ctypes as C
+
+import pytest
+import torch
+
+from srb200 import host_rng, _lib as L
+
+
+@pytest.fixture(autouse=True)
+def _need_replay():
+    if not host_rng.replay_available():
+        pytest.skip("this torch build does not use the serial mt19937 bernoulli path; torch itself draws the masks")
+
+
+@pytest.mark.parametrize("kind,p,shape", [(0, 0.9, (7, 64, 21, 21)), (0, 0.5, (1, 3, 1001)), (1, 0.00123, (5, 320, 10, 10)),
+                                          (1, 0.5, (100003,)), (0, 1.0, (1000,)), (1, 0.0, (1000,))])
+def test_replay_equals_torch(kind, p, shape):
+    torch.manual_seed(77)
+    torch.rand(5)
+    s0 = torch.get_rng_state()
+    want = host_rng._torch_draw(shape, p, kind)
+    s_want = torch.get_rng_state()
+    torch.set_rng_state(s0)
+    got, ones = host_rng._replay_draw(shape, p, kind)
+    assert torch.equal(want, got) and ones == int(want.sum())
+    assert torch.equal(torch.get_rng_state(), s_want)
+    # and the stream continues identically afterwards (the next session's nn.Linear init)
+    a = torch.nn.Linear(640, 5, bias=False).weight.clone()
+    torch.set_rng_state(s_want)
+    b = torch.nn.Linear(640, 5, bias=False).weight.clone()
+    assert torch.equal(a, b)
+
+
+def test_dropout_mask_equals_functional_dropout():
+    import torch.nn.functional as F
+    shape = (9, 64, 42, 42)
+    torch.manual_seed(5)
+    m = F.dropout(torch.ones(shape), 0.1, True)
+    s1 = torch.get_rng_state()
+    torch.manual_seed(5)
+    keep, _ = host_rng.bernoulli_u8(shape, 1 - 0.1, 0)
+    assert torch.equal((m != 0).to(torch.uint8), keep) and torch.equal(s1, torch.get_rng_state())
+    assert float(m.max()) == float(torch.ones(1).div_(1 - 0.1))
+
+
+def test_skip_matches_linear_init_and_dropblock_draws():
+    torch.manual_seed(11)
+    s0 = torch.get_rng_state()
+    torch.nn.Linear(640, 5, bias=False)
+    torch.distributions.Bernoulli(0.01).sample((3, 320, 10, 10))
+    s1 = torch.get_rng_state()
+    blob = s0.clone()
+    n = 5 * 640 + 3 * 320 * 100
+    assert L.load().sr_host_bernoulli(C.c_void_p(blob.data_ptr()), blob.numel(), 2, 0.0, n, None) == 0
+    assert torch.equal(blob, s1)
+
+
+def test_mask_prefetch_is_exact_and_self_checking():
+    shapes = [(4, 64, 42, 42), (4, 160, 21, 21)]
+    torch.manual_seed(21)
+    start = torch.get_rng_state()
+    # what the main thread will do later: Linear init, mask 0, a DropBlock draw, mask 1
+    torch.nn.Linear(640, 5, bias=False)
+    m0 = torch.empty(shapes[0], dtype=torch.uint8).bernoulli_(0.9)
+    torch.distributions.Bernoulli(0.02).sample((4, 320, 10, 10))
+    m1 = torch.empty(shapes[1], dtype=torch.uint8).bernoulli_(0.9)
+    end = torch.get_rng_state()
+
+    torch.set_rng_state(start)
+    bufs = [torch.empty(s, dtype=torch.uint8) for s in shapes]
+    pf = host_rng.MaskPrefetch([('skip', 3200), ('draw', 'a', bufs[0], 0.9), ('skip', 4 * 320 * 100), ('draw', 'b', bufs[1], 0.9)])
+    torch.nn.Linear(640, 5, bias=False)
+    got0 = pf.take('a', shapes[0])
+    assert got0 is not None and torch.equal(got0[0], m0)
+    torch.distributions.Bernoulli(0.02).sample((4, 320, 10, 10))
+    got1 = pf.take('b', shapes[1])
+    assert got1 is not None and torch.equal(got1[0], m1) and torch.equal(torch.get_rng_state(), end)
+
+    # a consumer the plan did not foresee: the prefetch must refuse and leave the generator alone
+    torch.set_rng_state(start)
+    pf = host_rng.MaskPrefetch([('skip', 3200), ('draw', 'a', bufs[0], 0.9)])
+    torch.nn.Linear(640, 5, bias=False)
+    torch.rand(1)
+    live = torch.get_rng_state()
+    assert pf.take('a', shapes[0]) is None and torch.equal(torch.get_rng_state(), live)
