@@ -12,7 +12,8 @@
 //   N (out channels) <= 256 per CTA, both sub-tiles share every B (weight) stage.
 //   K                one pipeline stage = one tap x one KC-channel block (KC = 64/32/16 <-> 128/64/32-byte swizzle).
 //   accumulators     2 x N fp32 columns of TMEM, written by tcgen05.mma (cta_group::1, M = 128).
-//   warps            0: TMA producer (one lane)   1: TMEM alloc + MMA issue (one lane)   2-9: epilogue
+//   warps            0: TMA producer (one lane)   1, 2: MMA issue for sub-tile 0 / 1 (one lane each; warp 1 owns TMEM)
+//                    3-10: epilogue
 //   schedule         persistent: one CTA per SM walks (pixel tile, channel split) items; the producer prefetches across
 //                    tile boundaries and up to four TMEM accumulator stages let epilogue(i) overlap mainloop(i+1)
 //   epilogue         TMEM -> registers -> (+shift, +residual, LeakyReLU) -> bf16 NHWC, optionally through a shared
@@ -22,6 +23,7 @@
 //                    (BN scales are folded into both weight sets, the shifts are summed on the host).
 #include <cuda_bf16.h>
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include "common.h"
 #include "ptx.cuh"
@@ -30,20 +32,22 @@ namespace {
 
 using namespace srb;
 
-constexpr int kThreads = 320;       // 10 warps
-constexpr int kEpiWarps = 8;        // warps 2..9
+constexpr int kThreads = 352;       // 11 warps
+constexpr int kEpiWarp0 = 3;        // first epilogue warp
+constexpr int kEpiWarps = 8;        // warps 3..10
 constexpr int kEpiThreads = 256;
 constexpr int kSubRows = 128;       // UMMA M
 constexpr int kStagePitchBf16 = 80; // bytes per staged row (32 bf16 + pad, conflict-free 16-byte accesses)
 constexpr int kStagePitchF32 = 33;  // floats per staged row (32 fp32 + 1)
 
 struct PanelDev {
-    CUtensorMap tmA;  // rank 4: (C, W, H, N), box (KC, TW, TH, TN)
+    CUtensorMap tmA;  // rank 4: (C, W, H, N); box (KC, TW, TH, TN), or the tall box (KC, TW, 2*TH+2, 1) when `reuse`
     CUtensorMap tmB;  // rank 2: (taps*cin_pad, cout), box (KC, n_cta)
     int taps;
     int ncb;       // channel blocks per tap
     int kc_bytes;  // bytes per operand row per stage == swizzle span (32/64/128)
     int cin_pad;
+    int reuse;     // 3x3 panel, row-stacked tile: one tall A box per (dw, channel block) serves the three dh taps
 };
 
 struct ConvParams {
@@ -56,7 +60,7 @@ struct ConvParams {
     int acc_stages;
     int n_cta;
     int rows_sub;
-    int stages, stage_bytes, a_slot;
+    int nA, nB, a_slot, b_slot, sub_stride;   // A / B rings (slots, bytes per slot), byte offset of sub-tile 1 in an A slot
     int tmem_cols;
     int epi;
     float slope;
@@ -125,14 +129,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // Dynamic shared memory is only guaranteed 16-byte aligned; swizzle-128B tiles need 1024.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* staging = smem + (size_t)p.stages * p.stage_bytes;
+    uint8_t* ringB = smem + (size_t)p.nA * p.a_slot;
+    uint8_t* staging = ringB + (size_t)p.nB * p.b_slot;
 
-    __shared__ uint64_t full_bar[16];
-    __shared__ uint64_t empty_bar[16];
+    __shared__ uint64_t fullA[16];
+    __shared__ uint64_t emptyA[16];
+    __shared__ uint64_t fullB[16];
+    __shared__ uint64_t emptyB[16];
     __shared__ uint64_t tmem_full_bar[4];
     __shared__ uint64_t tmem_empty_bar[4];
     __shared__ uint32_t tmem_slot;
-    __shared__ float s_sum[256];
+    __shared__ __align__(16) float s_sum[256];   // per-channel sums (RAW_STATS) or the folded-BN shift table (ACT modes)
     __shared__ float s_sq[256];
 
     const int warp = threadIdx.x >> 5;
@@ -142,12 +149,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     const int acc_cols = 2 * p.n_cta;  // TMEM columns of one accumulator stage (two sub-tiles)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.stages; ++i) {
-            mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+        // two MMA-issuing warps (one per sub-tile) each commit on the consumer-side barriers
+        for (int i = 0; i < p.nA; ++i) {
+            mbar_init(&fullA[i], 1);
+            mbar_init(&emptyA[i], 2);
+        }
+        for (int i = 0; i < p.nB; ++i) {
+            mbar_init(&fullB[i], 1);
+            mbar_init(&emptyB[i], 2);
         }
         for (int i = 0; i < p.acc_stages; ++i) {
-            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_full_bar[i], 2);
             mbar_init(&tmem_empty_bar[i], kEpiWarps);
         }
         mbar_fence_init();
@@ -164,76 +176,109 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    // 32-bit shared addresses of every barrier / ring, computed once (see ptx.cuh: address-taking variants)
+    const uint32_t a_fullA = smem_u32(&fullA[0]), a_emptyA = smem_u32(&emptyA[0]);
+    const uint32_t a_fullB = smem_u32(&fullB[0]), a_emptyB = smem_u32(&emptyB[0]);
+    const uint32_t a_tfull = smem_u32(&tmem_full_bar[0]), a_tempty = smem_u32(&tmem_empty_bar[0]);
+    const uint32_t smem_base = smem_u32(smem), ringB_base = smem_u32(ringB);
 
     if (warp == 0) {
         // ================= TMA producer =================
+        // Two rings: an A slot holds the activation rows of one (tap | dw, channel block) step, a B slot one weight tile.
+        // With `reuse` one tall A box (2*TH+2 image rows) is loaded per (dw, channel block) and the three dh taps are
+        // row-shifted views of it, so the activations cross L2 -> SM three times per pixel instead of nine.
         if (lane == 0) {
-            int it = 0;
+            int sa = 0, sb = 0;
+            uint32_t phA = 0, phB = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const TileCoord tc = decode_tile(p, tile);
                 for (int pi = 0; pi < p.n_panels; ++pi) {
                     const PanelDev& pn = p.panel[pi];
                     const int kc = pn.kc_bytes >> 1;
-                    const uint32_t tx = (uint32_t)(2 * p.rows_sub + p.n_cta) * (uint32_t)pn.kc_bytes;
-                    for (int tap = 0; tap < pn.taps; ++tap) {
-                        const int dh = pn.taps == 9 ? tap / 3 - 1 : 0;
-                        const int dw = pn.taps == 9 ? tap % 3 - 1 : 0;
-                        for (int cb = 0; cb < pn.ncb; ++cb, ++it) {
-                            const int s = it % p.stages;
-                            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                            mbar_wait(&empty_bar[s], ph ^ 1u);
-                            uint8_t* st = smem + (size_t)s * p.stage_bytes;
-                            mbar_expect_tx(&full_bar[s], tx);
-                            tma_load_4d(st, &pn.tmA, &full_bar[s], cb * kc, tc.w0 + dw, tc.h0 + dh, tc.n0);
-                            tma_load_4d(st + p.a_slot, &pn.tmA, &full_bar[s], cb * kc, tc.w0 + dw, tc.h0 + dh + sub_dh,
-                                        tc.n0 + sub_dn);
-                            tma_load_2d(st + 2 * p.a_slot, &pn.tmB, &full_bar[s], tap * pn.cin_pad + cb * kc, tc.co0);
+                    const uint32_t txB = (uint32_t)p.n_cta * (uint32_t)pn.kc_bytes;
+                    const int outer = pn.reuse ? 3 : pn.taps;
+                    const int inner = pn.reuse ? 3 : 1;
+                    for (int o = 0; o < outer; ++o) {
+                        for (int cb = 0; cb < pn.ncb; ++cb) {
+                            mbar_wait_a(a_emptyA + 8u * sa, phA ^ 1u);
+                            const uint32_t slot = smem_base + (uint32_t)sa * (uint32_t)p.a_slot;
+                            const uint32_t fa = a_fullA + 8u * sa;
+                            if (pn.reuse) {
+                                mbar_expect_tx_a(fa, (uint32_t)((2 * p.TH + 2) * p.TW) * (uint32_t)pn.kc_bytes);
+                                tma_load_4d_a(slot, &pn.tmA, fa, cb * kc, tc.w0 + o - 1, tc.h0 - 1, tc.n0);
+                            } else {
+                                const int dh = pn.taps == 9 ? o / 3 - 1 : 0;
+                                const int dw = pn.taps == 9 ? o % 3 - 1 : 0;
+                                mbar_expect_tx_a(fa, (uint32_t)(2 * p.rows_sub) * (uint32_t)pn.kc_bytes);
+                                tma_load_4d_a(slot, &pn.tmA, fa, cb * kc, tc.w0 + dw, tc.h0 + dh, tc.n0);
+                                tma_load_4d_a(slot + (uint32_t)p.sub_stride, &pn.tmA, fa, cb * kc, tc.w0 + dw, tc.h0 + dh + sub_dh,
+                                              tc.n0 + sub_dn);
+                            }
+                            if (++sa == p.nA) { sa = 0; phA ^= 1u; }
+                            for (int j = 0; j < inner; ++j) {
+                                mbar_wait_a(a_emptyB + 8u * sb, phB ^ 1u);
+                                const int tap = pn.reuse ? j * 3 + o : o;
+                                mbar_expect_tx_a(a_fullB + 8u * sb, txB);
+                                tma_load_2d_a(ringB_base + (uint32_t)sb * (uint32_t)p.b_slot, &pn.tmB, a_fullB + 8u * sb,
+                                              tap * pn.cin_pad + cb * kc, tc.co0);
+                                if (++sb == p.nB) { sb = 0; phB ^= 1u; }
+                            }
                         }
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
+    } else if (warp == 1 || warp == 2) {
+        // ================= MMA issuers: warp 1 drives sub-tile 0, warp 2 sub-tile 1 =================
+        // (one thread can launch an MMA every ~50 cycles; an N = 64 MMA lasts 32, so a single issuer starves the pipe)
         if (lane == 0) {
+            const int sub = warp - 1;
             const uint32_t idesc = umma_idesc_bf16(kSubRows, (uint32_t)p.n_cta);
-            int it = 0, t = 0;
+            int sa = 0, sb = 0, t = 0;
+            uint32_t phA = 0, phB = 0;   // ring slot + phase, advanced without divisions (this thread paces the tensor pipe)
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
                 const int as = t % p.acc_stages;
                 const uint32_t use = (uint32_t)(t / p.acc_stages);
-                mbar_wait(&tmem_empty_bar[as], (use & 1u) ^ 1u);  // the epilogue has drained this accumulator
+                mbar_wait_a(a_tempty + 8u * as, (use & 1u) ^ 1u);  // the epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t acc = tmem_base + (uint32_t)(as * acc_cols);
+                const uint32_t acc = tmem_base + (uint32_t)(as * acc_cols + sub * p.n_cta);
                 bool first = true;
                 for (int pi = 0; pi < p.n_panels; ++pi) {
                     const PanelDev& pn = p.panel[pi];
                     const int ksteps = pn.kc_bytes >> 5;  // UMMA K = 16 bf16 = 32 bytes
-                    const int nk = pn.taps * pn.ncb;
-                    for (int kb = 0; kb < nk; ++kb, ++it) {
-                        const int s = it % p.stages;
-                        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                        mbar_wait(&full_bar[s], ph);
-                        tc_fence_after();
-                        const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
-                        for (int sub = 0; sub < 2; ++sub) {
-                            for (int ks = 0; ks < ksteps; ++ks) {
-                                const uint64_t da = umma_smem_desc(st + sub * p.a_slot + ks * 32, (uint32_t)pn.kc_bytes);
-                                const uint64_t db = umma_smem_desc(st + 2 * p.a_slot + ks * 32, (uint32_t)pn.kc_bytes);
-                                umma_f16(acc + (uint32_t)(sub * p.n_cta), da, db, idesc, (first && ks == 0) ? 0u : 1u);
-                            }
+                    const int nsteps = (pn.reuse ? 3 : pn.taps) * pn.ncb;
+                    const int inner = pn.reuse ? 3 : 1;
+                    const uint32_t dhi = umma_desc_hi((uint32_t)pn.kc_bytes);
+                    // byte offsets of the two sub-tile views inside an A slot, and their increment per dh tap
+                    const uint32_t sub_off = sub ? (pn.reuse ? (uint32_t)(p.TH * p.TW * pn.kc_bytes) : (uint32_t)p.sub_stride) : 0u;
+                    const uint32_t dh_step = pn.reuse ? (uint32_t)(p.TW * pn.kc_bytes) : 0u;
+                    for (int st = 0; st < nsteps; ++st) {
+                        mbar_wait_a(a_fullA + 8u * sa, phA);
+                        uint32_t a0 = smem_base + (uint32_t)sa * (uint32_t)p.a_slot + sub_off;
+                        for (int j = 0; j < inner; ++j, a0 += dh_step) {
+                            mbar_wait_a(a_fullB + 8u * sb, phB);
+                            tc_fence_after();
+                            const uint32_t alo = umma_desc_lo(a0);
+                            const uint32_t blo = umma_desc_lo(ringB_base + (uint32_t)sb * (uint32_t)p.b_slot);
+                            // descriptors advance by 32 bytes (2 units of 16) per K step inside the swizzle atom
+                            umma_f16_split(acc, alo, blo, dhi, idesc, first ? 0u : 1u);
+                            for (int ks = 1; ks < ksteps; ++ks) umma_f16_split(acc, alo + 2 * ks, blo + 2 * ks, dhi, idesc, 1u);
+                            first = false;
+                            umma_commit_a(a_emptyB + 8u * sb);  // frees the weight slot once the MMAs above have read it
+                            if (++sb == p.nB) { sb = 0; phB ^= 1u; }
                         }
-                        first = false;
-                        umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+                        umma_commit_a(a_emptyA + 8u * sa);
+                        if (++sa == p.nA) { sa = 0; phA ^= 1u; }
                     }
                 }
-                umma_commit(&tmem_full_bar[as]);
+                umma_commit_a(a_tfull + 8u * as);
             }
         }
     } else {
-        // ================= epilogue (warps 2..9): two warps per TMEM lane quarter, 16 columns each =================
-        const int et = threadIdx.x - 64;
+        // ================= epilogue (warps 3..10): two warps per TMEM lane quarter, 16 columns each =================
+        const int et = threadIdx.x - kEpiWarp0 * 32;
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;       // which 16 of the 32 columns of a chunk
+        const int half = (warp - kEpiWarp0) >> 2;  // which 16 of the 32 columns of a chunk
         const int m = q * 32 + lane;
         const int hw_sub = p.TH * p.TW;
         const int nl = m / hw_sub;
@@ -241,6 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         const int hl = rem / p.TW;
         const int wl = rem - hl * p.TW;
         const int nchunks = p.n_cta >> 5;
+        int shift_co0 = -1;
         int t = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
             const TileCoord tc = decode_tile(p, tile);
@@ -252,23 +298,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     s_sq[i] = 0.f;
                 }
                 named_bar_sync(1, kEpiThreads);
+            } else if (tc.co0 != shift_co0) {
+                // folded-BN shifts of this channel split -> shared memory (s_sum doubles as the shift table)
+                if (shift_co0 >= 0) named_bar_sync(1, kEpiThreads);   // everyone is done with the previous table
+                for (int i = et; i < p.n_cta; i += kEpiThreads) s_sum[i] = p.shift ? __ldg(p.shift + tc.co0 + i) : 0.f;
+                shift_co0 = tc.co0;
+                named_bar_sync(1, kEpiThreads);
             }
-            mbar_wait(&tmem_full_bar[as], use & 1u);
+            mbar_wait_a(a_tfull + 8u * as, use & 1u);
             tc_fence_after();
             const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols);
 
             for (int ch = 0; ch < nchunks; ++ch) {
                 const int c16 = ch * 32 + half * 16;     // first of this thread's 16 channels inside the CTA's N range
                 const int cbase = tc.co0 + c16;
-#pragma unroll 1
+                float vv[2][16];
+                tmem_ld16(acc + (uint32_t)c16, vv[0]);
+                tmem_ld16(acc + (uint32_t)(p.n_cta + c16), vv[1]);
+                tmem_ld_wait();
+#pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
                     const int n = tc.n0 + nl + sub * sub_dn;
                     const int h = tc.h0 + hl + sub * sub_dh;
                     const int w = tc.w0 + wl;
                     const bool valid = (m < p.rows_sub) && (n < p.B) && (h < p.H);
-                    float v[16];
-                    tmem_ld16(acc + (uint32_t)(sub * p.n_cta + c16), v);
-                    tmem_ld_wait();
+                    float* v = vv[sub];
                     const size_t pix = ((size_t)n * p.H + h) * p.W + w;
 
                     if (p.epi == SR_EPI_RAW_STATS) {
@@ -293,11 +347,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     }
 
                     // shift (+ residual) + LeakyReLU
-                    if (p.shift != nullptr) {
-                        const float4* sp = reinterpret_cast<const float4*>(p.shift + cbase);
+                    {
+                        const float4* sp = reinterpret_cast<const float4*>(s_sum + c16);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float4 s4 = __ldg(sp + j);
+                            const float4 s4 = sp[j];
                             v[4 * j] += s4.x; v[4 * j + 1] += s4.y; v[4 * j + 2] += s4.z; v[4 * j + 3] += s4.w;
                         }
                     }
@@ -413,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             // all of this warp's TMEM reads of the tile are complete: hand the accumulator back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+            if (lane == 0) mbar_arrive_a(a_tempty + 8u * as);
 
             if (p.epi == SR_EPI_RAW_STATS) {
                 named_bar_sync(1, kEpiThreads);
@@ -561,7 +615,7 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
     p.tmem_cols = 512;                                 // one persistent CTA per SM owns all of TMEM
     p.n_splits = ns;
 
-    int kc_max = 0;
+    int kc_max = 0, any_reuse = 0;
     for (int i = 0; i < a->n_panels; ++i) {
         const sr_conv_panel& sp = a->panel[i];
         if (!sp.act || !sp.wgt) return fail(SR_E_ARG, "sr_conv: null panel pointer");
@@ -574,13 +628,18 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
         pd.cin_pad = sp.cin_pad;
         pd.kc_bytes = kc_bytes_for(sp.cin_pad);
         pd.ncb = (sp.cin_pad * 2 + pd.kc_bytes - 1) / pd.kc_bytes;
+        // Tap reuse: a row-stacked tile of one image (84x84 / 42x42 maps) covers 2*TH consecutive image rows, so one tall
+        // box with a one-row halo above and below holds every dh tap of a given dw.
+        pd.reuse = (sp.taps == 9 && tile.stack_h && tile.TN == 1 && !getenv("SRB_NO_TAP_REUSE")) ? 1 : 0;
+        any_reuse |= pd.reuse;
         kc_max = std::max(kc_max, pd.kc_bytes);
         const int kc = pd.kc_bytes / 2;
         {
             cuuint64_t gdim[4] = {(cuuint64_t)sp.cin_pad, (cuuint64_t)a->width, (cuuint64_t)a->height, (cuuint64_t)a->batch};
             cuuint64_t gstr[3] = {(cuuint64_t)sp.cin_pad * 2, (cuuint64_t)sp.cin_pad * 2 * a->width,
                                   (cuuint64_t)sp.cin_pad * 2 * a->width * a->height};
-            cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)tile.TW, (cuuint32_t)tile.TH, (cuuint32_t)tile.TN};
+            cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)tile.TW,
+                                 (cuuint32_t)(pd.reuse ? 2 * tile.TH + 2 : tile.TH), (cuuint32_t)tile.TN};
             cuuint32_t est[4] = {1, 1, 1, 1};
             CUresult r = encode(&pd.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(sp.act), gdim, gstr, box,
                                 est, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(pd.kc_bytes),
@@ -598,9 +657,12 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
             if (r != CUDA_SUCCESS) return fail(SR_E_CUDA, "sr_conv: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
         }
     }
-    p.a_slot = kSubRows * kc_max;
-    const int b_slot = (int)align_up((int64_t)p.n_cta * kc_max, 1024);
-    p.stage_bytes = 2 * p.a_slot + b_slot;
+    // A slot: two 128-row sub-tiles, or the tall box plus the 128-row window that starts at its last tap offset
+    p.sub_stride = kSubRows * kc_max;
+    int a_rows = 2 * kSubRows;
+    if (any_reuse) a_rows = std::max(a_rows, (tile.TH + 2) * tile.TW + kSubRows);
+    p.a_slot = (int)align_up((int64_t)a_rows * kc_max, 1024);
+    p.b_slot = (int)align_up((int64_t)p.n_cta * kc_max, 1024);
     int staging = 0;   // the producer prefetches the next tile during the epilogue: staging cannot alias the pipeline
     if (a->epilogue == SR_EPI_ACT_POOL2) staging = 2 * kSubRows * kStagePitchBf16;
     if (a->epilogue == SR_EPI_ACT_AVG) staging = 2 * kSubRows * kStagePitchF32 * 4;
@@ -617,9 +679,23 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
     });
     if (attr_err != cudaSuccess)
         return fail(SR_E_CUDA, "sr_conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
-    p.stages = std::min(12, (max_dyn - 1024 - staging) / p.stage_bytes);
-    if (p.stages < 2) return fail(SR_E_ARG, "sr_conv: pipeline does not fit in shared memory");
-    const int dyn_smem = p.stages * p.stage_bytes + staging + 1024;
+    // Ring sizes: maximise the prefetch distance min((nA-1) * r, nB-1) in units of one weight-tile step, r = weight
+    // tiles per A slot (3 with tap reuse).
+    const int budget = max_dyn - 1024 - staging;
+    const int r = any_reuse ? 3 : 1;
+    int best = -1;
+    for (int nA = 2; nA <= 12; ++nA) {
+        const int nB = std::min(16, (budget - nA * p.a_slot) / p.b_slot);
+        if (nB < r + 1) break;
+        const int depth = std::min((nA - 1) * r, nB - 1);
+        if (depth > best) {
+            best = depth;
+            p.nA = nA;
+            p.nB = nB;
+        }
+    }
+    if (best < 0) return fail(SR_E_ARG, "sr_conv: pipeline does not fit in shared memory");
+    const int dyn_smem = p.nA * p.a_slot + p.nB * p.b_slot + staging + 1024;
 
     const int tiles_n = tile.stack_h ? a->batch : (a->batch + 2 * tile.TN - 1) / (2 * tile.TN);
     p.total_tiles = tile.tiles_w * tile.tiles_h * tiles_n * ns;

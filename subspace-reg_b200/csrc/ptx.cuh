@@ -116,6 +116,26 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same MMA with the shared-memory descriptors given as 32-bit halves: lo = (address >> 4) | LBO field, hi = SBO | version |
+// swizzle (constant per operand layout).  The single issuing thread is the pacing resource of a tcgen05 kernel (one MMA
+// every 32-80 cycles), so the per-MMA instruction count matters: this form needs no 64-bit arithmetic.
+__device__ __forceinline__ void umma_f16_split(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t swizzle_bytes) {
+    const uint32_t layout = swizzle_bytes == 128 ? 2u : (swizzle_bytes == 64 ? 4u : 6u);
+    return ((swizzle_bytes * 8u) >> 4) | (1u << 14) | (layout << 29);   // SBO | version 1 | swizzle mode
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+
 // Arrive on an mbarrier when every previously issued tcgen05.mma of this thread has retired
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -175,6 +195,55 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
     d |= (N >> 3) << 17;   // N / 8
     d |= (M >> 4) << 24;   // M / 16
     return d;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Address-taking variants (32-bit shared::cta addresses computed ONCE by the caller).  Passing pointers makes the compiler
+// redo the generic->shared conversion (S2UR SR_CgaCtaId + ULEA, ~50 cycles each) at every barrier operation, which is
+// what paced the single MMA-issuing thread in the first version of the convolution kernel.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_a(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_a(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) {
+            printf("srb200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];\n" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
 }
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
