@@ -55,6 +55,11 @@ int32_t sr_bn_fold(const float* gamma, const float* beta, const float* running_m
 int32_t sr_pack_weight(const float* w_oihw, const float* scale, void* w_packed_bf16, int32_t cout, int32_t cin,
                        int32_t kh, int32_t kw, int32_t cin_pad, void* stream);
 
+/* AdaptiveAvgPool2d(1) on a bf16 NHWC map -> fp32 [batch, channels] (resnet_language.py:179-181 when the last block is
+ * pooled, i.e. resnet12; resnet18's last block averages inside sr_conv / sr_bn_apply). */
+int32_t sr_global_avg(const void* x_nhwc_bf16, float* y, int32_t batch, int32_t height, int32_t width, int32_t channels,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Backbone: implicit-GEMM convolution on tcgen05 / TMEM fed by TMA
  * Replaces nn.Conv2d + nn.BatchNorm2d(eval) + LeakyReLU + residual add + MaxPool2d / AdaptiveAvgPool2d

@@ -60,6 +60,7 @@ struct ConvParams {
     int acc_stages;
     int n_cta;
     int rows_sub;
+    int bgroup;   // weight tiles per B slot / barrier round (3 = the dh taps of a tall A box travel together)
     int nA, nB, a_slot, b_slot, sub_stride;   // A / B rings (slots, bytes per slot), byte offset of sub-tile 1 in an A slot
     int tmem_cols;
     int epi;
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     // Dynamic shared memory is only guaranteed 16-byte aligned; swizzle-128B tiles need 1024.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* ringB = smem + (size_t)p.nA * p.a_slot;
-    uint8_t* staging = ringB + (size_t)p.nB * p.b_slot;
+    uint8_t* staging = ringB + (size_t)p.nB * p.bgroup * p.b_slot;
 
     __shared__ uint64_t fullA[16];
     __shared__ uint64_t emptyA[16];
@@ -215,12 +216,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                                               tc.n0 + sub_dn);
                             }
                             if (++sa == p.nA) { sa = 0; phA ^= 1u; }
-                            for (int j = 0; j < inner; ++j) {
+                            const int grp = pn.reuse ? p.bgroup : 1;   // weight tiles per barrier round
+                            for (int j = 0; j < inner; j += grp) {
                                 mbar_wait_a(a_emptyB + 8u * sb, phB ^ 1u);
-                                const int tap = pn.reuse ? j * 3 + o : o;
-                                mbar_expect_tx_a(a_fullB + 8u * sb, txB);
-                                tma_load_2d_a(ringB_base + (uint32_t)sb * (uint32_t)p.b_slot, &pn.tmB, a_fullB + 8u * sb,
-                                              tap * pn.cin_pad + cb * kc, tc.co0);
+                                mbar_expect_tx_a(a_fullB + 8u * sb, txB * (uint32_t)grp);
+                                for (int g = 0; g < grp; ++g) {
+                                    const int tap = pn.reuse ? (j + g) * 3 + o : o;
+                                    tma_load_2d_a(ringB_base + (uint32_t)(sb * p.bgroup + g) * (uint32_t)p.b_slot, &pn.tmB,
+                                                  a_fullB + 8u * sb, tap * pn.cin_pad + cb * kc, tc.co0);
+                                }
                                 if (++sb == p.nB) { sb = 0; phB ^= 1u; }
                             }
                         }
@@ -255,15 +259,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     for (int st = 0; st < nsteps; ++st) {
                         mbar_wait_a(a_fullA + 8u * sa, phA);
                         uint32_t a0 = smem_base + (uint32_t)sa * (uint32_t)p.a_slot + sub_off;
-                        for (int j = 0; j < inner; ++j, a0 += dh_step) {
+                        const int grp = pn.reuse ? p.bgroup : 1;
+                        for (int j = 0; j < inner; j += grp) {
                             mbar_wait_a(a_fullB + 8u * sb, phB);
                             tc_fence_after();
-                            const uint32_t alo = umma_desc_lo(a0);
-                            const uint32_t blo = umma_desc_lo(ringB_base + (uint32_t)sb * (uint32_t)p.b_slot);
-                            // descriptors advance by 32 bytes (2 units of 16) per K step inside the swizzle atom
-                            umma_f16_split(acc, alo, blo, dhi, idesc, first ? 0u : 1u);
-                            for (int ks = 1; ks < ksteps; ++ks) umma_f16_split(acc, alo + 2 * ks, blo + 2 * ks, dhi, idesc, 1u);
-                            first = false;
+                            uint32_t b0 = ringB_base + (uint32_t)(sb * p.bgroup) * (uint32_t)p.b_slot;
+                            for (int g = 0; g < grp; ++g, a0 += dh_step, b0 += (uint32_t)p.b_slot) {
+                                const uint32_t alo = umma_desc_lo(a0);
+                                const uint32_t blo = umma_desc_lo(b0);
+                                // descriptors advance by 32 bytes (2 units of 16) per K step inside the swizzle atom
+                                umma_f16_split(acc, alo, blo, dhi, idesc, first ? 0u : 1u);
+                                for (int ks = 1; ks < ksteps; ++ks)
+                                    umma_f16_split(acc, alo + 2 * ks, blo + 2 * ks, dhi, idesc, 1u);
+                                first = false;
+                            }
                             umma_commit_a(a_emptyB + 8u * sb);  // frees the weight slot once the MMAs above have read it
                             if (++sb == p.nB) { sb = 0; phB ^= 1u; }
                         }
@@ -679,23 +688,36 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
     });
     if (attr_err != cudaSuccess)
         return fail(SR_E_CUDA, "sr_conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
-    // Ring sizes: maximise the prefetch distance min((nA-1) * r, nB-1) in units of one weight-tile step, r = weight
-    // tiles per A slot (3 with tap reuse).
+    // Ring sizes.  With tap reuse the three dh weight tiles of an A slot travel under ONE barrier when that fits (the
+    // MMA-issuing threads pay ~200 instructions per barrier round, so fewer, larger rounds keep the tensor pipe busier);
+    // otherwise maximise the prefetch distance min((nA-1) * r, nB-1) in weight-tile steps, r = weight tiles per A slot.
     const int budget = max_dyn - 1024 - staging;
-    const int r = any_reuse ? 3 : 1;
+    p.bgroup = 1;
     int best = -1;
-    for (int nA = 2; nA <= 12; ++nA) {
-        const int nB = std::min(16, (budget - nA * p.a_slot) / p.b_slot);
-        if (nB < r + 1) break;
-        const int depth = std::min((nA - 1) * r, nB - 1);
-        if (depth > best) {
-            best = depth;
+    if (any_reuse && getenv("SRB_BGROUP")) {   // measured slower on B200 (12.4 vs 11.4 ms per 1024 images): off by default
+        const int nA = std::min(4, (budget - 2 * 3 * p.b_slot) / p.a_slot);
+        if (nA >= 2) {
+            p.bgroup = 3;
             p.nA = nA;
-            p.nB = nB;
+            p.nB = std::min(nA + 1, (budget - nA * p.a_slot) / (3 * p.b_slot));
+            best = 1;
+        }
+    }
+    if (best < 0) {
+        const int r = any_reuse ? 3 : 1;
+        for (int nA = 2; nA <= 12; ++nA) {
+            const int nB = std::min(16, (budget - nA * p.a_slot) / p.b_slot);
+            if (nB < r + 1) break;
+            const int depth = std::min((nA - 1) * r, nB - 1);
+            if (depth > best) {
+                best = depth;
+                p.nA = nA;
+                p.nB = nB;
+            }
         }
     }
     if (best < 0) return fail(SR_E_ARG, "sr_conv: pipeline does not fit in shared memory");
-    const int dyn_smem = p.nA * p.a_slot + p.nB * p.b_slot + staging + 1024;
+    const int dyn_smem = p.nA * p.a_slot + p.nB * p.bgroup * p.b_slot + staging + 1024;
 
     const int tiles_n = tile.stack_h ? a->batch : (a->batch + 2 * tile.TN - 1) / (2 * tile.TN);
     p.total_tiles = tile.tiles_w * tile.tiles_h * tiles_n * ns;

@@ -200,7 +200,30 @@ __global__ void bn_apply_avg_kernel(const BnApplyParams p) {
     for (int j = 0; j < 8; ++j) o[j] = acc[j] / (float)HW;
 }
 
+// bf16 NHWC [B,H,W,C] -> fp32 [B,C] mean over H x W (AdaptiveAvgPool2d(1) after a pooled last block: resnet12)
+__global__ void global_avg_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int B, int HW, int C) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * C) return;
+    const int c = (int)(i % C);
+    const int64_t n = i / C;
+    float acc = 0.f;
+    for (int q = 0; q < HW; ++q) acc += __bfloat162float(x[(n * HW + q) * C + c]);
+    y[i] = acc / (float)HW;
+}
+
 }  // namespace
+
+extern "C" int32_t sr_global_avg(const void* x_nhwc_bf16, float* y, int32_t batch, int32_t height, int32_t width,
+                                 int32_t channels, void* stream_v) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (!x_nhwc_bf16 || !y || batch < 1 || height < 1 || width < 1 || channels < 1)
+        return fail(SR_E_ARG, "sr_global_avg: bad arguments");
+    const int64_t total = (int64_t)batch * channels;
+    global_avg_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x_nhwc_bf16), y,
+                                                                          batch, height * width, channels);
+    SR_CUDA_OK(cudaGetLastError());
+    return SR_OK;
+}
 
 extern "C" int32_t sr_pack_input(const float* x, void* y, int32_t batch, int32_t channels, int32_t height, int32_t width,
                                  int32_t cpad, void* stream_v) {

@@ -114,15 +114,19 @@ class BackboneEngine(object):
             if b['downsample']:
                 epi = L.SR_EPI_ACT_POOL2 if b['pool'] == 2 else L.SR_EPI_ACT
                 out = ops.conv([(h2, w['w3']), (h, w['wd'])], cout, shift=w['s3'], slope=SLOPE, epilogue=epi)
-                if last:
-                    raise RuntimeError("srb200: a pooled last block needs the separate average kernel (resnet12) - "
-                                       "not built in this round")
+                if last:                                    # resnet12: pooled last block, then AdaptiveAvgPool2d(1)
+                    if taps is not None:
+                        taps.append(out)
+                    out = ops.global_avg(out)
             else:
-                epi = L.SR_EPI_ACT_AVG if last else L.SR_EPI_ACT
+                # the last block normally averages inside the conv epilogue; is_feat=True needs the map itself (f3)
+                epi = L.SR_EPI_ACT_AVG if (last and taps is None) else L.SR_EPI_ACT
                 out = ops.conv([(h2, w['w3'])], cout, shift=w['s3'], residual=h, slope=SLOPE, epilogue=epi)
-            if taps is not None and not last:
-                if bi + 1 == nb or self.blocks[bi + 1]['prefix'].endswith('.0'):
+                if last and taps is not None:
                     taps.append(out)
+                    out = ops.global_avg(out)
+            if taps is not None and not last and self.blocks[bi + 1]['prefix'].endswith('.0'):
+                taps.append(out)                            # f0, f1, f2: outputs of layer1..3
             h = out
         return h
 
@@ -248,4 +252,6 @@ class BackboneEngine(object):
                 h = ops.bn_apply(r3, mu3, is3, m.bn3.weight.detach(), m.bn3.bias.detach(), res_act=h, lrelu=True,
                                  slope=SLOPE, pool=pool, keep=keep, keep_scale=scale)
         self.invalidate()   # running statistics moved: the folded weights are stale
+        if h.dim() == 4:    # resnet12: the last block is pooled 2x2, the global average follows
+            h = ops.global_avg(h)
         return h

@@ -362,3 +362,13 @@ def score_logits(logits, labels, confusion=None):
     L.check(L.load().sr_score_logits(C.byref(a), _stream()), "sr_score_logits")
     LAUNCHES[0] += 1
     return {"pred": pred, "counts": counts, "loss_sum": loss_sum}
+
+
+def global_avg(x_nhwc):
+    """bf16 NHWC [B,H,W,C] -> fp32 [B,C] (AdaptiveAvgPool2d(1))."""
+    B, H, W, Cc = x_nhwc.shape
+    y = torch.empty((B, Cc), dtype=torch.float32, device=x_nhwc.device)
+    rc = L.load().sr_global_avg(_ptr(x_nhwc, torch.bfloat16, "x"), _ptr(y), B, H, W, Cc, _stream())
+    L.check(rc, "sr_global_avg")
+    LAUNCHES[0] += 1
+    return y

@@ -72,3 +72,26 @@ def test_backbone_linearity_in_last_residual():
         f_again = net.features(x)
     assert torch.equal(f_all, f_again)
     assert torch.equal(f_all[37:150], f_part)
+
+
+@pytest.mark.parametrize("model", ["resnet18", "resnet12"])
+def test_backbone_features_and_taps_vs_oracle(model):
+    """Eval-mode features of both models in model_pool against the fp32 oracle (bf16 tensor-core convolutions: rel-l2
+    below 1e-2), and the is_feat=True surface: [f0, f1, f2, f3, feat] with the reference's shapes."""
+    from models.util import create_model
+    from oracle import backbone as obb, init as oinit
+    from srb200 import synthetic
+    opt = synthetic.default_opt(1, model=model)
+    net = synthetic.init_model(create_model, opt, 1).cuda().eval()
+    sd = oinit.init_state_dict(1, model=model)
+    x = synthetic.make_world(1, n_sessions=1, n_base_batch=12).base_val_loader.batches[0][0]
+    plan = obb.block_plan(model, True)
+    with torch.no_grad():
+        want = obb.features(sd, plan, x, False, obb.new_counters(plan))
+        feats, logits = net(x.cuda(), is_feat=True)
+        got = net.features(x.cuda())
+    rel = ((got.cpu() - want).norm() / want.norm()).item()
+    assert rel < 1e-2, rel
+    assert [tuple(f.shape[1:]) for f in feats] == [(64, 42, 42), (160, 21, 21), (320, 10, 10), (640, 5, 5), (640,)]
+    assert ((feats[-1].cpu() - want).norm() / want.norm()).item() < 1e-2
+    assert logits.shape == (12, 60)
