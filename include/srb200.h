@@ -231,6 +231,10 @@ int32_t sr_linear_fwd(const float* x, const float* w, const float* bias, int32_t
                       void* stream);
 int32_t sr_linear_bwd(const float* dy, const float* x, int32_t n, int32_t k, int32_t m, float* dw, float* dbias,
                       void* stream);
+/* learn_mapping.py:50-62 pieces: nn.MSELoss (mean) value + gradient, and the momentum-free SGD step with weight decay.
+ * loss[0] += mean((y-target)^2) (caller zeroes it); dy = 2 (y - target) / n;  param -= lr * (grad + weight_decay * param). */
+int32_t sr_mse_grad(const float* y, const float* target, int64_t n, float* dy, float* loss, void* stream);
+int32_t sr_sgd_update(float* param, const float* grad, int64_t n, float lr, float weight_decay, void* stream);
 /* out[0] = sum((a-b)^2)  (torch.norm(a-b)**2, :90,232,239). */
 int32_t sr_sqdist(const float* a, const float* b, int64_t n, float* out, void* stream);
 /* out = (a-b) * scale * gout[0] * (sq ? 1/sqrt(sq[0]), 0 when sq[0]==0 : 1): backward of s*||a-b||^2 (sq NULL,

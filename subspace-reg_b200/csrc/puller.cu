@@ -126,7 +126,49 @@ __global__ void __launch_bounds__(256) project_rows_kernel(const float* __restri
         out[(int64_t)i * d + k] = s;
     }
 }
+// MSELoss(mean) forward + gradient: loss[0] += sum((y-t)^2)/n (caller zeroes it); dy = 2 (y - t) / n
+__global__ void mse_grad_kernel(const float* __restrict__ y, const float* __restrict__ t, int64_t n, float* __restrict__ dy,
+                                float* __restrict__ loss) {
+    __shared__ double red[32];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0.0;
+    if (i < n) {
+        const float dlt = y[i] - t[i];
+        dy[i] = 2.f * dlt / (float)n;
+        s = (double)dlt * (double)dlt;
+    }
+    s = warp_sum_d(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += red[k];
+        atomicAdd(loss, (float)(tot / (double)n));
+    }
+}
+
+// torch.optim.SGD without momentum: p -= lr * (g + wd * p)
+__global__ void sgd_update_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t n, float lr, float wd) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = p[i] - lr * fmaf(wd, p[i], g[i]);
+}
 }  // namespace
+
+extern "C" int32_t sr_mse_grad(const float* y, const float* target, int64_t n, float* dy, float* loss, void* stream_v) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (!y || !target || !dy || !loss || n < 1) return fail(SR_E_ARG, "sr_mse_grad: bad arguments");
+    mse_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(y, target, n, dy, loss);
+    SR_CUDA_OK(cudaGetLastError());
+    return SR_OK;
+}
+
+extern "C" int32_t sr_sgd_update(float* param, const float* grad, int64_t n, float lr, float weight_decay, void* stream_v) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (!param || !grad || n < 1) return fail(SR_E_ARG, "sr_sgd_update: bad arguments");
+    sgd_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(param, grad, n, lr, weight_decay);
+    SR_CUDA_OK(cudaGetLastError());
+    return SR_OK;
+}
 
 extern "C" int32_t sr_semantic_pullers(const float* novel_embeds, const float* base_embeds, const float* base_weight,
                                        int32_t n_novel, int32_t n_base, int32_t embed_dim, int32_t dim, float temperature,

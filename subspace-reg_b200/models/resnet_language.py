@@ -44,6 +44,14 @@ class LangPuller(nn.Module):
         self._factor = None      # (key, qt, q_rows, identity) cache: W0 is constant for a whole run
 
     def _load(self, vocab):
+        desc = getattr(self.opt, 'description_embed_path', None)
+        if desc is not None:
+            # BASELINE config 3 (ii): label-description embeddings (description_embeds/*.pickle: dict label -> Tensor[768]).
+            # The reference ships the pickles but no consumer; they enter through the same two puller modes.
+            import pickle
+            with open(desc, "rb") as f:
+                table = pickle.load(f)
+            return torch.stack([torch.as_tensor(table[name]).float() for name in vocab], 0).cuda().contiguous()
         e = get_embeds(self._path, vocab).float().cuda()
         if self.opt.glove:       # the first 300 dims of the saved vectors are GloVe
             e = e[:, :300].contiguous()

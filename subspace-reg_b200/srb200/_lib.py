@@ -18,7 +18,7 @@ EXPORTS = [
     "sr_last_error", "sr_version", "sr_check_device", "sr_pack_input", "sr_bn_fold", "sr_pack_weight", "sr_conv",
     "sr_bn_finalize", "sr_bn_apply", "sr_subspace_factor_workspace_bytes", "sr_subspace_factor",
     "sr_head_workspace_bytes", "sr_head_run", "sr_eval_logits", "sr_semantic_pullers", "sr_linear_fwd",
-    "sr_linear_bwd", "sr_sqdist", "sr_diff_scale", "sr_project_rows", "sr_score_logits", "sr_host_bernoulli", "sr_global_avg",
+    "sr_linear_bwd", "sr_sqdist", "sr_diff_scale", "sr_project_rows", "sr_score_logits", "sr_host_bernoulli", "sr_global_avg", "sr_mse_grad", "sr_sgd_update",
 ]
 
 
@@ -113,6 +113,10 @@ def load():
     lib.sr_head_run.argtypes = [C.POINTER(HeadArgs), vp]
     lib.sr_eval_logits.restype = i32
     lib.sr_eval_logits.argtypes = [C.POINTER(EvalArgs), vp]
+    lib.sr_mse_grad.restype = i32
+    lib.sr_mse_grad.argtypes = [vp, vp, i64, vp, vp, vp]
+    lib.sr_sgd_update.restype = i32
+    lib.sr_sgd_update.argtypes = [vp, vp, i64, f32, f32, vp]
     lib.sr_global_avg.restype = i32
     lib.sr_global_avg.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.sr_host_bernoulli.restype = i64

@@ -119,3 +119,60 @@ def test_validate_and_eval_base_api(word_embed_dir):
     logits = net(world.base_val_loader.batches[0][0].cuda())
     want = (logits.argmax(1).cpu() == world.base_val_loader.batches[0][1]).float().mean().item() * 100
     assert abs(acc - want) < 1e-4
+
+
+def test_fit_linear_map_matches_learn_mapping_recipe(word_embed_dir):
+    """learn_mapping.py:41-67 on the B200 kernels vs the same loop in fp64 torch: 200 full-batch SGD steps (lr 1.0,
+    wd 5e-4, MSE) from the same init."""
+    from srb200 import mapping
+    g = torch.Generator().manual_seed(0)
+    E = torch.randn(60, 300, generator=g) * 0.3
+    T = torch.randn(60, 640, generator=g) * 0.05
+    init = {'map.weight': torch.randn(640, 300, generator=g) * 0.02, 'map.bias': torch.zeros(640)}
+    sd, losses = mapping.fit_linear_map(E.cuda(), T.cuda(), epochs=200, lr=1.0, weight_decay=5e-4, init=init)
+    W = init['map.weight'].double().clone().requires_grad_(True)
+    b = init['map.bias'].double().clone().requires_grad_(True)
+    opt = torch.optim.SGD([W, b], lr=1.0, weight_decay=5e-4)
+    ref = []
+    for _ in range(200):
+        loss = torch.nn.functional.mse_loss(E.double() @ W.t() + b, T.double())
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ref.append(loss.item())
+    np.testing.assert_allclose(losses, ref, rtol=1e-4)
+    assert ((sd['map.weight'].cpu().double() - W.detach()).abs().max() / W.detach().abs().max()).item() < 1e-4
+    assert ((sd['map.bias'].cpu().double() - b.detach()).abs().max() / (b.detach().abs().max() + 1e-12)).item() < 1e-3
+
+
+def test_description_embedding_pullers(tmp_path, word_embed_dir):
+    """Config 3 (ii): 768-d label-description embeddings through the softmax-mix puller and through a LinearMap fitted
+    with the learn_mapping recipe; oracle = the restated LangPuller with the same embeddings assigned directly."""
+    import pickle
+    from models.resnet_language import LangPuller
+    from oracle import regularizer as rg
+    from srb200 import mapping, synthetic
+    g = torch.Generator().manual_seed(4)
+    table = {name: torch.randn(768, generator=g) * 0.2 for name in synthetic.LABELS}
+    path = tmp_path / "miniImageNet_bert-base-cased_layer6.pickle"
+    with open(path, "wb") as f:
+        pickle.dump(table, f)
+    base, sessions = synthetic.class_split(1)
+    vb = [synthetic.LABELS[c] for c in base]
+    vn = [synthetic.LABELS[c] for c in sessions[0]]
+    opt = synthetic.default_opt(1, word_embed_path=word_embed_dir, attraction_override=None, temperature=3.0,
+                                description_embed_path=str(path))
+    lp = LangPuller(opt, vb, vn)
+    assert lp.base_embeds.shape == (60, 768) and lp.novel_embeds.shape == (5, 768)
+    W0 = torch.randn(60, 640, generator=g) * 0.04
+    o = rg.Puller.__new__(rg.Puller)
+    o.opt, o.mapping = opt, None
+    o.base_embeds = torch.stack([table[n] for n in vb])
+    o.novel_embeds = torch.stack([table[n] for n in vn])
+    want = o.pullers(W0)
+    got = lp(W0.cuda())
+    assert ((got.cpu() - want).abs().max() / want.abs().max()).item() < 1e-5
+    sd, _ = mapping.fit_linear_map(lp.base_embeds, W0.cuda(), epochs=50, seed=9)
+    lp.create_pulling_mapping({k: v.cpu() for k, v in sd.items()})
+    o.set_mapping({k: v.cpu() for k, v in sd.items()})
+    assert ((lp(W0.cuda()).cpu() - o.pullers(W0)).abs().max() / o.pullers(W0).abs().max()).item() < 1e-5
