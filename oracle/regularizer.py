@@ -52,7 +52,10 @@ class Puller(object):
     def update_novel(self, vocab_novel):                     # :56-65
         self.novel_embeds = self._load(vocab_novel)
 
-    def set_mapping(self, state_dict):                       # :67-72, LinearMap = nn.Linear(indim, 640)
+    def set_mapping(self, state_dict, base_weight_size=640):  # create_pulling_mapping :67-72
+        # LinearMap(indim, outdim) is CONSTRUCTED (default nn.Linear init, which draws from the CPU generator) before
+        # load_state_dict overwrites it - every session; the draws matter for the dropout masks that follow.
+        torch.nn.Linear(self.novel_embeds.size(1), base_weight_size)
         self.mapping = (state_dict['map.weight'].float(), state_dict['map.bias'].float())
 
     def pullers(self, base_weight):                          # forward :74-87

@@ -215,7 +215,10 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
             # the next session's dropout masks are drawn on a host thread while the GPU runs this session's cache build
             # and head loop (verified against the live generator when they are consumed)
             nxt = [n_sup] + ([n_mem + 25] if (opt.memory_replay == 1) else [])
-            net.engine().start_mask_prefetch(nxt, skip_words_first=opt.n_ways * W_cols)
+            skip = opt.n_ways * W_cols                       # next session's nn.Linear(640, n_ways) init
+            if use_pull and opt.attraction_override == "mapping_linear_label2image":
+                skip += lang_puller.novel_embeds.size(1) * W_cols + W_cols   # LinearMap re-created every session
+            net.engine().start_mask_prefetch(nxt, skip_words_first=skip)
         tp1 = _tick()
         ph['train_pass'] += tp1 - tp0
         W = net.classifier.weight.data
