@@ -598,7 +598,7 @@ int32_t launch_head(const HeadParams& p, int grid, size_t dyn, cudaStream_t stre
 extern "C" int64_t sr_head_workspace_bytes(const sr_head_args* a) {
     if (!a) return 0;
     int64_t n = head_layout(a).total;
-    if (a->dim >= 32 && a->dim % 32 == 0) n = std::max<int64_t>(n, srb::head_small_workspace_bytes(a));
+    if (a->dim >= 64 && a->dim % 64 == 0) n = std::max<int64_t>(n, srb::head_small_workspace_bytes(a));
     return n;
 }
 

@@ -47,7 +47,7 @@ struct HeadCtrl {          // lives at the start of the workspace (zeroed by the
     float prev_loss;
     int error;
     int pad[2];
-    unsigned long long t_ns[4];   // CTA 0 wall time (ns) in phase 1 / barrier 1 / phase 2 / barrier 2 (profiling aid)
+    unsigned long long t_ns[6];   // profiling aid: CTA 0 ns in phase 1 / barrier 1 / phase 2 / barrier 2; loss CTA, pull CTA phase 1
     double norm_base_sq;   // ||W[:nb] - W0||_F^2
     double norm_prev_sq;   // ||W[nb:nb+np] - Wres||_F^2
 };

@@ -22,14 +22,14 @@ using namespace srb;
 
 constexpr int kT = 256;
 constexpr int DC = 8;     // feature columns per column CTA
-constexpr int KC = 32;    // k-chunk of the W stream (phase 1) / n-chunk of the DLt stream (phase 2)
-constexpr int PITCH = 36; // floats per staged row: 16-byte aligned for cp.async, conflict-free LDS.128
-constexpr int NS = 6;     // cp.async stages of the W / DLt streams (one region, the two phases never overlap in a CTA)
+constexpr int KC = 64;    // k-chunk of the W stream (phase 1) / n-chunk of the DLt stream (phase 2)
+constexpr int PITCH = 68; // floats per staged row: 16-byte aligned for cp.async, conflict-free LDS.128
+constexpr int NS = 4;     // cp.async stages of the W / DLt streams (one region, the two phases never overlap in a CTA)
 
 struct SmallParams {
     sr_head_args a;
     int n_total, ldn;      // ldn: row pitch of DLt (n_total rounded up to 32)
-    int R, GA, GC, G;      // rows per row CTA, #row CTAs, #column CTAs, grid (= max(GA, GC) + 1 pull CTA)
+    int R, GA, GC, G;      // rows per row CTA, #row CTAs, #column CTAs, grid (= max(GA, GC) + loss CTA + pull CTA)
     int CP;                // classes padded to 64 or 128 (thread mapping of phase 1)
     HeadCtrl* ctrl;
     float* DLt;            // [C][ldn]
@@ -105,7 +105,7 @@ __device__ void assemble_loss(const SmallParams& p, int e, double* red) {
     __syncthreads();
 }
 
-template <int R>
+template <int R, int CP>
 __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) {
     extern __shared__ __align__(16) uint8_t dyn[];
     __shared__ double red[32];
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
     const int C = a.n_classes, d = a.dim, NT = p.n_total, q = a.q_rows;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cta = blockIdx.x;
-    const bool is_row = cta < p.GA, is_col = cta < p.GC, is_pull = cta == p.G - 1;
+    const bool is_row = cta < p.GA, is_col = cta < p.GC, is_pull = cta == p.G - 1, is_loss = cta == p.G - 2;
     const bool has_base = a.base_weight != nullptr;
     const bool has_prev = a.reserve_weight != nullptr && a.n_prev_novel > 0;
     const bool proj = a.pull_mode == SR_PULL_PROJECT && q < d;   // q >= d: P = I, the term vanishes
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
     // ---- shared memory carve-up ----
     float* sp = reinterpret_cast<float*>(dyn);
     float* Xrow = sp;            sp += is_row ? R * d : 0;                 // [R][d]
-    float* Zs = sp;              sp += is_row ? R * (p.CP + 1) : 0;        // [R][CP+1] logits
+    float* Zs = sp;              sp += is_row ? R * (CP + 1) : 0;        // [R][CP+1] logits
     const int xp = p.ldn + 4;    // pitch of the X column slice: +4 floats keeps the 8 rows on different banks
     float* Xc = sp;              sp += is_col ? DC * xp : 0;               // [DC][xp]   (column-major slice of X)
     float* Wc = sp;              sp += is_col ? C * DC : 0;                // [C][DC] master copy of this CTA's W columns
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
     float* Rc = sp;              sp += (is_col && has_prev) ? a.n_prev_novel * DC : 0;
     float* Pc = sp;              sp += (is_col && (proj || fixed)) ? (proj ? q : a.n_new) * DC : 0;  // Q^T or puller columns
     float* Us = sp;              sp += (is_col && proj) ? ((a.n_new * q + 3) & ~3) : 0;      // [n_new][q] projection coefficients
-    float* Stg = sp;             sp += (is_row || is_col) ? NS * p.CP * PITCH : 0;   // NS x [CP][PITCH] stream stages
+    float* Stg = sp;             sp += (is_row || is_col) ? NS * CP * PITCH : 0;   // NS x [CP][PITCH] stream stages
     float* Qs = sp;              sp += (is_pull && proj) ? q * d : 0;      // [q][d]
     float* wn = sp;              sp += (is_pull && proj) ? a.n_new * d : 0;
 
@@ -186,22 +186,27 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
     unsigned int bar_target = 0;
     grid_barrier(p.ctrl, bar_target);
 
-    const int CP = p.CP;
-    const int RG = kT / CP;          // row groups in phase 1 (2 or 4)
-    const int RPT = R / RG;          // rows per thread
+    constexpr int RG = kT / CP;      // row groups in phase 1 (2 or 4)
+    constexpr int RPT = R / RG;      // rows per thread
+    static_assert(RPT >= 1, "too few rows per CTA for this class padding");
     const int c1 = tid % CP, rg = tid / CP;
+    // rows >= C of the stream stages are never written by cp.async: zero them once so that the hot loops need no guards
+    if (is_row || is_col) {
+        for (int i = tid; i < NS * CP * PITCH; i += kT) Stg[i] = 0.f;
+        __syncthreads();
+    }
     int e = 0;
     bool stopped = false;
     for (; e < a.max_epochs; ++e) {
         const int par = e & 1;
         unsigned long long ts0 = 0, ts1 = 0, ts2 = 0, ts3 = 0;
-        if (cta == 0 && tid == 0) ts0 = global_ns();
+        if ((cta == 0 || is_loss || is_pull) && tid == 0) ts0 = global_ns();
         // ======================= phase 1 =======================
-        if (cta == 0 && e > 0) assemble_loss(p, e - 1, red);
+        if (is_loss && e > 0) assemble_loss(p, e - 1, red);   // a CTA of its own: off the row CTAs' critical path
         if (is_row) {
-            float acc[R / 2];
+            float acc[RPT];
 #pragma unroll
-            for (int i = 0; i < R / 2; ++i) acc[i] = 0.f;
+            for (int i = 0; i < RPT; ++i) acc[i] = 0.f;
             const int nchunk = d / KC;
             auto issue = [&](int ck) {
                 float* dst = Stg + (ck % NS) * CP * PITCH;
@@ -215,33 +220,30 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
                 cp_async_commit();
             }
             for (int ck = 0; ck < nchunk; ++ck) {
-                if (ck + NS - 1 < nchunk) issue(ck + NS - 1);
+                cp_async_wait<NS - 2>();     // chunk ck has landed (groups are committed one per iteration)
+                __syncthreads();             // ... for every thread, and everyone is done with chunk ck-1
+                if (ck + NS - 1 < nchunk) issue(ck + NS - 1);   // refills the stage chunk ck-1 used
                 cp_async_commit();
-                cp_async_wait<NS - 1>();
-                __syncthreads();
                 const float* wsrc = Stg + (ck % NS) * CP * PITCH + c1 * PITCH;
-                if (c1 < C) {
+                const float* xsrc = Xrow + rg * RPT * d + ck * KC;
 #pragma unroll
-                    for (int k4 = 0; k4 < KC / 4; ++k4) {
-                        const float4 w4 = *reinterpret_cast<const float4*>(wsrc + k4 * 4);
+                for (int k4 = 0; k4 < KC / 4; ++k4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wsrc + k4 * 4);
 #pragma unroll
-                        for (int i = 0; i < R / 2; ++i) {
-                            if (i < RPT) {
-                                const float4 x4 = *reinterpret_cast<const float4*>(Xrow + (rg * RPT + i) * d + ck * KC + k4 * 4);
-                                acc[i] = fmaf(x4.x, w4.x, acc[i]);
-                                acc[i] = fmaf(x4.y, w4.y, acc[i]);
-                                acc[i] = fmaf(x4.z, w4.z, acc[i]);
-                                acc[i] = fmaf(x4.w, w4.w, acc[i]);
-                            }
-                        }
+                    for (int i = 0; i < RPT; ++i) {
+                        const float4 x4 = *reinterpret_cast<const float4*>(xsrc + i * d + k4 * 4);
+                        acc[i] = fmaf(x4.x, w4.x, acc[i]);
+                        acc[i] = fmaf(x4.y, w4.y, acc[i]);
+                        acc[i] = fmaf(x4.z, w4.z, acc[i]);
+                        acc[i] = fmaf(x4.w, w4.w, acc[i]);
                     }
                 }
-                __syncthreads();
             }
             cp_async_wait<0>();
+            __syncthreads();
 #pragma unroll
-            for (int i = 0; i < R / 2; ++i)
-                if (i < RPT && c1 < C) Zs[(rg * RPT + i) * (CP + 1) + c1] = acc[i];
+            for (int i = 0; i < RPT; ++i)
+                if (c1 < C) Zs[(rg * RPT + i) * (CP + 1) + c1] = acc[i];
             __syncthreads();
             // softmax per row: warp w handles rows w, w + 8, ...
             for (int r = warp; r < R; r += kT / 32) {
@@ -282,15 +284,41 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
             for (int i = tid; i < a.n_new * (d / 4); i += kT)
                 *reinterpret_cast<float4*>(wn + i * 4) = *reinterpret_cast<const float4*>(a.weight + (int64_t)new0 * d + (int64_t)i * 4);
             __syncthreads();
-            for (int o = warp; o < a.n_new * q; o += kT / 32) {
-                const int i = o / q, jq = o % q;
-                float s = 0.f;
-                for (int k = lane; k < d; k += 32) s = fmaf(Qs[jq * d + k], wn[i * d + k], s);
-                s = warp_sum(s);
-                if (lane == 0) p.u[o] = s;
+            if (a.n_new == 5 && d == 640) {
+                // paper shape: each lane keeps its 20 k-values of the five new rows in registers; per Q row that leaves
+                // 20 shared loads for 100 independent FMAs (one dependent chain per output was latency-bound at 18 us)
+                float wr[5][20];
+#pragma unroll
+                for (int i = 0; i < 5; ++i)
+#pragma unroll
+                    for (int t = 0; t < 20; ++t) wr[i][t] = wn[i * 640 + t * 32 + lane];
+                for (int jq = warp; jq < q; jq += kT / 32) {
+                    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int t = 0; t < 20; ++t) {
+                        const float qv = Qs[jq * 640 + t * 32 + lane];
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) acc[i] = fmaf(qv, wr[i][t], acc[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        const float tsum = warp_sum(acc[i]);
+                        if (lane == 0) p.u[i * q + jq] = tsum;
+                    }
+                }
+            } else {
+                for (int o = warp; o < a.n_new * q; o += kT / 32) {
+                    const int i = o / q, jq = o % q;
+                    float sacc = 0.f;
+                    for (int k = lane; k < d; k += 32) sacc = fmaf(Qs[jq * d + k], wn[i * d + k], sacc);
+                    sacc = warp_sum(sacc);
+                    if (lane == 0) p.u[o] = sacc;
+                }
             }
         }
         if (cta == 0 && tid == 0) ts1 = global_ns();
+        if (is_loss && tid == 0) p.ctrl->t_ns[4] += global_ns() - ts0;
+        if (is_pull && tid == 0) p.ctrl->t_ns[5] += global_ns() - ts0;
         grid_barrier(p.ctrl, bar_target);
         if (cta == 0 && tid == 0) ts2 = global_ns();
         if (tid == 0) s_stop = p.ctrl->stop;
@@ -311,6 +339,7 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
             const float sb = nb > 0.f ? a.lmbd_base / nb : 0.f;
             const float sn = nn > 0.f ? a.lmbd_novel / nn : 0.f;
             const int j = tid % DC, cg = tid / DC;          // cg in [0, 32): classes cg, cg + 32, cg + 64, cg + 96
+            constexpr int CPT = CP / 32;   // classes per thread in phase 2
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             const int nchunk = p.ldn / KC;
             auto issue = [&](int ck) {
@@ -325,30 +354,27 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
                 cp_async_commit();
             }
             for (int ck = 0; ck < nchunk; ++ck) {
+                cp_async_wait<NS - 2>();
+                __syncthreads();
                 if (ck + NS - 1 < nchunk) issue(ck + NS - 1);
                 cp_async_commit();
-                cp_async_wait<NS - 1>();
-                __syncthreads();
                 const float* dsrc = Stg + (ck % NS) * CP * PITCH;
                 const float* xsrc = Xc + j * xp + ck * KC;
 #pragma unroll
                 for (int n4 = 0; n4 < KC / 4; ++n4) {
                     const float4 x4 = *reinterpret_cast<const float4*>(xsrc + n4 * 4);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int c = cg + 32 * i;
-                        if (c < C) {
-                            const float4 d4 = *reinterpret_cast<const float4*>(dsrc + c * PITCH + n4 * 4);
-                            acc[i] = fmaf(d4.x, x4.x, acc[i]);
-                            acc[i] = fmaf(d4.y, x4.y, acc[i]);
-                            acc[i] = fmaf(d4.z, x4.z, acc[i]);
-                            acc[i] = fmaf(d4.w, x4.w, acc[i]);
-                        }
+                    for (int i = 0; i < CPT; ++i) {
+                        const float4 d4 = *reinterpret_cast<const float4*>(dsrc + (cg + 32 * i) * PITCH + n4 * 4);
+                        acc[i] = fmaf(d4.x, x4.x, acc[i]);
+                        acc[i] = fmaf(d4.y, x4.y, acc[i]);
+                        acc[i] = fmaf(d4.z, x4.z, acc[i]);
+                        acc[i] = fmaf(d4.w, x4.w, acc[i]);
                     }
                 }
-                __syncthreads();
             }
             cp_async_wait<0>();
+            __syncthreads();
             const int step = a.step0 + e;
             float bc1 = 1.f, bc2s = 1.f;
             if (a.optimizer == SR_OPT_ADAM) {
@@ -357,7 +383,7 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
             }
             double nbp = 0.0, nnp = 0.0, pp = 0.0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < CPT; ++i) {
                 const int c = cg + 32 * i;
                 if (c >= C) continue;
                 const int idx = c * DC + j;
@@ -420,14 +446,14 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
         }
     }
     // ---- tail: loss of the last applied epoch when the loop ran out of epochs; write back optimiser state ----
-    if (!stopped && cta == 0 && e > 0) assemble_loss(p, e - 1, red);
+    if (!stopped && is_loss && e > 0) assemble_loss(p, e - 1, red);
     if (is_col) {
         for (int i = tid; i < C * DC; i += kT) {
             const int c = i / DC, j = i % DC;
             for (int s = 0; s < n_opt; ++s) a.opt_state[(int64_t)s * C * d + (int64_t)c * d + j0 + j] = Vc[s * C * DC + i];
         }
     }
-    if (cta == 0) {
+    if (is_loss) {
         __syncthreads();
         if (tid == 0) {
             a.status[0] = p.ctrl->epochs_done;
@@ -437,6 +463,10 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
         }
     }
 }
+
+// Rows of X per row CTA: as few as keeps the grid within one wave (every row CTA streams all of W each epoch, so
+// fewer rows per CTA buy parallelism with L2 traffic).
+int pick_rows(int nt) { return nt <= 384 ? 4 : (nt <= 768 ? 8 : 16); }
 
 struct SmallLayout {
     int64_t ctrl, DLt, rowloss, rowhit, nb, nn, pull, u, total;
@@ -459,14 +489,14 @@ SmallLayout small_layout(const sr_head_args* a, int GC) {
     return L;
 }
 
-template <int R>
+template <int R, int CP>
 int32_t launch_small(const SmallParams& p, size_t dyn, cudaStream_t stream) {
     static std::once_flag once;
     std::call_once(once, [] {
-        cudaFuncSetAttribute(head_small_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(head_small_kernel<R, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     });
     void* args[] = {const_cast<SmallParams*>(&p)};
-    SR_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(head_small_kernel<R>), dim3(p.G), dim3(kT), args, dyn,
+    SR_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(head_small_kernel<R, CP>), dim3(p.G), dim3(kT), args, dyn,
                                            stream));
     return SR_OK;
 }
@@ -492,12 +522,12 @@ namespace srb {
 bool head_small_applicable(const sr_head_args* a) {
     const int nt = a->n_support + a->n_memory;
     if (a->logits_support != nullptr) return false;
-    if (a->n_classes > 128 || a->dim % 32 != 0 || a->dim > 1024 || a->dim / DC > 147 || nt > 1024) return false;
+    if (a->n_classes > 128 || a->dim % 64 != 0 || a->dim > 1024 || a->dim / DC > 146 || nt > 1024) return false;
     if (a->pull_mode == SR_PULL_PROJECT && a->q_rows < a->dim && (a->q_rows > 256 || a->n_new > 16)) return false;
-    const int R = nt <= 200 ? 8 : 16;
+    const int R = pick_rows(nt);
     const int CP = a->n_classes <= 64 ? 64 : 128;
     const int ldn = (int)align_up(nt, KC);
-    if ((nt + R - 1) / R > 147) return false;
+    if ((nt + R - 1) / R > 146) return false;
     return small_smem_bytes(a, R, CP, ldn, true) <= 200 * 1024;
 }
 
@@ -508,10 +538,10 @@ int32_t head_small_run(const sr_head_args* a, cudaStream_t stream) {
     p.a = *a;
     p.n_total = a->n_support + a->n_memory;
     p.ldn = (int)align_up(p.n_total, KC);
-    p.R = p.n_total <= 200 ? 8 : 16;
+    p.R = pick_rows(p.n_total);
     p.GA = (p.n_total + p.R - 1) / p.R;
     p.GC = a->dim / DC;
-    p.G = std::max(p.GA, p.GC) + 1;
+    p.G = std::max(p.GA, p.GC) + 2;   // + one CTA for the loss / stopping rule, one for the projection coefficients
     p.CP = a->n_classes <= 64 ? 64 : 128;
     const SmallLayout L = small_layout(a, p.GC);
     if (a->workspace_bytes < L.total) return fail(SR_E_SMALLWS, "sr_head_run: workspace %lld < %lld",
@@ -527,7 +557,12 @@ int32_t head_small_run(const sr_head_args* a, cudaStream_t stream) {
     p.u = reinterpret_cast<float*>(ws + L.u);
     SR_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)L.total, stream));   // control block, DLt padding columns, partials
     const size_t dyn = small_smem_bytes(a, p.R, p.CP, p.ldn, true);
-    return p.R == 8 ? launch_small<8>(p, dyn, stream) : launch_small<16>(p, dyn, stream);
+    if (p.CP == 64) {
+        if (p.R == 4) return launch_small<4, 64>(p, dyn, stream);
+        return p.R == 8 ? launch_small<8, 64>(p, dyn, stream) : launch_small<16, 64>(p, dyn, stream);
+    }
+    if (p.R == 4) return launch_small<4, 128>(p, dyn, stream);
+    return p.R == 8 ? launch_small<8, 128>(p, dyn, stream) : launch_small<16, 128>(p, dyn, stream);
 }
 
 }  // namespace srb
