@@ -179,6 +179,41 @@ def cpu_reference_sample(seed, sessions, base_batch, epochs, wdir):
                 images_backbone=T.images_backbone)
 
 
+def head_stress(device, hbm_gbs, steps=5):
+    """Fine-tune steps of the fused head at the config-5 shapes; algorithmic bytes / FLOPs per step from SURVEY 8d."""
+    import torch
+    from srb200 import ops, _lib as L
+    out = {}
+    g = torch.Generator(device=device).manual_seed(1)
+    for name, n_base in (("n_base1000_P=I", 1000), ("n_base256", 256)):
+        N, n_new, d = 10000, 100, 512
+        Cn = n_base + n_new
+        X = (torch.randn(N, d, device=device, generator=g) * 0.45 + 0.53).clamp_min(-0.11)
+        y = n_base + torch.arange(n_new, device=device).repeat_interleave(N // n_new)
+        W = (torch.rand(Cn, d, device=device, generator=g) * 2 - 1) / d ** 0.5
+        base = W[:n_base].clone().contiguous()
+        qt, q, _ = ops.subspace_factor(base)
+        hs = ops.HeadSession(X, N, 0, y, W, n_base, n_new, base_weight=base, pull_mode=L.SR_PULL_PROJECT, pull=qt, q_rows=q,
+                             lmbd_base=0.2, gamma=1.0, stable=False, target_train_loss=-1.0, min_novel_epochs=0,
+                             max_novel_epochs=10 ** 6)
+        hs.run(2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        hs.run(steps)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        qr = min(n_base, d)
+        bytes_step = 4 * N * d + 8 * N + 4 * Cn * d * 4 + 4 * n_base * d + 4 * qr * d
+        flops_step = 4.0 * N * Cn * d + (4.0 * n_new * qr * d if n_base < d else 0.0)
+        out[name] = {"ms_per_step": ms, "steps_per_s": 1e3 / ms, "algorithmic_MB": bytes_step / 1e6,
+                     "achieved_GBps": bytes_step / (ms * 1e-3) / 1e9, "hbm_frac": bytes_step / (ms * 1e-3) / 1e9 / hbm_gbs,
+                     "fp32_TFLOPs": flops_step / (ms * 1e-3) / 1e12,
+                     "binding": "compute (fp32 SIMT tiles; 22.5 GFLOP/step >> 5 us of HBM time)"}
+    return out
+
+
 def main():
     args = parse()
     import torch
@@ -302,6 +337,11 @@ def main():
                 "peak_source": peak_src, "images": nimg, "ms": bb_ms, "img_per_s": nimg / (bb_ms * 1e-3),
                 "flops_per_image": GFLOP_PER_IMAGE * 1e9}
 
+    # ---- BASELINE config 5: head / regulariser stress shapes (1000 base + 100 novel classes, 100-shot, 512-d) ----
+    stress = None
+    if rank == 0:
+        stress = head_stress(device, peaks.get("hbm_gbs", 6650.0))
+
     value = epochs_all / (ms_max * 1e-3)
     line = {"metric": metric, "value": value, "unit": "steps/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
@@ -312,7 +352,8 @@ def main():
             "e2e": {"value": epochs_e2e_all / (ms_e2e_max * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e_max / max(args.steps, 1)},
             "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline,
-            "accuracy": {"weighted_mean_last": float(weighted[:, -1].mean()), "confusion_total": int(conf.sum())}}
+            "accuracy": {"weighted_mean_last": float(weighted[:, -1].mean()), "confusion_total": int(conf.sum())},
+            "stress_head": stress}
 
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         r = cpu_reference_sample(1, 1, 64, args.cpu_epochs, wdir)

@@ -99,8 +99,11 @@ class BackboneEngine(object):
         outputs (NHWC bf16) for ResNet.forward(is_feat=True)."""
         self._ensure_folded()
         outs = []
-        for i0 in range(0, x.shape[0], self.chunk):
-            outs.append(self._eval_chunk(x[i0:i0 + self.chunk].contiguous(), taps))
+        n = x.shape[0]
+        n_chunks = (n + self.chunk - 1) // self.chunk
+        step = (n + n_chunks - 1) // n_chunks          # equal chunks: no small last chunk with a ragged final wave
+        for i0 in range(0, n, step):
+            outs.append(self._eval_chunk(x[i0:i0 + step].contiguous(), taps))
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
     def _eval_chunk(self, x, taps):
