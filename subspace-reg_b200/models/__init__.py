@@ -1,12 +1,7 @@
-"""Drop-in for the reference's ``models`` package (models/__init__.py:1-11): same names, B200-native internals."""
-from .resnet_language import resnet12, resnet18
+"""Drop-in for the reference's ``models`` package: ``model_pool`` (names accepted by ``--model``) and ``model_dict``
+(name -> constructor), both derived from the constructors this package actually implements."""
+from . import resnet_language as _rl
 
-model_pool = [
-    'resnet12',
-    'resnet18',
-]
-
-model_dict = {
-    'resnet12': resnet12,
-    'resnet18': resnet18,
-}
+model_dict = {fn.__name__: fn for fn in (_rl.resnet12, _rl.resnet18)}
+model_pool = sorted(model_dict)
+resnet12, resnet18 = _rl.resnet12, _rl.resnet18
