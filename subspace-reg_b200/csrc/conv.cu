@@ -10,10 +10,15 @@
 //                    zero padding is TMA out-of-bounds fill.  Box shapes are chosen per feature-map size so that
 //                    >= 93 % of the 128 UMMA rows are real pixels and 2x2 pooling windows never leave the CTA.
 //   N (out channels) <= 256 per CTA, both sub-tiles share every B (weight) stage.
-//   K                one pipeline stage = one tap x one KC-channel block (KC = 64/32/16 <-> 128/64/32-byte swizzle).
+//   K                one pipeline stage = one KC-channel block (KC = 64/32/16 <-> 128/64/32-byte swizzle) of one tap, or
+//                    - on row-stacked tiles (84x84 / 42x42 maps) - of the three dh taps of one dw: ONE tall activation box
+//                    with a one-row halo serves them as row-shifted views, next to their three weight tiles.
 //   accumulators     2 x N fp32 columns of TMEM, written by tcgen05.mma (cta_group::1, M = 128).
-//   warps            0: TMA producer (one lane)   1, 2: MMA issue for sub-tile 0 / 1 (one lane each; warp 1 owns TMEM)
-//                    3-10: epilogue
+//   warps            0: TMA producer   1, 2: MMA issue for sub-tile 0 / 1 (warp 1 owns TMEM)   3-10: epilogue
+//   pipeline         one full / one empty mbarrier per stage.  Measured on B200 (tools/ubench_sync.cu): a ring handshake
+//                    costs each role 330-450 cycles whatever the stage holds, the tensor pipe queues only ~2 MMAs behind
+//                    the issuing thread, so a stage must carry >= ~350 cycles of MMAs per issuing warp and the two
+//                    issuing warps cover each other's synchronisation gaps.
 //   schedule         persistent: one CTA per SM walks (pixel tile, channel split) items; the producer prefetches across
 //                    tile boundaries and up to four TMEM accumulator stages let epilogue(i) overlap mainloop(i+1)
 //   epilogue         TMEM -> registers -> (+shift, +residual, LeakyReLU) -> bf16 NHWC, optionally through a shared
@@ -44,10 +49,11 @@ struct PanelDev {
     CUtensorMap tmA;  // rank 4: (C, W, H, N); box (KC, TW, TH, TN), or the tall box (KC, TW, 2*TH+2, 1) when `reuse`
     CUtensorMap tmB;  // rank 2: (taps*cin_pad, cout), box (KC, n_cta)
     int taps;
-    int ncb;       // channel blocks per tap
-    int kc_bytes;  // bytes per operand row per stage == swizzle span (32/64/128)
+    int ncb;          // channel blocks per tap
+    int kc_bytes;     // bytes per operand row per stage == swizzle span (32/64/128)
     int cin_pad;
-    int reuse;     // 3x3 panel, row-stacked tile: one tall A box per (dw, channel block) serves the three dh taps
+    int reuse;        // 3x3 panel, row-stacked tile: one tall A box per (dw, channel block) serves the three dh taps
+    int last_ksteps;  // UMMA K steps (16 channels each) of the last, possibly ragged, channel block
 };
 
 struct ConvParams {
@@ -60,8 +66,8 @@ struct ConvParams {
     int acc_stages;
     int n_cta;
     int rows_sub;
-    int bgroup;   // weight tiles per B slot / barrier round (3 = the dh taps of a tall A box travel together)
-    int nA, nB, a_slot, b_slot, sub_stride;   // A / B rings (slots, bytes per slot), byte offset of sub-tile 1 in an A slot
+    int n_stages, stage_bytes, b_off, sub_stride;   // ring: stages, bytes per stage, offset of the weight tiles inside a
+                                                    // stage, offset of sub-tile 1's activation box (plain panels)
     int tmem_cols;
     int epi;
     float slope;
@@ -130,13 +136,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // Dynamic shared memory is only guaranteed 16-byte aligned; swizzle-128B tiles need 1024.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* ringB = smem + (size_t)p.nA * p.a_slot;
-    uint8_t* staging = ringB + (size_t)p.nB * p.bgroup * p.b_slot;
+    uint8_t* staging = smem + (size_t)p.n_stages * p.stage_bytes;
 
-    __shared__ uint64_t fullA[16];
-    __shared__ uint64_t emptyA[16];
-    __shared__ uint64_t fullB[16];
-    __shared__ uint64_t emptyB[16];
+    __shared__ uint64_t full_bar[8];
+    __shared__ uint64_t empty_bar[8];
     __shared__ uint64_t tmem_full_bar[4];
     __shared__ uint64_t tmem_empty_bar[4];
     __shared__ uint32_t tmem_slot;
@@ -151,13 +154,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         // two MMA-issuing warps (one per sub-tile) each commit on the consumer-side barriers
-        for (int i = 0; i < p.nA; ++i) {
-            mbar_init(&fullA[i], 1);
-            mbar_init(&emptyA[i], 2);
-        }
-        for (int i = 0; i < p.nB; ++i) {
-            mbar_init(&fullB[i], 1);
-            mbar_init(&emptyB[i], 2);
+        for (int i = 0; i < p.n_stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 2);
         }
         for (int i = 0; i < p.acc_stages; ++i) {
             mbar_init(&tmem_full_bar[i], 2);
@@ -177,111 +176,131 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    // 32-bit shared addresses of every barrier / ring, computed once (see ptx.cuh: address-taking variants)
-    const uint32_t a_fullA = smem_u32(&fullA[0]), a_emptyA = smem_u32(&emptyA[0]);
-    const uint32_t a_fullB = smem_u32(&fullB[0]), a_emptyB = smem_u32(&emptyB[0]);
+    // 32-bit shared addresses of every barrier / the ring, computed once (see ptx.cuh: address-taking variants)
+    const uint32_t a_full = smem_u32(&full_bar[0]), a_empty = smem_u32(&empty_bar[0]);
     const uint32_t a_tfull = smem_u32(&tmem_full_bar[0]), a_tempty = smem_u32(&tmem_empty_bar[0]);
-    const uint32_t smem_base = smem_u32(smem), ringB_base = smem_u32(ringB);
+    const uint32_t smem_base = smem_u32(smem);
+    const int my_tiles = ((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        // Two rings: an A slot holds the activation rows of one (tap | dw, channel block) step, a B slot one weight tile.
-        // With `reuse` one tall A box (2*TH+2 image rows) is loaded per (dw, channel block) and the three dh taps are
-        // row-shifted views of it, so the activations cross L2 -> SM three times per pixel instead of nine.
-        if (lane == 0) {
-            int sa = 0, sb = 0;
-            uint32_t phA = 0, phB = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord tc = decode_tile(p, tile);
-                for (int pi = 0; pi < p.n_panels; ++pi) {
-                    const PanelDev& pn = p.panel[pi];
-                    const int kc = pn.kc_bytes >> 1;
-                    const uint32_t txB = (uint32_t)p.n_cta * (uint32_t)pn.kc_bytes;
-                    const int outer = pn.reuse ? 3 : pn.taps;
-                    const int inner = pn.reuse ? 3 : 1;
-                    for (int o = 0; o < outer; ++o) {
-                        for (int cb = 0; cb < pn.ncb; ++cb) {
-                            mbar_wait_a(a_emptyA + 8u * sa, phA ^ 1u);
-                            const uint32_t slot = smem_base + (uint32_t)sa * (uint32_t)p.a_slot;
-                            const uint32_t fa = a_fullA + 8u * sa;
-                            if (pn.reuse) {
-                                mbar_expect_tx_a(fa, (uint32_t)((2 * p.TH + 2) * p.TW) * (uint32_t)pn.kc_bytes);
-                                tma_load_4d_a(slot, &pn.tmA, fa, cb * kc, tc.w0 + o - 1, tc.h0 - 1, tc.n0);
+        // ================= TMA producer (whole warp converged, one elected lane issues) =================
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileCoord tc = decode_tile(p, tile);
+#pragma unroll
+            for (int pi = 0; pi < 2; ++pi) {
+                if (pi >= p.n_panels) break;
+                const PanelDev& pn = p.panel[pi];
+                const int kc = pn.kc_bytes >> 1;
+                const int reuse = pn.reuse;
+                const int ncb = pn.ncb;
+                const int cin_pad = pn.cin_pad;
+                const uint32_t b_tile = (uint32_t)p.n_cta * (uint32_t)pn.kc_bytes;
+                const uint32_t tx = reuse ? (uint32_t)((2 * p.TH + 2) * p.TW) * (uint32_t)pn.kc_bytes + 3u * b_tile
+                                          : (uint32_t)(2 * p.rows_sub) * (uint32_t)pn.kc_bytes + b_tile;
+                const int outer = reuse ? 3 : pn.taps;
+                for (int o = 0; o < outer; ++o) {
+                    // activation box origin and first weight row of this tap (or of the dh = -1 tap of column dw = o - 1)
+                    int dh = 0, dw = 0;
+                    if (reuse) {
+                        dh = -1;
+                        dw = o - 1;
+                    } else if (pn.taps == 9) {
+                        dh = o / 3 - 1;
+                        dw = o - (dh + 1) * 3 - 1;
+                    }
+                    const int w = tc.w0 + dw, h = tc.h0 + dh;
+                    int krow = o * cin_pad;
+                    for (int cb = 0; cb < ncb; ++cb, krow += kc) {
+                        mbar_wait_a(a_empty + 8u * s, ph ^ 1u);
+                        if (elect_one()) {
+                            const uint32_t slot = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
+                            const uint32_t fb = a_full + 8u * s;
+                            mbar_expect_tx_a(fb, tx);
+                            tma_load_4d_a(slot, &pn.tmA, fb, cb * kc, w, h, tc.n0);
+                            if (reuse) {
+                                tma_load_2d_a(slot + (uint32_t)p.b_off, &pn.tmB, fb, krow, tc.co0);
+                                tma_load_2d_a(slot + (uint32_t)p.b_off + b_tile, &pn.tmB, fb, krow + 3 * cin_pad, tc.co0);
+                                tma_load_2d_a(slot + (uint32_t)p.b_off + 2u * b_tile, &pn.tmB, fb, krow + 6 * cin_pad, tc.co0);
                             } else {
-                                const int dh = pn.taps == 9 ? o / 3 - 1 : 0;
-                                const int dw = pn.taps == 9 ? o % 3 - 1 : 0;
-                                mbar_expect_tx_a(fa, (uint32_t)(2 * p.rows_sub) * (uint32_t)pn.kc_bytes);
-                                tma_load_4d_a(slot, &pn.tmA, fa, cb * kc, tc.w0 + dw, tc.h0 + dh, tc.n0);
-                                tma_load_4d_a(slot + (uint32_t)p.sub_stride, &pn.tmA, fa, cb * kc, tc.w0 + dw, tc.h0 + dh + sub_dh,
-                                              tc.n0 + sub_dn);
-                            }
-                            if (++sa == p.nA) { sa = 0; phA ^= 1u; }
-                            const int grp = pn.reuse ? p.bgroup : 1;   // weight tiles per barrier round
-                            for (int j = 0; j < inner; j += grp) {
-                                mbar_wait_a(a_emptyB + 8u * sb, phB ^ 1u);
-                                mbar_expect_tx_a(a_fullB + 8u * sb, txB * (uint32_t)grp);
-                                for (int g = 0; g < grp; ++g) {
-                                    const int tap = pn.reuse ? (j + g) * 3 + o : o;
-                                    tma_load_2d_a(ringB_base + (uint32_t)(sb * p.bgroup + g) * (uint32_t)p.b_slot, &pn.tmB,
-                                                  a_fullB + 8u * sb, tap * pn.cin_pad + cb * kc, tc.co0);
-                                }
-                                if (++sb == p.nB) { sb = 0; phB ^= 1u; }
+                                tma_load_4d_a(slot + (uint32_t)p.sub_stride, &pn.tmA, fb, cb * kc, w, h + sub_dh, tc.n0 + sub_dn);
+                                tma_load_2d_a(slot + (uint32_t)p.b_off, &pn.tmB, fb, krow, tc.co0);
                             }
                         }
+                        __syncwarp();
+                        if (++s == p.n_stages) { s = 0; ph ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 1 || warp == 2) {
         // ================= MMA issuers: warp 1 drives sub-tile 0, warp 2 sub-tile 1 =================
-        // (one thread can launch an MMA every ~50 cycles; an N = 64 MMA lasts 32, so a single issuer starves the pipe)
-        if (lane == 0) {
-            const int sub = warp - 1;
-            const uint32_t idesc = umma_idesc_bf16(kSubRows, (uint32_t)p.n_cta);
-            int sa = 0, sb = 0, t = 0;
-            uint32_t phA = 0, phB = 0;   // ring slot + phase, advanced without divisions (this thread paces the tensor pipe)
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-                const int as = t % p.acc_stages;
-                const uint32_t use = (uint32_t)(t / p.acc_stages);
-                mbar_wait_a(a_tempty + 8u * as, (use & 1u) ^ 1u);  // the epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t acc = tmem_base + (uint32_t)(as * acc_cols + sub * p.n_cta);
-                bool first = true;
-                for (int pi = 0; pi < p.n_panels; ++pi) {
-                    const PanelDev& pn = p.panel[pi];
-                    const int ksteps = pn.kc_bytes >> 5;  // UMMA K = 16 bf16 = 32 bytes
-                    const int nsteps = (pn.reuse ? 3 : pn.taps) * pn.ncb;
-                    const int inner = pn.reuse ? 3 : 1;
-                    const uint32_t dhi = umma_desc_hi((uint32_t)pn.kc_bytes);
-                    // byte offsets of the two sub-tile views inside an A slot, and their increment per dh tap
-                    const uint32_t sub_off = sub ? (pn.reuse ? (uint32_t)(p.TH * p.TW * pn.kc_bytes) : (uint32_t)p.sub_stride) : 0u;
-                    const uint32_t dh_step = pn.reuse ? (uint32_t)(p.TW * pn.kc_bytes) : 0u;
-                    for (int st = 0; st < nsteps; ++st) {
-                        mbar_wait_a(a_fullA + 8u * sa, phA);
-                        uint32_t a0 = smem_base + (uint32_t)sa * (uint32_t)p.a_slot + sub_off;
-                        const int grp = pn.reuse ? p.bgroup : 1;
-                        for (int j = 0; j < inner; j += grp) {
-                            mbar_wait_a(a_fullB + 8u * sb, phB);
-                            tc_fence_after();
-                            uint32_t b0 = ringB_base + (uint32_t)(sb * p.bgroup) * (uint32_t)p.b_slot;
-                            for (int g = 0; g < grp; ++g, a0 += dh_step, b0 += (uint32_t)p.b_slot) {
-                                const uint32_t alo = umma_desc_lo(a0);
-                                const uint32_t blo = umma_desc_lo(b0);
-                                // descriptors advance by 32 bytes (2 units of 16) per K step inside the swizzle atom
-                                umma_f16_split(acc, alo, blo, dhi, idesc, first ? 0u : 1u);
-                                for (int ks = 1; ks < ksteps; ++ks)
-                                    umma_f16_split(acc, alo + 2 * ks, blo + 2 * ks, dhi, idesc, 1u);
-                                first = false;
+        // Whole warp converged (the compiler keeps descriptors in uniform registers), one elected lane issues.  The wait
+        // for the NEXT stage is started before this stage's MMAs are issued, so its latency hides behind them.
+        const int sub = warp - 1;
+        const uint32_t idesc = umma_idesc_bf16(kSubRows, (uint32_t)p.n_cta);
+        int steps_per_tile = 0;
+        for (int pi = 0; pi < p.n_panels; ++pi) steps_per_tile += (p.panel[pi].reuse ? 3 : p.panel[pi].taps) * p.panel[pi].ncb;
+        int steps_left = my_tiles * steps_per_tile;
+        int s = 0, as = 0;
+        uint32_t ph = 0, aph = 0;
+        bool ready = steps_left > 0 && mbar_try_wait_a(a_full, 0u);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            mbar_wait_a(a_tempty + 8u * as, aph ^ 1u);  // the epilogue has drained this accumulator
+            const uint32_t acc = tmem_base + (uint32_t)(as * acc_cols + sub * p.n_cta);
+            uint32_t accum = 0u;
+#pragma unroll
+            for (int pi = 0; pi < 2; ++pi) {
+                if (pi >= p.n_panels) break;
+                const PanelDev& pn = p.panel[pi];
+                const int reuse = pn.reuse;
+                const int ncb = pn.ncb;
+                const int ksteps = pn.kc_bytes >> 5;  // UMMA K = 16 bf16 = 32 bytes
+                const int last_ksteps = pn.last_ksteps;
+                const int nsteps = (reuse ? 3 : pn.taps) * ncb;
+                const uint32_t dhi = umma_desc_hi((uint32_t)pn.kc_bytes);
+                // 16-byte units: offset of this warp's sub-tile view inside a stage, increment per dh tap, weight tile size
+                const uint32_t sub_off = (sub ? (reuse ? (uint32_t)(p.TH * p.TW * pn.kc_bytes) : (uint32_t)p.sub_stride) : 0u) >> 4;
+                const uint32_t dh_step = (uint32_t)(p.TW * pn.kc_bytes) >> 4;
+                const uint32_t b_tile = ((uint32_t)p.n_cta * (uint32_t)pn.kc_bytes) >> 4;
+                int cb = 0;
+                for (int st = 0; st < nsteps; ++st) {
+                    if (!ready) mbar_wait_slow(a_full + 8u * s, ph);
+                    tc_fence_after();
+                    const uint32_t alo = umma_desc_lo(smem_base + (uint32_t)s * (uint32_t)p.stage_bytes) + sub_off;
+                    const uint32_t blo = umma_desc_lo(smem_base + (uint32_t)s * (uint32_t)p.stage_bytes + (uint32_t)p.b_off);
+                    const uint32_t eb = a_empty + 8u * s;
+                    if (++s == p.n_stages) { s = 0; ph ^= 1u; }
+                    --steps_left;
+                    ready = steps_left > 0 && mbar_try_wait_a(a_full + 8u * s, ph);
+                    const int kn = (cb == ncb - 1) ? last_ksteps : ksteps;
+                    if (++cb == ncb) cb = 0;
+                    if (elect_one()) {
+                        // descriptors advance by 32 bytes (2 units of 16) per K step inside the swizzle atom
+                        if (reuse) {
+#pragma unroll
+                            for (int g = 0; g < 3; ++g) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks)
+                                    if (ks < kn)
+                                        umma_f16_split(acc, alo + g * dh_step + 2 * ks, blo + g * b_tile + 2 * ks, dhi, idesc,
+                                                       (g | ks) ? 1u : accum);
                             }
-                            umma_commit_a(a_emptyB + 8u * sb);  // frees the weight slot once the MMAs above have read it
-                            if (++sb == p.nB) { sb = 0; phB ^= 1u; }
+                        } else {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                if (ks < kn) umma_f16_split(acc, alo + 2 * ks, blo + 2 * ks, dhi, idesc, ks ? 1u : accum);
                         }
-                        umma_commit_a(a_emptyA + 8u * sa);
-                        if (++sa == p.nA) { sa = 0; phA ^= 1u; }
+                        umma_commit_a(eb);  // frees the stage once the MMAs above have read it
                     }
+                    accum = 1u;
+                    __syncwarp();
                 }
-                umma_commit_a(a_tfull + 8u * as);
             }
+            if (elect_one()) umma_commit_a(a_tfull + 8u * as);
+            __syncwarp();
+            if (++as == p.acc_stages) { as = 0; aph ^= 1u; }
         }
     } else {
         // ================= epilogue (warps 3..10): two warps per TMEM lane quarter, 16 columns each =================
@@ -624,7 +643,24 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
     p.tmem_cols = 512;                                 // one persistent CTA per SM owns all of TMEM
     p.n_splits = ns;
 
-    int kc_max = 0, any_reuse = 0;
+    int staging = 0;   // the producer prefetches the next tile during the epilogue: staging cannot alias the pipeline
+    if (a->epilogue == SR_EPI_ACT_POOL2) staging = 2 * kSubRows * kStagePitchBf16;
+    if (a->epilogue == SR_EPI_ACT_AVG) staging = 2 * kSubRows * kStagePitchF32 * 4;
+
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    static int max_dyn = 0;
+    std::call_once(attr_once, [] {
+        cudaFuncAttributes fa;
+        attr_err = cudaFuncGetAttributes(&fa, conv_umma_kernel);
+        if (attr_err != cudaSuccess) return;
+        max_dyn = 227 * 1024 - (int)fa.sharedSizeBytes;  // static + dynamic <= 227 KB per CTA
+        attr_err = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    });
+    if (attr_err != cudaSuccess)
+        return fail(SR_E_CUDA, "sr_conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+    const int budget = max_dyn - 1024 - staging;
+
     for (int i = 0; i < a->n_panels; ++i) {
         const sr_conv_panel& sp = a->panel[i];
         if (!sp.act || !sp.wgt) return fail(SR_E_ARG, "sr_conv: null panel pointer");
@@ -632,16 +668,51 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
         if (sp.taps != 9 && sp.taps != 1) return fail(SR_E_ARG, "sr_conv: taps must be 9 or 1");
         if ((reinterpret_cast<uintptr_t>(sp.act) | reinterpret_cast<uintptr_t>(sp.wgt)) & 15)
             return fail(SR_E_ARG, "sr_conv: operand pointers must be 16-byte aligned");
+        // Tap reuse: a row-stacked tile of one image (84x84 / 42x42 maps) covers 2*TH consecutive image rows, so one tall
+        // box with a one-row halo above and below holds every dh tap of a given dw.
+        p.panel[i].reuse = (sp.taps == 9 && tile.stack_h && tile.TN == 1 && !getenv("SRB_NO_TAP_REUSE")) ? 1 : 0;
+    }
+    // Stage geometry for a given row width: activations (two 128-row sub-tiles, or the tall box plus the 128-row window
+    // that starts at its last tap offset) followed by one weight tile per tap of the stage.
+    auto stage_bytes_for = [&](int kcb, int* b_off) {
+        int a_rows = 0, b_tiles = 0;
+        for (int i = 0; i < a->n_panels; ++i) {
+            const int rows = p.panel[i].reuse ? std::max(2 * kSubRows, (tile.TH + 2) * tile.TW + kSubRows) : 2 * kSubRows;
+            a_rows = std::max(a_rows, rows);
+            b_tiles = std::max(b_tiles, p.panel[i].reuse ? 3 : 1);
+        }
+        const int a_bytes = (int)align_up((int64_t)a_rows * kcb, 1024);
+        *b_off = a_bytes;
+        return a_bytes + b_tiles * p.n_cta * kcb;   // n_cta is a multiple of 32: every weight tile stays 1024-aligned
+    };
+    // Row width (channels per stage): the widest one that still leaves three stages in flight - every barrier round costs
+    // the issuing warps ~350 cycles whatever it carries, so stages should be as fat as the ring depth allows.
+    const int kc_cap = kc_bytes_for(a->panel[0].cin_pad);
+    int kc0 = 0;
+    if (const char* e = getenv("SRB_KC_BYTES")) kc0 = std::min(kc_cap, atoi(e));
+    if (kc0 != 32 && kc0 != 64 && kc0 != 128) {
+        kc0 = 32;
+        for (int kcb = kc_cap; kcb >= 32; kcb >>= 1) {
+            int off;
+            if (budget / stage_bytes_for(kcb, &off) >= 3) {
+                kc0 = kcb;
+                break;
+            }
+        }
+    }
+    p.stage_bytes = stage_bytes_for(kc0, &p.b_off);
+    p.n_stages = std::min(8, budget / p.stage_bytes);
+    if (p.n_stages < 2) return fail(SR_E_ARG, "sr_conv: pipeline does not fit in shared memory");
+    p.sub_stride = kSubRows * kc0;
+
+    for (int i = 0; i < a->n_panels; ++i) {
+        const sr_conv_panel& sp = a->panel[i];
         PanelDev& pd = p.panel[i];
         pd.taps = sp.taps;
         pd.cin_pad = sp.cin_pad;
-        pd.kc_bytes = kc_bytes_for(sp.cin_pad);
+        pd.kc_bytes = std::min(kc0, kc_bytes_for(sp.cin_pad));
         pd.ncb = (sp.cin_pad * 2 + pd.kc_bytes - 1) / pd.kc_bytes;
-        // Tap reuse: a row-stacked tile of one image (84x84 / 42x42 maps) covers 2*TH consecutive image rows, so one tall
-        // box with a one-row halo above and below holds every dh tap of a given dw.
-        pd.reuse = (sp.taps == 9 && tile.stack_h && tile.TN == 1 && !getenv("SRB_NO_TAP_REUSE")) ? 1 : 0;
-        any_reuse |= pd.reuse;
-        kc_max = std::max(kc_max, pd.kc_bytes);
+        pd.last_ksteps = (sp.cin_pad * 2 - (pd.ncb - 1) * pd.kc_bytes) / 32;   // cin_pad is a multiple of 16 channels
         const int kc = pd.kc_bytes / 2;
         {
             cuuint64_t gdim[4] = {(cuuint64_t)sp.cin_pad, (cuuint64_t)a->width, (cuuint64_t)a->height, (cuuint64_t)a->batch};
@@ -666,58 +737,7 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
             if (r != CUDA_SUCCESS) return fail(SR_E_CUDA, "sr_conv: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
         }
     }
-    // A slot: two 128-row sub-tiles, or the tall box plus the 128-row window that starts at its last tap offset
-    p.sub_stride = kSubRows * kc_max;
-    int a_rows = 2 * kSubRows;
-    if (any_reuse) a_rows = std::max(a_rows, (tile.TH + 2) * tile.TW + kSubRows);
-    p.a_slot = (int)align_up((int64_t)a_rows * kc_max, 1024);
-    p.b_slot = (int)align_up((int64_t)p.n_cta * kc_max, 1024);
-    int staging = 0;   // the producer prefetches the next tile during the epilogue: staging cannot alias the pipeline
-    if (a->epilogue == SR_EPI_ACT_POOL2) staging = 2 * kSubRows * kStagePitchBf16;
-    if (a->epilogue == SR_EPI_ACT_AVG) staging = 2 * kSubRows * kStagePitchF32 * 4;
-
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    static int max_dyn = 0;
-    std::call_once(attr_once, [] {
-        cudaFuncAttributes fa;
-        attr_err = cudaFuncGetAttributes(&fa, conv_umma_kernel);
-        if (attr_err != cudaSuccess) return;
-        max_dyn = 227 * 1024 - (int)fa.sharedSizeBytes;  // static + dynamic <= 227 KB per CTA
-        attr_err = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
-    });
-    if (attr_err != cudaSuccess)
-        return fail(SR_E_CUDA, "sr_conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
-    // Ring sizes.  With tap reuse the three dh weight tiles of an A slot travel under ONE barrier when that fits (the
-    // MMA-issuing threads pay ~200 instructions per barrier round, so fewer, larger rounds keep the tensor pipe busier);
-    // otherwise maximise the prefetch distance min((nA-1) * r, nB-1) in weight-tile steps, r = weight tiles per A slot.
-    const int budget = max_dyn - 1024 - staging;
-    p.bgroup = 1;
-    int best = -1;
-    if (any_reuse && getenv("SRB_BGROUP")) {   // measured slower on B200 (12.4 vs 11.4 ms per 1024 images): off by default
-        const int nA = std::min(4, (budget - 2 * 3 * p.b_slot) / p.a_slot);
-        if (nA >= 2) {
-            p.bgroup = 3;
-            p.nA = nA;
-            p.nB = std::min(nA + 1, (budget - nA * p.a_slot) / (3 * p.b_slot));
-            best = 1;
-        }
-    }
-    if (best < 0) {
-        const int r = any_reuse ? 3 : 1;
-        for (int nA = 2; nA <= 12; ++nA) {
-            const int nB = std::min(16, (budget - nA * p.a_slot) / p.b_slot);
-            if (nB < r + 1) break;
-            const int depth = std::min((nA - 1) * r, nB - 1);
-            if (depth > best) {
-                best = depth;
-                p.nA = nA;
-                p.nB = nB;
-            }
-        }
-    }
-    if (best < 0) return fail(SR_E_ARG, "sr_conv: pipeline does not fit in shared memory");
-    const int dyn_smem = p.nA * p.a_slot + p.nB * p.bgroup * p.b_slot + staging + 1024;
+    const int dyn_smem = p.n_stages * p.stage_bytes + staging + 1024;
 
     const int tiles_n = tile.stack_h ? a->batch : (a->batch + 2 * tile.TN - 1) / (2 * tile.TN);
     p.total_tiles = tile.tiles_w * tile.tiles_h * tiles_n * ns;

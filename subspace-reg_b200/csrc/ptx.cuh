@@ -213,8 +213,9 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait_a(bar, parity)) return;
+// Slow path of a wait, kept out of line so that the role loops stay small: spin on try_wait (a hardware-suspended wait, not
+// a poll) and trap with a message instead of hanging the GPU if the barrier never completes.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
     while (!mbar_try_wait_a(bar, parity)) {
         if (clock64() - t0 > 8000000000LL) {
@@ -222,6 +223,9 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
             __trap();
         }
     }
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    if (!mbar_try_wait_a(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
