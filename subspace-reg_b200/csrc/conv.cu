@@ -68,7 +68,10 @@ struct ConvParams {
     int rows_sub;
     int n_stages, stage_bytes, b_off, sub_stride;   // ring: stages, bytes per stage, offset of the weight tiles inside a
                                                     // stage, offset of sub-tile 1's activation box (plain panels)
+    int staging_bytes;
     int tmem_cols;
+    int dbg;      // SRB_CONV_DBG (timing experiments only): 1 = no global stores, 2 = no MMAs, 4 = epilogue only hands the
+                  // accumulator back, 8 = no TMA loads
     int epi;
     float slope;
     int Ho, Wo;
@@ -76,7 +79,13 @@ struct ConvParams {
     const __nv_bfloat16* residual;
     void* out;
     double* stats;
+    long long* trace;   // SRB_CONV_DBG & 16: clock64 stamps of CTA 0, [tile][8 events]
 };
+
+#define SRB_TRACE(ev)                                                                         \
+    do {                                                                                      \
+        if (p.trace && blockIdx.x == 0 && lane == 0 && tl < 96) p.trace[tl * 8 + (ev)] = clock64(); \
+    } while (0)
 
 __device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
 
@@ -113,21 +122,47 @@ struct TileCoord {
     int w0, h0, n0, co0;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
-    // n-split fastest: CTAs that run concurrently share the same activation tile in L2
-    const int nsp = tile % p.n_splits;
-    int t = tile / p.n_splits;
-    const int tw = t % p.tiles_w;
-    t /= p.tiles_w;
-    const int th = t % p.tiles_h;
-    const int tn = t / p.tiles_h;
-    TileCoord c;
-    c.w0 = tw * p.TW;
-    c.h0 = th * (p.stack_h ? 2 * p.TH : p.TH);
-    c.n0 = tn * (p.stack_h ? p.TN : 2 * p.TN);
-    c.co0 = nsp * p.n_cta;
-    return c;
-}
+// Walks the (pixel tile, channel split) work items of one persistent CTA: tile = blockIdx.x, blockIdx.x + gridDim.x, ...
+// The item index is kept as mixed-radix digits (n-split fastest: CTAs that run concurrently share the same activation
+// tile in L2) and advanced by the digits of the stride, so the per-tile cost is a few adds instead of six divisions.
+struct TileIter {
+    int d_ns, d_w, d_h, d_n;   // digits of the current item
+    int s_ns, s_w, s_h, s_n;   // digits of the stride
+    __device__ __forceinline__ void init(const ConvParams& p, int tile, int stride) {
+        d_ns = tile % p.n_splits;
+        int t = tile / p.n_splits;
+        d_w = t % p.tiles_w;
+        t /= p.tiles_w;
+        d_h = t % p.tiles_h;
+        d_n = t / p.tiles_h;
+        s_ns = stride % p.n_splits;
+        t = stride / p.n_splits;
+        s_w = t % p.tiles_w;
+        t /= p.tiles_w;
+        s_h = t % p.tiles_h;
+        s_n = t / p.tiles_h;
+    }
+    __device__ __forceinline__ void next(const ConvParams& p) {
+        d_ns += s_ns;
+        int c = d_ns >= p.n_splits ? 1 : 0;
+        d_ns -= c ? p.n_splits : 0;
+        d_w += s_w + c;
+        c = d_w >= p.tiles_w ? 1 : 0;
+        d_w -= c ? p.tiles_w : 0;
+        d_h += s_h + c;
+        c = d_h >= p.tiles_h ? 1 : 0;
+        d_h -= c ? p.tiles_h : 0;
+        d_n += s_n + c;
+    }
+    __device__ __forceinline__ TileCoord coord(const ConvParams& p) const {
+        TileCoord c;
+        c.w0 = d_w * p.TW;
+        c.h0 = d_h * (p.stack_h ? 2 * p.TH : p.TH);
+        c.n0 = d_n * (p.stack_h ? p.TN : 2 * p.TN);
+        c.co0 = d_ns * p.n_cta;
+        return c;
+    }
+};
 
 // Persistent kernel: one CTA per SM loops over (pixel tile, channel split) work items.  The TMA producer runs ahead across
 // tile boundaries, the MMA warp only waits for a free TMEM accumulator stage, so the epilogue of tile i overlaps the
@@ -137,13 +172,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     // Dynamic shared memory is only guaranteed 16-byte aligned; swizzle-128B tiles need 1024.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* staging = smem + (size_t)p.n_stages * p.stage_bytes;
+    float* s_shift = reinterpret_cast<float*>(staging + p.staging_bytes);   // folded-BN shifts of all Cout channels (ACT modes)
 
     __shared__ uint64_t full_bar[8];
     __shared__ uint64_t empty_bar[8];
     __shared__ uint64_t tmem_full_bar[4];
     __shared__ uint64_t tmem_empty_bar[4];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(16) float s_sum[256];   // per-channel sums (RAW_STATS) or the folded-BN shift table (ACT modes)
+    __shared__ __align__(16) float s_sum[256];   // per-channel sums of this tile (RAW_STATS)
     __shared__ float s_sq[256];
 
     const int warp = threadIdx.x >> 5;
@@ -180,14 +216,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     const uint32_t a_full = smem_u32(&full_bar[0]), a_empty = smem_u32(&empty_bar[0]);
     const uint32_t a_tfull = smem_u32(&tmem_full_bar[0]), a_tempty = smem_u32(&tmem_empty_bar[0]);
     const uint32_t smem_base = smem_u32(smem);
-    const int my_tiles = ((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0) {
         // ================= TMA producer (whole warp converged, one elected lane issues) =================
         int s = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const TileCoord tc = decode_tile(p, tile);
+        int tl = 0;
+        TileIter it;
+        it.init(p, (int)blockIdx.x, (int)gridDim.x);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl, it.next(p)) {
+            const TileCoord tc = it.coord(p);
+            SRB_TRACE(0);
 #pragma unroll
             for (int pi = 0; pi < 2; ++pi) {
                 if (pi >= p.n_panels) break;
@@ -214,7 +253,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     int krow = o * cin_pad;
                     for (int cb = 0; cb < ncb; ++cb, krow += kc) {
                         mbar_wait_a(a_empty + 8u * s, ph ^ 1u);
-                        if (elect_one()) {
+                        if (p.dbg & 8) {
+                            if (elect_one()) mbar_arrive_a(a_full + 8u * s);
+                        } else if (elect_one()) {
                             const uint32_t slot = smem_base + (uint32_t)s * (uint32_t)p.stage_bytes;
                             const uint32_t fb = a_full + 8u * s;
                             mbar_expect_tx_a(fb, tx);
@@ -233,21 +274,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     }
                 }
             }
+            SRB_TRACE(1);
         }
     } else if (warp == 1 || warp == 2) {
         // ================= MMA issuers: warp 1 drives sub-tile 0, warp 2 sub-tile 1 =================
-        // Whole warp converged (the compiler keeps descriptors in uniform registers), one elected lane issues.  The wait
-        // for the NEXT stage is started before this stage's MMAs are issued, so its latency hides behind them.
+        // Whole warp converged (the compiler keeps descriptors in uniform registers), one elected lane issues.
         const int sub = warp - 1;
         const uint32_t idesc = umma_idesc_bf16(kSubRows, (uint32_t)p.n_cta);
-        int steps_per_tile = 0;
-        for (int pi = 0; pi < p.n_panels; ++pi) steps_per_tile += (p.panel[pi].reuse ? 3 : p.panel[pi].taps) * p.panel[pi].ncb;
-        int steps_left = my_tiles * steps_per_tile;
         int s = 0, as = 0;
         uint32_t ph = 0, aph = 0;
-        bool ready = steps_left > 0 && mbar_try_wait_a(a_full, 0u);
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+            if (warp == 1) SRB_TRACE(2);
             mbar_wait_a(a_tempty + 8u * as, aph ^ 1u);  // the epilogue has drained this accumulator
+            if (warp == 1) SRB_TRACE(3);
             const uint32_t acc = tmem_base + (uint32_t)(as * acc_cols + sub * p.n_cta);
             uint32_t accum = 0u;
 #pragma unroll
@@ -266,15 +306,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                 const uint32_t b_tile = ((uint32_t)p.n_cta * (uint32_t)pn.kc_bytes) >> 4;
                 int cb = 0;
                 for (int st = 0; st < nsteps; ++st) {
-                    if (!ready) mbar_wait_slow(a_full + 8u * s, ph);
+                    mbar_wait_a(a_full + 8u * s, ph);
                     tc_fence_after();
                     const uint32_t alo = umma_desc_lo(smem_base + (uint32_t)s * (uint32_t)p.stage_bytes) + sub_off;
                     const uint32_t blo = umma_desc_lo(smem_base + (uint32_t)s * (uint32_t)p.stage_bytes + (uint32_t)p.b_off);
                     const uint32_t eb = a_empty + 8u * s;
                     if (++s == p.n_stages) { s = 0; ph ^= 1u; }
-                    --steps_left;
-                    ready = steps_left > 0 && mbar_try_wait_a(a_full + 8u * s, ph);
-                    const int kn = (cb == ncb - 1) ? last_ksteps : ksteps;
+                    const int kn = (p.dbg & 2) ? 0 : ((cb == ncb - 1) ? last_ksteps : ksteps);
                     if (++cb == ncb) cb = 0;
                     if (elect_one()) {
                         // descriptors advance by 32 bytes (2 units of 16) per K step inside the swizzle atom
@@ -298,15 +336,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     __syncwarp();
                 }
             }
+            if (warp == 1) SRB_TRACE(4);
             if (elect_one()) umma_commit_a(a_tfull + 8u * as);
             __syncwarp();
             if (++as == p.acc_stages) { as = 0; aph ^= 1u; }
         }
     } else {
-        // ================= epilogue (warps 3..10): two warps per TMEM lane quarter, 16 columns each =================
+        // ================= epilogue (warps 3..10) =================
+        // Warp w drains TMEM lane quarter (w & 3) of sub-tile (w - 3) / 4: per 32-channel chunk one thread holds 32 channels
+        // of one output pixel.
         const int et = threadIdx.x - kEpiWarp0 * 32;
-        const int q = warp & 3;                 // TMEM lane quarter this warp may read
-        const int half = (warp - kEpiWarp0) >> 2;  // which 16 of the 32 columns of a chunk
+        const int q = warp & 3;                   // TMEM lane quarter this warp may read
+        const int sub = (warp - kEpiWarp0) >> 2;  // sub-tile
         const int m = q * 32 + lane;
         const int hw_sub = p.TH * p.TW;
         const int nl = m / hw_sub;
@@ -314,114 +355,148 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         const int hl = rem / p.TW;
         const int wl = rem - hl * p.TW;
         const int nchunks = p.n_cta >> 5;
-        int shift_co0 = -1;
+        // SR_EPI_ACT writes go through a warp-private transposition in shared memory so that one store instruction covers
+        // 8 pixels x 64 contiguous bytes (a thread's own 64 bytes sit Cout*2 bytes apart from its neighbour's: 32 partial
+        // lines per instruction).  This lane then stores 16-byte piece (lane & 3) of rows (lane >> 2) + 8 i, i = 0..3.
+        const int piece = lane & 3;
+        // element offsets relative to the tile origin (sub-tile included); tile-independent
+        const int sub_n = sub * sub_dn, sub_h = sub * sub_dh;
+        const int own_rel = ((nl + sub_n) * p.H + hl + sub_h) * p.W + wl;
+        int t_nl[4], t_hl[4], t_rel[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = q * 32 + (lane >> 2) + 8 * i;
+            const int rn = r / hw_sub;
+            const int rr = r - rn * hw_sub;
+            const int rh = rr / p.TW;
+            t_nl[i] = (r < p.rows_sub ? rn : (1 << 20)) + sub_n;   // rows past the box are never valid
+            t_hl[i] = rh + sub_h;
+            t_rel[i] = (((rn + sub_n) * p.H + rh + sub_h) * p.W + (rr - rh * p.TW)) * p.Cout + piece * 8;
+        }
+        const uint32_t stg_s = smem_u32(staging);
+        const uint32_t shift_s = smem_u32(s_shift);
+        const uint32_t my_row = stg_s + (uint32_t)((sub * kSubRows + m) * kStagePitchBf16);
+        const uint32_t t_rows = stg_s + (uint32_t)((sub * kSubRows + q * 32 + (lane >> 2)) * kStagePitchBf16 + piece * 16);
+        if (p.epi != SR_EPI_RAW_STATS) {
+            for (int i = et; i < p.Cout; i += kEpiThreads) s_shift[i] = p.shift ? __ldg(p.shift + i) : 0.f;
+            named_bar_sync(1, kEpiThreads);
+        }
         int t = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-            const TileCoord tc = decode_tile(p, tile);
-            const int as = t % p.acc_stages;
-            const uint32_t use = (uint32_t)(t / p.acc_stages);
+        TileIter it;
+        it.init(p, (int)blockIdx.x, (int)gridDim.x);
+        int as = 0;
+        uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t, it.next(p)) {
+            const TileCoord tc = it.coord(p);
             if (p.epi == SR_EPI_RAW_STATS) {
                 for (int i = et; i < p.n_cta; i += kEpiThreads) {
                     s_sum[i] = 0.f;
                     s_sq[i] = 0.f;
                 }
                 named_bar_sync(1, kEpiThreads);
-            } else if (tc.co0 != shift_co0) {
-                // folded-BN shifts of this channel split -> shared memory (s_sum doubles as the shift table)
-                if (shift_co0 >= 0) named_bar_sync(1, kEpiThreads);   // everyone is done with the previous table
-                for (int i = et; i < p.n_cta; i += kEpiThreads) s_sum[i] = p.shift ? __ldg(p.shift + tc.co0 + i) : 0.f;
-                shift_co0 = tc.co0;
-                named_bar_sync(1, kEpiThreads);
             }
-            mbar_wait_a(a_tfull + 8u * as, use & 1u);
+            // this thread's own output pixel, and (SR_EPI_ACT) the four pixels whose pieces it writes out
+            const bool valid = (m < p.rows_sub) && (tc.n0 + nl + sub_n < p.B) && (tc.h0 + hl + sub_h < p.H);
+            const size_t origin = ((size_t)tc.n0 * p.H + tc.h0) * p.W + tc.w0;   // pixel index of the tile origin
+            const size_t pix = origin + own_rel;
+            __nv_bfloat16* const t_base = reinterpret_cast<__nv_bfloat16*>(p.out) + origin * p.Cout + tc.co0;
+            bool t_ok[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t_ok[i] = (tc.n0 + t_nl[i] < p.B) && (tc.h0 + t_hl[i] < p.H) && !(p.dbg & 1);
+            const int tl = t;
+            if (warp == kEpiWarp0) SRB_TRACE(5);
+            mbar_wait_a(a_tfull + 8u * as, aph);
             tc_fence_after();
-            const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols);
+            if (warp == kEpiWarp0) SRB_TRACE(6);
+            const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * acc_cols + sub * p.n_cta);
 
-            for (int ch = 0; ch < nchunks; ++ch) {
-                const int c16 = ch * 32 + half * 16;     // first of this thread's 16 channels inside the CTA's N range
+            // One 16-channel half of a chunk: TMEM values of this thread's pixel -> activation -> staging (or raw + stats).
+            auto do_half = [&](float* v, int c16) {
                 const int cbase = tc.co0 + c16;
-                float vv[2][16];
-                tmem_ld16(acc + (uint32_t)c16, vv[0]);
-                tmem_ld16(acc + (uint32_t)(p.n_cta + c16), vv[1]);
-                tmem_ld_wait();
+                if (p.epi == SR_EPI_RAW_STATS) {
+                    if (valid) {
+                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Cout + cbase);
 #pragma unroll
-                for (int sub = 0; sub < 2; ++sub) {
-                    const int n = tc.n0 + nl + sub * sub_dn;
-                    const int h = tc.h0 + hl + sub * sub_dh;
-                    const int w = tc.w0 + wl;
-                    const bool valid = (m < p.rows_sub) && (n < p.B) && (h < p.H);
-                    float* v = vv[sub];
-                    const size_t pix = ((size_t)n * p.H + h) * p.W + w;
-
-                    if (p.epi == SR_EPI_RAW_STATS) {
-                        if (valid) {
-                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Cout + cbase);
+                        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = 0.f;
-                        }
-                        float sq[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
-                        const float tsum = warp_transpose_sum16(v, lane);
-                        const float tsq = warp_transpose_sum16(sq, lane);
-                        if (lane < 16) {
-                            atomicAdd(&s_sum[c16 + lane], tsum);
-                            atomicAdd(&s_sq[c16 + lane], tsq);
-                        }
-                        continue;
+                        for (int j = 0; j < 16; ++j) v[j] = 0.f;
                     }
-
-                    // shift (+ residual) + LeakyReLU
-                    {
-                        const float4* sp = reinterpret_cast<const float4*>(s_sum + c16);
+                    float sq[16];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 s4 = sp[j];
-                            v[4 * j] += s4.x; v[4 * j + 1] += s4.y; v[4 * j + 2] += s4.z; v[4 * j + 3] += s4.w;
-                        }
+                    for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+                    const float tsum = warp_transpose_sum16(v, lane);
+                    const float tsq = warp_transpose_sum16(sq, lane);
+                    if (lane < 16) {
+                        atomicAdd(&s_sum[c16 + lane], tsum);
+                        atomicAdd(&s_sq[c16 + lane], tsq);
                     }
-                    if (p.residual != nullptr && valid) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + cbase);
+                    return;
+                }
+                // shift (+ residual) + LeakyReLU
+                {
+                    const uint32_t sp = shift_s + (uint32_t)cbase * 4u;
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const uint4 r = __ldg(rp + j);
-                            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[k]);
-                                v[8 * j + 2 * k] += __bfloat162float(b2.x);
-                                v[8 * j + 2 * k + 1] += __bfloat162float(b2.y);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j], p.slope);
-
-                    if (p.epi == SR_EPI_ACT) {
-                        if (valid) {
-                            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + cbase);
-#pragma unroll
-                            for (int j = 0; j < 2; ++j)
-                                dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                    pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                        }
-                    } else if (p.epi == SR_EPI_ACT_POOL2) {
-                        uint4* dst = reinterpret_cast<uint4*>(staging + (size_t)(sub * kSubRows + m) * kStagePitchBf16 + half * 32);
-#pragma unroll
-                        for (int j = 0; j < 2; ++j)
-                            dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                    } else {  // SR_EPI_ACT_AVG
-                        float* dst = reinterpret_cast<float*>(staging) + (size_t)(sub * kSubRows + m) * kStagePitchF32 + half * 16;
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) dst[j] = v[j];
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 s4 = lds128(sp + 16u * j);
+                        v[4 * j] += __uint_as_float(s4.x); v[4 * j + 1] += __uint_as_float(s4.y);
+                        v[4 * j + 2] += __uint_as_float(s4.z); v[4 * j + 3] += __uint_as_float(s4.w);
                     }
                 }
+                if (p.residual != nullptr && valid) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + cbase);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint4 r = __ldg(rp + j);
+                        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[k]);
+                            v[8 * j + 2 * k] += __bfloat162float(b2.x);
+                            v[8 * j + 2 * k + 1] += __bfloat162float(b2.y);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j], p.slope);
+                if (p.epi == SR_EPI_ACT_AVG) {
+                    float* dst = reinterpret_cast<float*>(staging) + (size_t)(sub * kSubRows + m) * kStagePitchF32 + (c16 & 16);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) dst[j] = v[j];
+                } else {
+                    // bf16 half row (32 bytes) into the staging tile: pitch 80 keeps the 16-byte accesses conflict-free
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        sts128(my_row + (uint32_t)((c16 & 16) * 2 + 16 * j),
+                               make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                          pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7])));
+                }
+            };
 
-                if (p.epi == SR_EPI_ACT_POOL2) {
+            const int nch = (p.dbg & 4) ? 0 : nchunks;
+            float va[16], vb[16];
+            if (nch > 0) tmem_ld16(acc, va);
+            for (int ch = 0; ch < nch; ++ch) {
+                const int c32 = ch * 32;            // first of this thread's 32 channels inside the CTA's N range
+                // the two halves are double-buffered in registers: the TMEM read of one overlaps the arithmetic of the other
+                tmem_ld_wait();
+                tmem_ld16(acc + (uint32_t)(c32 + 16), vb);
+                do_half(va, c32);
+                tmem_ld_wait();
+                if (ch + 1 < nch) tmem_ld16(acc + (uint32_t)(c32 + 32), va);
+                do_half(vb, c32 + 16);
+                if (p.epi == SR_EPI_RAW_STATS) continue;
+
+                if (p.epi == SR_EPI_ACT) {
+                    __syncwarp();
+                    uint4 x[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[i] = lds128(t_rows + (uint32_t)(8 * i * kStagePitchBf16));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (t_ok[i]) *reinterpret_cast<uint4*>(t_base + t_rel[i] + c32) = x[i];
+                    __syncwarp();   // the rows are rewritten by the next chunk
+                } else if (p.epi == SR_EPI_ACT_POOL2) {
                     named_bar_sync(1, kEpiThreads);
                     const int Wp = p.TW >> 1;
                     const int Hp = p.stack_h ? p.TH : (p.TH >> 1);
@@ -434,10 +509,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                         pp /= Wp;
                         const int ph = pp % Hp;
                         const int img = pp / Hp;
-                        const int n = tc.n0 + img;
+                        const int pn = tc.n0 + img;
                         const int hp = (tc.h0 >> 1) + ph;
                         const int wp = (tc.w0 >> 1) + pw;
-                        if (n >= p.B || hp >= p.Ho || wp >= p.Wo) continue;
+                        if (pn >= p.B || hp >= p.Ho || wp >= p.Wo) continue;
                         uint4 acc4 = make_uint4(0, 0, 0, 0);
 #pragma unroll
                         for (int dy = 0; dy < 2; ++dy) {
@@ -445,18 +520,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                             for (int dx = 0; dx < 2; ++dx) {
                                 const int hh = 2 * ph + dy;
                                 const int ww = 2 * pw + dx;
-                                int sub, hloc, nloc;
+                                int psub, hloc, nloc;
                                 if (p.stack_h) {
-                                    sub = hh >= p.TH ? 1 : 0;
-                                    hloc = hh - sub * p.TH;
+                                    psub = hh >= p.TH ? 1 : 0;
+                                    hloc = hh - psub * p.TH;
                                     nloc = 0;
                                 } else {
-                                    sub = img >= p.TN ? 1 : 0;
-                                    nloc = img - sub * p.TN;
+                                    psub = img >= p.TN ? 1 : 0;
+                                    nloc = img - psub * p.TN;
                                     hloc = hh;
                                 }
-                                const int mrow = sub * kSubRows + (nloc * p.TH + hloc) * p.TW + ww;
-                                const uint4 x = *reinterpret_cast<const uint4*>(staging + (size_t)mrow * kStagePitchBf16 + g * 16);
+                                const int mrow = psub * kSubRows + (nloc * p.TH + hloc) * p.TW + ww;
+                                const uint4 x = lds128(stg_s + (uint32_t)(mrow * kStagePitchBf16 + g * 16));
                                 if (dy == 0 && dx == 0) {
                                     acc4 = x;
                                 } else {
@@ -468,34 +543,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                             }
                         }
                         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                           (((size_t)n * p.Ho + hp) * p.Wo + wp) * p.Cout + tc.co0 + ch * 32 + g * 8;
+                                           (((size_t)pn * p.Ho + hp) * p.Wo + wp) * p.Cout + tc.co0 + c32 + g * 8;
                         *reinterpret_cast<uint4*>(o) = acc4;
                     }
                     named_bar_sync(1, kEpiThreads);
-                } else if (p.epi == SR_EPI_ACT_AVG) {
+                } else {  // SR_EPI_ACT_AVG
                     named_bar_sync(1, kEpiThreads);
                     const int imgs = 2 * p.TN;
                     const float* stg = reinterpret_cast<const float*>(staging);
                     for (int item = et; item < imgs * 32; item += kEpiThreads) {
                         const int j = item & 31;
                         const int img = item >> 5;
-                        const int n = tc.n0 + img;
-                        if (n >= p.B) continue;
-                        const int sub = img >= p.TN ? 1 : 0;
-                        const int nloc = img - sub * p.TN;
-                        const float* src = stg + (size_t)(sub * kSubRows + nloc * hw_sub) * kStagePitchF32 + j;
+                        const int an = tc.n0 + img;
+                        if (an >= p.B) continue;
+                        const int asub = img >= p.TN ? 1 : 0;
+                        const int nloc = img - asub * p.TN;
+                        const float* src = stg + (size_t)(asub * kSubRows + nloc * hw_sub) * kStagePitchF32 + j;
                         float a = 0.f;
                         for (int r = 0; r < hw_sub; ++r) a += src[(size_t)r * kStagePitchF32];
-                        reinterpret_cast<float*>(p.out)[(size_t)n * p.Cout + tc.co0 + ch * 32 + j] = a / (float)hw_sub;
+                        reinterpret_cast<float*>(p.out)[(size_t)an * p.Cout + tc.co0 + c32 + j] = a / (float)hw_sub;
                     }
                     named_bar_sync(1, kEpiThreads);
                 }
             }
 
-            // all of this warp's TMEM reads of the tile are complete: hand the accumulator back to the MMA warp
+            // all of this warp's TMEM reads of the tile are complete: hand the accumulator back to the MMA warps
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_a(a_tempty + 8u * as);
+            if (warp == kEpiWarp0) SRB_TRACE(7);
+            if (++as == p.acc_stages) { as = 0; aph ^= 1u; }
 
             if (p.epi == SR_EPI_RAW_STATS) {
                 named_bar_sync(1, kEpiThreads);
@@ -543,7 +620,11 @@ struct Tile {
 };
 
 // Choose the TMA box (TW, TH, TN) of one 128-row sub-tile and how the CTA's two sub-tiles are stacked.
-bool pick_tile(int H, int W, int epi, Tile* out) {
+//   mode 0  (small maps) any box that maximises the useful UMMA rows; these are bandwidth-friendly enough because the
+//           whole map of many images stays in L2
+//   mode 1  prefer geometry: a row-stacked tile of ONE image with >= 95 % useful rows (it enables tap reuse: 3 instead of
+//           9 activation loads per pixel), else full-width boxes (long contiguous runs for TMA), else mode 0
+bool pick_tile_generic(int H, int W, int epi, bool full_width, bool stacked_only, double min_util, Tile* out) {
     const bool pooled = epi == SR_EPI_ACT_POOL2;
     const bool avg = epi == SR_EPI_ACT_AVG;
     const int Heff = pooled ? (H & ~1) : H;  // MaxPool2d(2) floors: an odd last row is never needed
@@ -552,11 +633,12 @@ bool pick_tile(int H, int W, int epi, Tile* out) {
         if (W % tiles_w) continue;
         const int TW = W / tiles_w;
         if (TW > 128) continue;
+        if (full_width && tiles_w != 1) continue;
         if (pooled && tiles_w > 1 && (TW & 1)) continue;  // pooling windows must not straddle CTAs
         if (avg && tiles_w != 1) continue;
         for (int TH = 1; TH <= Heff && TW * TH <= 128; ++TH) {
             if (avg && TH != H) continue;
-            for (int stack_h = 0; stack_h < 2; ++stack_h) {
+            for (int stack_h = stacked_only ? 1 : 0; stack_h < 2; ++stack_h) {
                 int TN, th_cnt;
                 double util;
                 if (!stack_h) {  // the CTA's two sub-tiles are consecutive groups of TN images
@@ -570,8 +652,10 @@ bool pick_tile(int H, int W, int epi, Tile* out) {
                     th_cnt = (Heff + 2 * TH - 1) / (2 * TH);
                     util = (double)(TW * TH) / 128.0 * (double)Heff / (double)(2 * TH * th_cnt);
                 }
-                // most useful UMMA rows first; ties: row stacking (halo locality), then taller boxes
-                const long key = (long)(util * 10000.0 + 0.5) * 1000 + stack_h * 500 + TH;
+                if (util < min_util) continue;
+                // most useful UMMA rows first; ties: wider boxes, row stacking (halo locality), then taller boxes
+                const long key = (long)(util * 10000.0 + 0.5) * 100000 + (stacked_only || full_width ? TW * 1000 : 0) +
+                                 stack_h * 500 + TH;
                 if (key > best_key) {
                     best_key = key;
                     *out = Tile{TW, TH, TN, stack_h, tiles_w, th_cnt};
@@ -580,6 +664,16 @@ bool pick_tile(int H, int W, int epi, Tile* out) {
         }
     }
     return best_key >= 0;
+}
+
+bool pick_tile(int H, int W, int epi, Tile* out) {
+    int mode = H * W >= 1024 ? 1 : 0;   // measured: 84x84 / 42x42 maps want mode 1, 21x21 and smaller run faster in mode 0
+    if (const char* e = getenv("SRB_TILE_MODE")) mode = atoi(e);
+    if (mode >= 1) {
+        if (pick_tile_generic(H, W, epi, false, true, 0.95, out)) return true;
+        if (pick_tile_generic(H, W, epi, true, false, 0.90, out)) return true;
+    }
+    return pick_tile_generic(H, W, epi, false, false, 0.0, out);
 }
 
 // Channel block per pipeline stage.  128-byte rows whenever the tensor has at least 64 channels: a ragged last block
@@ -641,10 +735,11 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
     if (2 * p.n_cta > 512) return fail(SR_E_ARG, "sr_conv: accumulators need %d TMEM columns", 2 * p.n_cta);
     p.acc_stages = std::min(4, 512 / (2 * p.n_cta));   // as many accumulator stages as TMEM holds
     p.tmem_cols = 512;                                 // one persistent CTA per SM owns all of TMEM
+    if (const char* e = getenv("SRB_CONV_DBG")) p.dbg = atoi(e);
     p.n_splits = ns;
 
     int staging = 0;   // the producer prefetches the next tile during the epilogue: staging cannot alias the pipeline
-    if (a->epilogue == SR_EPI_ACT_POOL2) staging = 2 * kSubRows * kStagePitchBf16;
+    if (a->epilogue == SR_EPI_ACT_POOL2 || a->epilogue == SR_EPI_ACT) staging = 2 * kSubRows * kStagePitchBf16;
     if (a->epilogue == SR_EPI_ACT_AVG) staging = 2 * kSubRows * kStagePitchF32 * 4;
 
     static std::once_flag attr_once;
@@ -659,7 +754,9 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
     });
     if (attr_err != cudaSuccess)
         return fail(SR_E_CUDA, "sr_conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
-    const int budget = max_dyn - 1024 - staging;
+    p.staging_bytes = staging;
+    const int shift_bytes = a->epilogue == SR_EPI_RAW_STATS ? 0 : (int)align_up((int64_t)a->cout * 4, 16);
+    const int budget = max_dyn - 1024 - staging - shift_bytes;
 
     for (int i = 0; i < a->n_panels; ++i) {
         const sr_conv_panel& sp = a->panel[i];
@@ -685,20 +782,20 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
         *b_off = a_bytes;
         return a_bytes + b_tiles * p.n_cta * kcb;   // n_cta is a multiple of 32: every weight tile stays 1024-aligned
     };
-    // Row width (channels per stage): the widest one that still leaves three stages in flight - every barrier round costs
-    // the issuing warps ~350 cycles whatever it carries, so stages should be as fat as the ring depth allows.
+    // Row width (channels per stage).  Measured on B200: tcgen05.mma reads 64-byte / 32-byte swizzled rows at half / a
+    // quarter of the shared-memory bandwidth of 128-byte rows (two / one rows per 128-byte wavefront instead of four), so
+    // the widest rows always win; if the tall-box stage does not leave three stages in flight at that width (N = 160
+    // layers: 103 KB per stage), give up tap reuse rather than row width.
     const int kc_cap = kc_bytes_for(a->panel[0].cin_pad);
-    int kc0 = 0;
-    if (const char* e = getenv("SRB_KC_BYTES")) kc0 = std::min(kc_cap, atoi(e));
-    if (kc0 != 32 && kc0 != 64 && kc0 != 128) {
-        kc0 = 32;
-        for (int kcb = kc_cap; kcb >= 32; kcb >>= 1) {
-            int off;
-            if (budget / stage_bytes_for(kcb, &off) >= 3) {
-                kc0 = kcb;
-                break;
-            }
-        }
+    int kc0 = kc_cap;
+    {
+        int off;
+        if (budget / stage_bytes_for(kc_cap, &off) < 3 && !getenv("SRB_KEEP_REUSE"))
+            for (int i = 0; i < a->n_panels; ++i) p.panel[i].reuse = 0;
+    }
+    if (const char* e = getenv("SRB_KC_BYTES")) {
+        const int v = atoi(e);
+        if (v == 32 || v == 64 || v == 128) kc0 = std::min(kc_cap, v);
     }
     p.stage_bytes = stage_bytes_for(kc0, &p.b_off);
     p.n_stages = std::min(8, budget / p.stage_bytes);
@@ -737,7 +834,7 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
             if (r != CUDA_SUCCESS) return fail(SR_E_CUDA, "sr_conv: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
         }
     }
-    const int dyn_smem = p.n_stages * p.stage_bytes + staging + 1024;
+    const int dyn_smem = p.n_stages * p.stage_bytes + staging + shift_bytes + 1024;
 
     const int tiles_n = tile.stack_h ? a->batch : (a->batch + 2 * tile.TN - 1) / (2 * tile.TN);
     p.total_tiles = tile.tiles_w * tile.tiles_h * tiles_n * ns;
@@ -748,7 +845,30 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     dim3 grid((unsigned)std::min(p.total_tiles, num_sms), 1, 1);
+    static long long* trace_buf = nullptr;
+    if (p.dbg & 16) {
+        if (!trace_buf) cudaMalloc(&trace_buf, 96 * 8 * sizeof(long long));
+        cudaMemsetAsync(trace_buf, 0, 96 * 8 * sizeof(long long), stream);
+        p.trace = trace_buf;
+    }
     conv_umma_kernel<<<grid, kThreads, dyn_smem, stream>>>(p);
     SR_CUDA_OK(cudaGetLastError());
+    if (p.dbg & 16) {
+        static int dumped = 0;
+        if (dumped++ == 4) {   // a warm launch
+            long long h[96 * 8];
+            cudaStreamSynchronize(stream);
+            cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "trace (cycles since first event; stages %d x %d B, acc stages %d, tiles/CTA %d)\n", p.n_stages,
+                    p.stage_bytes, p.acc_stages, p.total_tiles / (int)grid.x);
+            fprintf(stderr, "tile  prod_start prod_end | mma_wait mma_go mma_done | epi_wait epi_go epi_done\n");
+            const long long t0 = h[0];
+            for (int t = 0; t < 40; ++t) {
+                fprintf(stderr, "%3d ", t);
+                for (int e = 0; e < 8; ++e) fprintf(stderr, " %8lld", h[t * 8 + e] ? h[t * 8 + e] - t0 : -1);
+                fprintf(stderr, "\n");
+            }
+        }
+    }
     return SR_OK;
 }

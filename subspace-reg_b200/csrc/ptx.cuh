@@ -250,6 +250,17 @@ __device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* m
         : "memory");
 }
 
+// Explicit shared-space 16-byte accesses by 32-bit address (a generic pointer into dynamic shared memory makes the compiler
+// emit generic LD/ST, which are slower than LDS/STS and showed up as the top stall of the conv epilogue).
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }

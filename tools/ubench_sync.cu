@@ -12,7 +12,7 @@ using namespace srb;
 
 struct UB {
     CUtensorMap tm;
-    int steps, depth, n_cons, use_commit, mma_per_step, mma_n, tma_rows, n_tma, elect, slot_bytes;
+    int steps, depth, n_cons, use_commit, mma_per_step, mma_n, tma_rows, n_tma, elect, slot_bytes, row_bytes;
     long long* out;
 };
 
@@ -52,9 +52,9 @@ __global__ void __launch_bounds__(96, 1) k_ring(const __grid_constant__ UB p) {
             for (int it = 0; it < p.steps; ++it) {
                 mbar_wait_a(a_empty + 8u * s, ph ^ 1u);
                 if (p.n_tma) {
-                    mbar_expect_tx_a(a_full + 8u * s, (uint32_t)(p.n_tma * p.tma_rows * 128));
+                    mbar_expect_tx_a(a_full + 8u * s, (uint32_t)(p.n_tma * p.tma_rows * p.row_bytes));
                     for (int j = 0; j < p.n_tma; ++j) {
-                        tma_load_2d_a(base + (uint32_t)(s * p.slot_bytes + j * p.tma_rows * 128), &p.tm, a_full + 8u * s, 0, row);
+                        tma_load_2d_a(base + (uint32_t)(s * p.slot_bytes + j * p.tma_rows * p.row_bytes), &p.tm, a_full + 8u * s, 0, row);
                         row = (row + p.tma_rows) & 32767;
                     }
                 } else {
@@ -148,7 +148,7 @@ int main() {
     CK(cudaFuncSetAttribute(k_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 
     auto run = [&](const char* name, int grid, int depth, int n_cons, int use_commit, int mma_per_step, int mma_n, int tma_rows,
-                   int n_tma, int elect) {
+                   int n_tma, int elect, int row_bytes = 128, int slot_bytes = 32768) {
         UB p;
         memset(&p, 0, sizeof(p));
         p.steps = 4096;
@@ -160,15 +160,16 @@ int main() {
         p.tma_rows = tma_rows;
         p.n_tma = n_tma;
         p.elect = elect;
-        p.slot_bytes = 32768;
+        p.slot_bytes = slot_bytes;
+        p.row_bytes = row_bytes;
         p.out = dout;
         if (n_tma) {
-            cuuint64_t gdim[2] = {64, rows};
-            cuuint64_t gstr[1] = {128};
-            cuuint32_t box[2] = {64, (cuuint32_t)tma_rows};
+            cuuint64_t gdim[2] = {(cuuint64_t)row_bytes / 2, rows};
+            cuuint64_t gstr[1] = {(cuuint64_t)row_bytes};
+            cuuint32_t box[2] = {(cuuint32_t)row_bytes / 2, (cuuint32_t)tma_rows};
             cuuint32_t est[2] = {1, 1};
             CUresult r = encode(&p.tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, gbuf, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); exit(1); }
         }
         if (depth * p.slot_bytes > 196 * 1024) { printf("%s: ring too large\n", name); return; }
@@ -183,11 +184,22 @@ int main() {
         const double cps = (double)mx / p.steps;
         printf("%-44s grid %3d depth %d cons %d commit %d mma %2d N %3d tma %dx%3d rows elect %d : %8.1f cyc/step", name, grid, depth,
                n_cons, use_commit, mma_per_step, mma_n, n_tma, tma_rows, elect, cps);
-        if (n_tma) printf("  (%.1f B/cyc/SM)", (double)n_tma * tma_rows * 128 / cps);
+        if (n_tma) printf("  (%.1f B/cyc/SM, %.2f rows/cyc, %d B rows)", (double)n_tma * tma_rows * row_bytes / cps, (double)n_tma * tma_rows / cps, row_bytes);
         if (mma_per_step) printf("  (%.1f cyc/MMA/warp, pipe floor %d)", cps / mma_per_step, n_cons * 128 * mma_n / 256);
         printf("\n");
     };
 
+    if (getenv("UB_TMA")) {
+        for (int g : {1, 148}) {
+            for (int rb : {128, 64, 32}) {
+                for (int nt : {1, 2, 3, 4}) {
+                    if (nt * 256 * rb > 65536) continue;
+                    run("tma rate", g, 3, 1, 0, 0, 64, 256, nt, 0, rb, 65536);
+                }
+            }
+        }
+        return 0;
+    }
     // 1. pure handshake
     run("handshake arrive", 1, 4, 1, 0, 0, 64, 0, 0, 0);
     run("handshake commit", 1, 4, 1, 1, 0, 64, 0, 0, 0);
