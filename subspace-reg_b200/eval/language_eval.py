@@ -211,14 +211,18 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         if has_mem:
             f_train = torch.cat([f_train, net.features(memory.data)], 0)
         tm['backbone_imgs'] += n_sup + n_mem
-        if idx + 1 < iter_num:
-            # the next session's dropout masks are drawn on a host thread while the GPU runs this session's cache build
-            # and head loop (verified against the live generator when they are consumed)
-            nxt = [n_sup] + ([n_mem + 25] if (opt.memory_replay == 1) else [])
-            skip = opt.n_ways * W_cols                       # next session's nn.Linear(640, n_ways) init
+        if idx + 1 < iter_num and not net.engine().mask_prefetch_alive():
+            # the dropout masks of EVERY remaining session are drawn on a host thread, working ahead while the GPU runs
+            # the cache builds and head loops (each mask is verified against the live generator when it is consumed)
+            skip = opt.n_ways * W_cols                       # a session's nn.Linear(640, n_ways) init
             if use_pull and opt.attraction_override == "mapping_linear_label2image":
                 skip += lang_puller.novel_embeds.size(1) * W_cols + W_cols   # LinearMap re-created every session
-            net.engine().start_mask_prefetch(nxt, skip_words_first=skip)
+            fwds = []
+            for j in range(idx + 1, iter_num):
+                fwds.append((skip, n_sup))
+                if opt.memory_replay == 1:
+                    fwds.append((0, n_mem + 25 * (j - idx)))
+            net.engine().start_mask_prefetch(fwds)
         tp1 = _tick()
         ph['train_pass'] += tp1 - tp0
         W = net.classifier.weight.data

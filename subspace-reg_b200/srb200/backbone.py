@@ -134,12 +134,15 @@ class BackboneEngine(object):
         return h
 
     # ---------------------------------------------------------------- train-mode pass (epoch 1 of a session)
-    def start_mask_prefetch(self, batches, skip_words_first=0):
-        """Begin drawing, on a host thread, the dropout masks of the next len(batches) train-mode forwards (batch sizes
-        given), assuming `skip_words_first` generator draws happen before them (the next session's nn.Linear init).
-        DropBlock draws are skipped over (their gamma is not known yet) and made later from the live generator."""
-        steps = [('skip', skip_words_first)] if skip_words_first else []
-        for f, batch in enumerate(batches):
+    def start_mask_prefetch(self, forwards):
+        """Begin drawing, on a host thread, the dropout masks of the next len(forwards) train-mode forwards.
+        forwards: [(skip_words_before, batch), ...] in the order they will run; `skip_words_before` generator draws are
+        assumed to happen before that forward (the session's nn.Linear init).  DropBlock draws are skipped over (their
+        gamma is not known yet) and made later from the live generator.  May cover every remaining session of a run."""
+        steps = []
+        for f, (skip, batch) in enumerate(forwards):
+            if skip:
+                steps.append(('skip', skip))
             size = 84
             for bi, b in enumerate(self.blocks):
                 size = size // b['pool']
@@ -152,6 +155,9 @@ class BackboneEngine(object):
                     steps.append(('draw', (f, bi), ent[0], 1 - DROP_RATE))
         self._prefetch = host_rng.MaskPrefetch(steps)
         self._pf_fwd = 0
+
+    def mask_prefetch_alive(self):
+        return self._prefetch is not None and self._prefetch.alive()
 
     def _pinned(self, key, shape, sync=True):
         """Reusable pinned staging buffer (uint8) + the event of its last H2D copy."""

@@ -92,25 +92,37 @@ class MaskPrefetch(object):
     session's nn.Linear init only need to be SKIPPED: they use a fixed number of 32-bit draws.  Every pre-drawn mask
     remembers the generator state before and after it; `take` hands it out only if the live generator is exactly in
     the `before` state (then moves it to `after`), so a wrong guess about what happens in between costs nothing but
-    the prefetch."""
+    the prefetch.  One instance may cover every remaining session of a run: the thread then works ahead continuously
+    and `take` only waits for the mask it asks for."""
 
     def __init__(self, steps):
         """steps: list of ('skip', n_words) | ('draw', key, uint8 CPU buffer [shape], p)."""
         self.ok = replay_available()
         self.results = {}
         self.thread = None
+        self.dead = False          # the live stream diverged from the guess (or the replay failed): nothing is usable
+        self.finished = False
+        self._cv = threading.Condition()
+        self._pending = sum(1 for st in steps if st[0] == 'draw')
         if not self.ok:
+            self.dead = True
             return
         self._state = torch.get_rng_state().clone()
         self._steps = steps
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
+    def alive(self):
+        """True while there are pre-drawn (or still to be drawn) masks that the live stream may yet consume."""
+        return self.thread is not None and not self.dead and self._pending > 0
+
     def _run(self):
         lib = L.load()
         blob = self._state
         try:
             for st in self._steps:
+                if self.dead:
+                    break
                 if st[0] == 'skip':
                     if lib.sr_host_bernoulli(C.c_void_p(blob.data_ptr()), blob.numel(), 2, 0.0, int(st[1]), None) < 0:
                         raise RuntimeError("skip failed")
@@ -121,21 +133,30 @@ class MaskPrefetch(object):
                                                  C.c_void_p(buf.data_ptr()))
                     if ones < 0:
                         raise RuntimeError("draw failed")
-                    self.results[key] = (before, blob.clone(), buf, int(ones))
+                    with self._cv:
+                        self.results[key] = (before, blob.clone(), buf, int(ones))
+                        self._cv.notify_all()
         except Exception:
-            self.results = {}
+            self.dead = True
+        with self._cv:
+            self.finished = True
+            self._cv.notify_all()
 
     def take(self, key, shape):
         """-> (uint8 buffer, ones) or None.  Advances torch's live generator exactly as the draw would have."""
-        if self.thread is None:
+        if self.thread is None or self.dead:
             return None
-        self.thread.join()
-        ent = self.results.pop(key, None)
+        with self._cv:
+            while key not in self.results and not self.finished and not self.dead:
+                self._cv.wait()
+            ent = self.results.pop(key, None)
         if ent is None:
             return None
+        self._pending -= 1
         before, after, buf, ones = ent
         if tuple(buf.shape) != tuple(shape) or not torch.equal(torch.get_rng_state(), before):
-            self.results = {}          # the stream went somewhere else: everything drawn after this point is void too
+            self.dead = True           # the stream went somewhere else: everything drawn after this point is void too
+            self.results = {}
             return None
         torch.set_rng_state(after)
         return buf, ones
