@@ -255,6 +255,12 @@ int32_t sr_project_rows(const float* x, const float* qt, int32_t n, int32_t q_ro
  * ---------------------------------------------------------------------------------------------- */
 int64_t sr_host_bernoulli(void* state_blob, int64_t blob_bytes, int32_t kind, double p, int64_t n, uint8_t* out);
 
+/* Host helper: DropBlock._compute_block_mask (resnet_language.py:327-352) on the drawn seeds.
+ * seeds: HOST uint8[planes, hs, ws] (1 = block seed); keep: HOST uint8[planes, hs+bs-1, ws+bs-1], 0 wherever a
+ * bs x bs block anchored at a seed covers the pixel, 1 elsewhere (= 1 - padded mask).  Returns the number of ones in
+ * `keep` (count_ones of :321), or -1 on bad arguments. */
+int64_t sr_host_dropblock(const uint8_t* seeds, int64_t planes, int32_t hs, int32_t ws, int32_t bs, uint8_t* keep);
+
 #ifdef __cplusplus
 }
 #endif

@@ -305,3 +305,27 @@ extern "C" int64_t sr_host_bernoulli(void* state_blob, int64_t blob_bytes, int32
     b->next = (uint64_t)pos;
     return ones;
 }
+
+extern "C" int64_t sr_host_dropblock(const uint8_t* seeds, int64_t planes, int32_t hs, int32_t ws, int32_t bs, uint8_t* keep) {
+    if (!seeds || !keep || planes < 0 || hs < 1 || ws < 1 || bs < 1) return -1;
+    const int ho = hs + bs - 1, wo = ws + bs - 1;
+    const int64_t plane_in = (int64_t)hs * ws, plane_out = (int64_t)ho * wo;
+    const int64_t total = planes * plane_out;
+    memset(keep, 1, (size_t)total);
+    // seeds are sparse (gamma is a few percent): jump from seed to seed with memchr over the whole seed array
+    const uint8_t* const end = seeds + planes * plane_in;
+    for (const uint8_t* q = seeds; q < end;) {
+        q = static_cast<const uint8_t*>(memchr(q, 1, (size_t)(end - q)));
+        if (!q) break;
+        const int64_t idx = q - seeds;
+        const int64_t pl = idx / plane_in;
+        const int r = (int)(idx - pl * plane_in);
+        const int y = r / ws, x = r - y * ws;
+        uint8_t* kp = keep + pl * plane_out + (int64_t)y * wo + x;
+        for (int i = 0; i < bs; ++i) memset(kp + (int64_t)i * wo, 0, (size_t)bs);
+        ++q;
+    }
+    uint64_t ones = 0;
+    for (int64_t k = 0; k < total; ++k) ones += keep[k];
+    return (int64_t)ones;
+}

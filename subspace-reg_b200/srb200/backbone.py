@@ -187,7 +187,7 @@ class BackboneEngine(object):
             if got is not None:                                                # drawn ahead of time on the host thread
                 ent = self._pinned(('pf', self._cur_fwd, bi), shape, sync=False)
             else:
-                ent = self._pinned(('m', bi), shape)
+                ent = self._pinned(('m', bi, self._cur_fwd & 1), shape)
                 host_rng.bernoulli_u8(shape, 1 - DROP_RATE, 0, out=ent[0])    # noise.bernoulli_(1 - p)
         else:
             bs = b['block_size']
@@ -196,20 +196,9 @@ class BackboneEngine(object):
             gamma = (1 - keep_rate) / bs ** 2 * size ** 2 / (size - bs + 1) ** 2
             seed_shape = (batch, b['cout'], size - (bs - 1), size - (bs - 1))
             seeds, n_seed = host_rng.bernoulli_u8(seed_shape, gamma, 1)        # Bernoulli(gamma).sample(...)
-            ent = self._pinned(('m', bi), shape)
-            if bs == 1:
-                ent[0].copy_(1 - seeds)
-                kept = seeds.numel() - n_seed
-            else:
-                left, right = int((bs - 1) / 2), int(bs / 2)
-                padded = F.pad(seeds, (left, right, left, right))
-                if n_seed > 0:
-                    Hm, Wm = seeds.shape[2], seeds.shape[3]
-                    for i in range(bs):
-                        for j in range(bs):
-                            padded[:, :, i:i + Hm, j:j + Wm] = torch.maximum(padded[:, :, i:i + Hm, j:j + Wm], seeds)
-                ent[0].copy_(1 - padded)
-                kept = int(ent[0].sum())
+            # alternate staging buffers: the second forward of a session must not wait for the H2D copy of the first
+            ent = self._pinned(('m', bi, self._cur_fwd & 1), shape)
+            kept = host_rng.dropblock_keep(seeds, bs, ent[0])                  # _compute_block_mask, 1 - mask, .sum()
             # countM / count_ones: python int over an fp32 0-d tensor -> fp32 division
             scale = float(torch.tensor(float(ent[0].numel()), dtype=torch.float32) / torch.tensor(float(kept), dtype=torch.float32))
         keep = ent[0].to(device, non_blocking=True)
@@ -230,12 +219,20 @@ class BackboneEngine(object):
         h = ops.pack_input(x.contiguous(), 16)
         nb = len(self.blocks)
 
+        # one zeroed fp64 scratch for the (sum, sum of squares) of every conv of this forward, one fused counter bump at
+        # the end: ~40 fewer tiny launches per forward (the train-mode pass is host-bound)
+        n_stats = sum(2 * b['cout'] * (4 if b['downsample'] else 3) for b in self.blocks)
+        stats_all = torch.zeros(n_stats, dtype=torch.float64, device=dev)
+        stats_off = [0]
+        bumped = []
+
         def conv_bn(act, wgt, bn, cout):
-            stats = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
+            stats = stats_all[stats_off[0]:stats_off[0] + 2 * cout]
+            stats_off[0] += 2 * cout
             raw = ops.conv([(act, wgt)], cout, epilogue=L.SR_EPI_RAW_STATS, stats=stats)
             count = raw.shape[0] * raw.shape[1] * raw.shape[2]
             mean, invstd = ops.bn_finalize(stats, count, bn.running_mean, bn.running_var, BN_EPS, BN_MOMENTUM)
-            bn.num_batches_tracked += 1
+            bumped.append(bn.num_batches_tracked)
             return raw, mean, invstd
 
         for bi, (b, w) in enumerate(zip(self.blocks, raw_w)):
@@ -260,6 +257,7 @@ class BackboneEngine(object):
             else:
                 h = ops.bn_apply(r3, mu3, is3, m.bn3.weight.detach(), m.bn3.bias.detach(), res_act=h, lrelu=True,
                                  slope=SLOPE, pool=pool, keep=keep, keep_scale=scale)
+        torch._foreach_add_(bumped, 1)   # BatchNorm2d.num_batches_tracked of every BN that ran
         self.invalidate()   # running statistics moved: the folded weights are stale
         if h.dim() == 4:    # resnet12: the last block is pooled 2x2, the global average follows
             h = ops.global_avg(h)

@@ -77,6 +77,17 @@ def bernoulli_u8(shape, p, kind, out=None):
     return t, int(t.sum())
 
 
+def dropblock_keep(seeds, block_size, out):
+    """DropBlock._compute_block_mask on host: seeds uint8 [B,C,hs,ws] -> out uint8 [B,C,hs+bs-1,ws+bs-1] (1 = keep);
+    returns the number of kept positions."""
+    B, Cc, hs, ws = seeds.shape
+    assert seeds.is_contiguous() and out.is_contiguous() and out.numel() == B * Cc * (hs + block_size - 1) * (ws + block_size - 1)
+    kept = L.load().sr_host_dropblock(C.c_void_p(seeds.data_ptr()), B * Cc, hs, ws, block_size, C.c_void_p(out.data_ptr()))
+    if kept < 0:
+        raise RuntimeError("srb200: sr_host_dropblock rejected its arguments")
+    return int(kept)
+
+
 def _numel(shape):
     n = 1
     for s in shape:

@@ -84,3 +84,25 @@ def test_mask_prefetch_is_exact_and_self_checking():
     torch.rand(1)
     live = torch.get_rng_state()
     assert pf.take('a', shapes[0]) is None and torch.equal(torch.get_rng_state(), live)
+
+
+def test_dropblock_keep_matches_the_torch_formulation():
+    """sr_host_dropblock == 1 - (union of the seeds shifted over a bs x bs window), as _compute_block_mask builds it
+    (reference models/resnet_language.py:327-352), and its return value is the count of kept positions."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    for bs, hs in ((5, 6), (3, 3), (1, 5), (2, 4)):
+        seeds = (torch.rand(4, 7, hs, hs, generator=g) < 0.08).to(torch.uint8)
+        left, right = int((bs - 1) / 2), int(bs / 2)
+        padded = F.pad(seeds, (left, right, left, right))
+        for i in range(bs):
+            for j in range(bs):
+                padded[:, :, i:i + hs, j:j + hs] = torch.maximum(padded[:, :, i:i + hs, j:j + hs], seeds)
+        want = 1 - padded
+        out = torch.empty(4, 7, hs + bs - 1, hs + bs - 1, dtype=torch.uint8)
+        kept = host_rng.dropblock_keep(seeds.contiguous(), bs, out)
+        assert torch.equal(out, want)
+        assert kept == int(want.sum())
+    # no seeds at all: everything is kept
+    out = torch.zeros(2, 3, 7, 7, dtype=torch.uint8)
+    assert host_rng.dropblock_keep(torch.zeros(2, 3, 5, 5, dtype=torch.uint8), 3, out) == out.numel() and bool(out.all())

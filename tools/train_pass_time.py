@@ -40,3 +40,20 @@ for rep in range(4):
     t2 = time.perf_counter()
     print("forward B=%d: host %.1f ms, +sync %.1f ms; draw_mask per block (ms): %s" %
           (B, (t1 - t0) * 1e3, (t2 - t1) * 1e3, {k: round(v * 1e3, 1) for k, v in times.items()}), flush=True)
+
+# ---- with the dropout masks prefetched (the session path): what is left on the critical path? ----
+print("with prefetch:")
+for rep in range(3):
+    t0 = time.perf_counter()
+    eng.start_mask_prefetch([(0, B)])
+    eng._prefetch.thread.join()
+    t1 = time.perf_counter()
+    times.clear()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    f = net.features(x)
+    t3 = time.perf_counter()
+    torch.cuda.synchronize()
+    t4 = time.perf_counter()
+    print("prefetch thread %.1f ms | forward host %.1f ms, +sync %.1f ms; draw_mask per block (ms): %s" %
+          ((t1 - t0) * 1e3, (t3 - t2) * 1e3, (t4 - t3) * 1e3, {k: round(v * 1e3, 1) for k, v in times.items()}), flush=True)
