@@ -29,8 +29,8 @@ for p in (PKG, ROOT):
 
 GFLOP_PER_IMAGE = 8.1219  # conv FLOPs (2*MAC) of the RFS ResNet-18 on one 84x84 image, SURVEY.md section 8a row 6
 # dram__bytes_read.sum + dram__bytes_write.sum of the 18 conv launches of one backbone pass, per image, from the ncu --set full
-# capture summarised in profiles/r01_conv_ncu_full_final.txt (algorithmic bf16 NHWC activation traffic: 9.56 MB per image)
-DRAM_BYTES_PER_IMAGE_NCU = 9.41e6
+# capture summarised in profiles/r01_conv_ncu_full_v2.txt (algorithmic bf16 NHWC activation traffic: 9.56 MB per image)
+DRAM_BYTES_PER_IMAGE_NCU = 9.47e6
 
 
 def parse():
@@ -89,7 +89,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "250"], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -337,7 +337,7 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.59 PF burst scaled"
     roofline = {"bound": "tensor", "kernel": "conv_umma_kernel (18 convs + 4 fused 1x1 panels per image, eval-mode backbone pass)",
                 "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak,
-                "traffic": DRAM_BYTES_PER_IMAGE_NCU * nimg, "traffic_source": "ncu --set full, profiles/r01_conv_ncu_full_final.txt",
+                "traffic": DRAM_BYTES_PER_IMAGE_NCU * nimg, "traffic_source": "ncu --set full, profiles/r01_conv_ncu_full_v2.txt",
                 "peak_source": peak_src, "images": nimg, "ms": bb_ms, "img_per_s": nimg / (bb_ms * 1e-3),
                 "flops_per_image": GFLOP_PER_IMAGE * 1e9}
 
