@@ -99,14 +99,15 @@ def group_conv_basic():
     ok &= conv_case(2, 42, 64, 64, 9, L.SR_EPI_ACT)       # 3x3 halo via TMA OOB
     ok &= conv_case(3, 84, 64, 64, 9, L.SR_EPI_ACT)       # two w-tiles
     ok &= conv_case(2, 42, 64, 160, 9, L.SR_EPI_ACT)      # N = 160
+    ok &= conv_case(1, 84, 64, 64, 9, L.SR_EPI_ACT)       # a single image: most CTAs of the persistent grid idle
     return ok
 
 
 def group_conv_k():
     from srb200 import _lib as L
     ok = True
-    ok &= conv_case(2, 42, 160, 160, 9, L.SR_EPI_ACT)     # KC = 32 (SW64), 5 blocks / tap
-    ok &= conv_case(2, 84, 3, 64, 9, L.SR_EPI_ACT)        # KC = 16 (SW32)
+    ok &= conv_case(2, 42, 160, 160, 9, L.SR_EPI_ACT)     # ragged channel blocks 64 + 64 + 32 (zero K steps skipped)
+    ok &= conv_case(2, 84, 3, 64, 9, L.SR_EPI_ACT)        # KC = 16 (SW32), tall-box tap reuse
     ok &= conv_case(5, 21, 160, 320, 9, L.SR_EPI_ACT)     # box (21,3,2), N split 2
     ok &= conv_case(13, 10, 320, 640, 9, L.SR_EPI_ACT)    # box (10,2,6), ragged batch, N split 4
     ok &= conv_case(7, 10, 640, 640, 9, L.SR_EPI_ACT)     # 10 k-blocks / tap
@@ -130,6 +131,8 @@ def group_conv_train():
     from srb200 import _lib as L
     ok = True
     ok &= conv_case(3, 42, 64, 160, 9, L.SR_EPI_RAW_STATS)
+    ok &= conv_case(2, 84, 64, 64, 9, L.SR_EPI_RAW_STATS)   # tall-box tap reuse + raw output / statistics
+    ok &= conv_case(2, 84, 3, 64, 9, L.SR_EPI_RAW_STATS)
     ok &= conv_case(5, 21, 160, 320, 1, L.SR_EPI_RAW_STATS)
     ok &= conv_case(7, 5, 640, 640, 9, L.SR_EPI_RAW_STATS)
     return ok
