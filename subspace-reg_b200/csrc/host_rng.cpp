@@ -310,22 +310,45 @@ extern "C" int64_t sr_host_dropblock(const uint8_t* seeds, int64_t planes, int32
     if (!seeds || !keep || planes < 0 || hs < 1 || ws < 1 || bs < 1) return -1;
     const int ho = hs + bs - 1, wo = ws + bs - 1;
     const int64_t plane_in = (int64_t)hs * ws, plane_out = (int64_t)ho * wo;
-    const int64_t total = planes * plane_out;
-    memset(keep, 1, (size_t)total);
-    // seeds are sparse (gamma is a few percent): jump from seed to seed with memchr over the whole seed array
-    const uint8_t* const end = seeds + planes * plane_in;
-    for (const uint8_t* q = seeds; q < end;) {
-        q = static_cast<const uint8_t*>(memchr(q, 1, (size_t)(end - q)));
-        if (!q) break;
-        const int64_t idx = q - seeds;
-        const int64_t pl = idx / plane_in;
-        const int r = (int)(idx - pl * plane_in);
-        const int y = r / ws, x = r - y * ws;
-        uint8_t* kp = keep + pl * plane_out + (int64_t)y * wo + x;
-        for (int i = 0; i < bs; ++i) memset(kp + (int64_t)i * wo, 0, (size_t)bs);
-        ++q;
+    // one pass per plane: a plane without seeds (the common case: gamma is a few percent of a 6x6 / 3x3 seed map) is a
+    // single memset; planes are independent, so large masks are split over a few threads
+    auto run = [&](int64_t p0, int64_t p1) -> int64_t {
+        int64_t kept = 0;
+        for (int64_t pl = p0; pl < p1; ++pl) {
+            const uint8_t* sp = seeds + pl * plane_in;
+            uint8_t* kp = keep + pl * plane_out;
+            memset(kp, 1, (size_t)plane_out);
+            const uint8_t* q = static_cast<const uint8_t*>(memchr(sp, 1, (size_t)plane_in));
+            if (!q) {
+                kept += plane_out;
+                continue;
+            }
+            for (; q; q = static_cast<const uint8_t*>(memchr(q + 1, 1, (size_t)(sp + plane_in - (q + 1))))) {
+                const int r = (int)(q - sp);
+                const int y = r / ws, x = r - y * ws;
+                for (int i = 0; i < bs; ++i) memset(kp + (int64_t)(y + i) * wo + x, 0, (size_t)bs);
+                if (q + 1 >= sp + plane_in) break;
+            }
+            int64_t ones = 0;
+            for (int64_t k = 0; k < plane_out; ++k) ones += kp[k];
+            kept += ones;
+        }
+        return kept;
+    };
+    int workers = 4;
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && workers > hw - 1) workers = hw - 1;
+    if (workers < 2 || planes * plane_out < (1 << 20)) return run(0, planes);
+    std::vector<int64_t> part((size_t)workers, 0);
+    std::vector<std::thread> pool;
+    const int64_t share = (planes + workers - 1) / workers;
+    for (int k = 1; k < workers; ++k) {
+        const int64_t p0 = k * share, p1 = p0 + share < planes ? p0 + share : planes;
+        if (p0 < p1) pool.emplace_back([&, k, p0, p1] { part[(size_t)k] = run(p0, p1); });
     }
-    uint64_t ones = 0;
-    for (int64_t k = 0; k < total; ++k) ones += keep[k];
-    return (int64_t)ones;
+    part[0] = run(0, share < planes ? share : planes);
+    for (auto& t : pool) t.join();
+    int64_t kept = 0;
+    for (int k = 0; k < workers; ++k) kept += part[(size_t)k];
+    return kept;
 }
