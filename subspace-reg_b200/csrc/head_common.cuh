@@ -47,7 +47,8 @@ struct HeadCtrl {          // lives at the start of the workspace (zeroed by the
     float prev_loss;
     int error;
     int pad[2];
-    unsigned long long t_ns[6];   // profiling aid: CTA 0 ns in phase 1 / barrier 1 / phase 2 / barrier 2; loss CTA, pull CTA phase 1
+    unsigned long long t_ns[12];  // profiling aid: CTA 0 ns in phase 1 / barrier 1 / phase 2 / barrier 2; loss CTA, pull CTA phase 1;
+                                  // [6..8] phase 1: W stream, logits to smem, softmax + dlogits; [9..11] phase 2: prologue, DLt stream, update
     double norm_base_sq;   // ||W[:nb] - W0||_F^2
     double norm_prev_sq;   // ||W[nb:nb+np] - Wres||_F^2
 };

@@ -2,11 +2,13 @@
 // the step is ~1.5 MB / 30-90 MFLOP, far below what one kernel launch costs, so everything that does not change
 // between epochs stays in shared memory for the whole session and an epoch is TWO grid phases:
 //
-//   phase 1  row CTAs (R rows of X resident): stream W through a cp.async double buffer, logits, softmax,
-//            CE / top-k per row, dlogits -> DLt[c][n] (class-major);
+//   phase 1  row CTAs (R rows of X resident, k-major): stream W^T (k-major copy kept by phase 2) through a cp.async ring,
+//            logits as 4-class x R-row register tiles per thread with the k range split over the warps, softmax,
+//            CE / top-k per row, dlogits -> DL[n][c] (sample-major);
 //            pull CTA (Q^T resident, 153 KB): u = W_new Q  (projection coefficients of the newest rows);
 //            CTA 0: assembles the loss of the PREVIOUS epoch and applies the stopping rule (language_eval.py:298-318)
-//   phase 2  column CTAs (8 feature columns of X, W, momentum, W0, reserve, Q^T resident): stream DLt, dW = dZ^T X,
+//   phase 2  column CTAs (8 feature columns of X, W, momentum, W0, reserve, Q^T resident): stream DL, dW = dZ^T X as
+//            4-class x 8-column register tiles with the sample range split over the warps,
 //            every regulariser gradient, weight decay, SGD-momentum / Adam, write W; partial sums of
 //            ||W - W0||^2, ||W_prev - W_res||^2 for the next epoch and ||P w - w||^2 for this one.
 //
@@ -16,15 +18,15 @@
 #include <mutex>
 #include "common.h"
 #include "head_common.cuh"
+#include "ptx.cuh"
 
 namespace {
 using namespace srb;
 
 constexpr int kT = 256;
-constexpr int DC = 8;     // feature columns per column CTA
-constexpr int KC = 64;    // k-chunk of the W stream (phase 1) / n-chunk of the DLt stream (phase 2)
-constexpr int PITCH = 68; // floats per staged row: 16-byte aligned for cp.async, conflict-free LDS.128
-constexpr int NS = 4;     // cp.async stages of the W / DLt streams (one region, the two phases never overlap in a CTA)
+constexpr int DC = 8;     // feature columns per column CTA (16 measured slower: the update and the tile arithmetic double)
+constexpr int KC = 64;    // k-chunk of the W^T stream (phase 1) / n-chunk of the DL stream (phase 2): KC rows of CP floats
+constexpr int NS = 4;     // cp.async stages of the W^T / DL streams (one region, the two phases never overlap in a CTA)
 
 struct SmallParams {
     sr_head_args a;
@@ -32,7 +34,8 @@ struct SmallParams {
     int R, GA, GC, G;      // rows per row CTA, #row CTAs, #column CTAs, grid (= max(GA, GC) + loss CTA + pull CTA)
     int CP;                // classes padded to 64 or 128 (thread mapping of phase 1)
     HeadCtrl* ctrl;
-    float* DLt;            // [C][ldn]
+    float* DL;             // [ldn][CP]  dlogits, sample-major, classes padded with zeros
+    float* Wt;             // [d][CP]    W^T, kept in step with `weight` by the column CTAs
     float* rowloss;        // [2][n_total]
     int* rowhit;           // [2][n_total]
     double* nb_part;       // [2][GC]
@@ -40,6 +43,16 @@ struct SmallParams {
     double* pull_part;     // [GC]
     float* u;              // [n_new][q_rows]
 };
+
+// One bulk asynchronous copy (TMA, 1-D) of `bytes` contiguous bytes into shared memory, completion on an mbarrier.
+// Measured: a cp.async (LDGSTS) ring sustains only ~21 B/clk per SM here (outstanding-request limit x L2 latency); the bulk
+// engine has no such limit.
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
@@ -124,19 +137,27 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
 
     // ---- shared memory carve-up ----
     float* sp = reinterpret_cast<float*>(dyn);
-    float* Xrow = sp;            sp += is_row ? R * d : 0;                 // [R][d]
+    float* Xt = sp;              sp += is_row ? R * d : 0;                 // [d][R]  this CTA's rows of X, k-major
     float* Zs = sp;              sp += is_row ? R * (CP + 1) : 0;        // [R][CP+1] logits
-    const int xp = p.ldn + 4;    // pitch of the X column slice: +4 floats keeps the 8 rows on different banks
-    float* Xc = sp;              sp += is_col ? DC * xp : 0;               // [DC][xp]   (column-major slice of X)
+    float* Xn = sp;              sp += is_col ? p.ldn * DC : 0;            // [ldn][DC]  this CTA's columns of X, sample-major
     float* Wc = sp;              sp += is_col ? C * DC : 0;                // [C][DC] master copy of this CTA's W columns
     float* Vc = sp;              sp += is_col ? n_opt * C * DC : 0;        // optimiser state columns
     float* W0c = sp;             sp += (is_col && has_base) ? a.n_base * DC : 0;
     float* Rc = sp;              sp += (is_col && has_prev) ? a.n_prev_novel * DC : 0;
     float* Pc = sp;              sp += (is_col && (proj || fixed)) ? (proj ? q : a.n_new) * DC : 0;  // Q^T or puller columns
     float* Us = sp;              sp += (is_col && proj) ? ((a.n_new * q + 3) & ~3) : 0;      // [n_new][q] projection coefficients
-    float* Stg = sp;             sp += (is_row || is_col) ? NS * CP * PITCH : 0;   // NS x [CP][PITCH] stream stages
+    float* Stg = sp;             sp += (is_row || is_col) ? NS * KC * CP : 0;      // NS x [KC][CP] stream stages
     float* Qs = sp;              sp += (is_pull && proj) ? q * d : 0;      // [q][d]
     float* wn = sp;              sp += (is_pull && proj) ? a.n_new * d : 0;
+
+    __shared__ uint64_t stream_bar[NS];   // "chunk landed" barriers of the W^T / DL stream ring
+    if (tid == 0) {
+        for (int i = 0; i < NS; ++i) mbar_init(&stream_bar[i], 1);
+        mbar_fence_init();
+    }
+    const uint32_t a_bar = smem_u32(&stream_bar[0]), a_stg = smem_u32(Stg);
+    constexpr uint32_t kChunkBytes = KC * CP * 4;
+    uint32_t gchunk = 0;   // chunks consumed so far by this CTA (both streams): stage = gchunk % NS, parity = (gchunk / NS) & 1
 
     // ---- one-time loads of everything that is constant over the session ----
     const int r0 = cta * R;
@@ -145,18 +166,22 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
             const int r = i / (d / 4), k4 = i % (d / 4);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r0 + r < NT) v = *reinterpret_cast<const float4*>(a.feat + feat_row(a, r0 + r) * d + k4 * 4);
-            *reinterpret_cast<float4*>(Xrow + r * d + k4 * 4) = v;
+            Xt[(k4 * 4 + 0) * R + r] = v.x;
+            Xt[(k4 * 4 + 1) * R + r] = v.y;
+            Xt[(k4 * 4 + 2) * R + r] = v.z;
+            Xt[(k4 * 4 + 3) * R + r] = v.w;
         }
     }
     const int j0 = cta * DC;
     if (is_col) {
         for (int i = tid; i < p.ldn * DC; i += kT) {
             const int n = i / DC, j = i % DC;
-            Xc[j * xp + n] = n < NT ? a.feat[feat_row(a, n) * d + j0 + j] : 0.f;
+            Xn[n * DC + j] = n < NT ? a.feat[feat_row(a, n) * d + j0 + j] : 0.f;
         }
         for (int i = tid; i < C * DC; i += kT) {
             const int c = i / DC, j = i % DC;
             Wc[i] = a.weight[(int64_t)c * d + j0 + j];
+            p.Wt[(int64_t)(j0 + j) * CP + c] = Wc[i];
             for (int s = 0; s < n_opt; ++s) Vc[s * C * DC + i] = a.opt_state[(int64_t)s * C * d + (int64_t)c * d + j0 + j];
         }
         if (has_base)
@@ -186,15 +211,10 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
     unsigned int bar_target = 0;
     grid_barrier(p.ctrl, bar_target);
 
-    constexpr int RG = kT / CP;      // row groups in phase 1 (2 or 4)
-    constexpr int RPT = R / RG;      // rows per thread
-    static_assert(RPT >= 1, "too few rows per CTA for this class padding");
-    const int c1 = tid % CP, rg = tid / CP;
-    // rows >= C of the stream stages are never written by cp.async: zero them once so that the hot loops need no guards
-    if (is_row || is_col) {
-        for (int i = tid; i < NS * CP * PITCH; i += kT) Stg[i] = 0.f;
-        __syncthreads();
-    }
+    constexpr int CG = CP / 4;       // 4-class groups (16 or 32)
+    constexpr int KS = kT / CG;      // slices of a chunk's KC rows, one per (warp, half-warp) (16 or 8)
+    static_assert(KC % KS == 0 && R % 4 == 0, "tile shapes");
+    const int cg4 = tid % CG, ks = tid / CG;
     int e = 0;
     bool stopped = false;
     for (; e < a.max_epochs; ++e) {
@@ -204,47 +224,67 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
         // ======================= phase 1 =======================
         if (is_loss && e > 0) assemble_loss(p, e - 1, red);   // a CTA of its own: off the row CTAs' critical path
         if (is_row) {
-            float acc[RPT];
+            float acc[R][4];
 #pragma unroll
-            for (int i = 0; i < RPT; ++i) acc[i] = 0.f;
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
             const int nchunk = d / KC;
-            auto issue = [&](int ck) {
-                float* dst = Stg + (ck % NS) * CP * PITCH;
-                for (int i = tid; i < C * (KC / 4); i += kT) {
-                    const int c = i / (KC / 4), k4 = i % (KC / 4);
-                    cp_async16(dst + c * PITCH + k4 * 4, a.weight + (int64_t)c * d + ck * KC + k4 * 4);
-                }
+            auto issue = [&](int ck) {   // a chunk is KC * CP contiguous floats of W^T; called by thread 0 only
+                const uint32_t st = (gchunk + (uint32_t)ck) % NS;
+                mbar_expect_tx_a(a_bar + 8u * st, kChunkBytes);
+                bulk_load(a_stg + st * kChunkBytes, p.Wt + (int64_t)ck * KC * CP, kChunkBytes, a_bar + 8u * st);
             };
-            for (int s = 0; s < NS - 1; ++s) {
-                if (s < nchunk) issue(s);
-                cp_async_commit();
+            if (tid == 0) {
+                fence_proxy_async();   // the stages were last touched through the generic proxy (reduction buffers)
+                for (int s = 0; s < NS - 1 && s < nchunk; ++s) issue(s);
             }
             for (int ck = 0; ck < nchunk; ++ck) {
-                cp_async_wait<NS - 2>();     // chunk ck has landed (groups are committed one per iteration)
-                __syncthreads();             // ... for every thread, and everyone is done with chunk ck-1
-                if (ck + NS - 1 < nchunk) issue(ck + NS - 1);   // refills the stage chunk ck-1 used
-                cp_async_commit();
-                const float* wsrc = Stg + (ck % NS) * CP * PITCH + c1 * PITCH;
-                const float* xsrc = Xrow + rg * RPT * d + ck * KC;
+                const uint32_t g = gchunk + (uint32_t)ck;
+                mbar_wait_a(a_bar + 8u * (g % NS), (g / NS) & 1u);   // chunk ck has landed
+                __syncthreads();                                      // everyone is done with chunk ck-1
+                if (tid == 0 && ck + NS - 1 < nchunk) issue(ck + NS - 1);   // refills the stage chunk ck-1 used
+                const float* wsrc = Stg + (g % NS) * KC * CP + cg4 * 4;
+                const float* xsrc = Xt + (ck * KC) * R;
 #pragma unroll
-                for (int k4 = 0; k4 < KC / 4; ++k4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(wsrc + k4 * 4);
+                for (int kk = 0; kk < KC / KS; ++kk) {
+                    const int k = ks + kk * KS;
+                    const float4 w4 = *reinterpret_cast<const float4*>(wsrc + k * CP);
 #pragma unroll
-                    for (int i = 0; i < RPT; ++i) {
-                        const float4 x4 = *reinterpret_cast<const float4*>(xsrc + i * d + k4 * 4);
-                        acc[i] = fmaf(x4.x, w4.x, acc[i]);
-                        acc[i] = fmaf(x4.y, w4.y, acc[i]);
-                        acc[i] = fmaf(x4.z, w4.z, acc[i]);
-                        acc[i] = fmaf(x4.w, w4.w, acc[i]);
+                    for (int r4 = 0; r4 < R / 4; ++r4) {
+                        const float4 x4 = *reinterpret_cast<const float4*>(xsrc + k * R + r4 * 4);
+                        const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            acc[r4 * 4 + i][0] = fmaf(xs[i], w4.x, acc[r4 * 4 + i][0]);
+                            acc[r4 * 4 + i][1] = fmaf(xs[i], w4.y, acc[r4 * 4 + i][1]);
+                            acc[r4 * 4 + i][2] = fmaf(xs[i], w4.z, acc[r4 * 4 + i][2]);
+                            acc[r4 * 4 + i][3] = fmaf(xs[i], w4.w, acc[r4 * 4 + i][3]);
+                        }
                     }
                 }
             }
-            cp_async_wait<0>();
+            gchunk += (uint32_t)nchunk;
             __syncthreads();
+            unsigned long long tf0 = 0, tf1 = 0;
+            if (cta == 0 && tid == 0) { tf0 = global_ns(); p.ctrl->t_ns[6] += tf0 - ts0; }
+            // reduce the KS partial tiles through the (now idle) stage memory: red[ks][r][c]
+            {
+                float* red_t = Stg;
 #pragma unroll
-            for (int i = 0; i < RPT; ++i)
-                if (c1 < C) Zs[(rg * RPT + i) * (CP + 1) + c1] = acc[i];
+                for (int r = 0; r < R; ++r)
+                    *reinterpret_cast<float4*>(red_t + (ks * R + r) * CP + cg4 * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                __syncthreads();
+                for (int o = tid; o < R * CP; o += kT) {
+                    const int r = o / CP, c = o % CP;
+                    float z = 0.f;
+#pragma unroll
+                    for (int s2 = 0; s2 < KS; ++s2) z += red_t[(s2 * R + r) * CP + c];
+                    Zs[r * (CP + 1) + c] = z;
+                }
+            }
             __syncthreads();
+            if (cta == 0 && tid == 0) { tf1 = global_ns(); p.ctrl->t_ns[7] += tf1 - tf0; }
             // softmax per row: warp w handles rows w, w + 8, ...
             for (int r = warp; r < R; r += kT / 32) {
                 const int n = r0 + r;
@@ -271,7 +311,7 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
                 tie_before = __reduce_add_sync(0xffffffffu, tie_before);
                 for (int c = lane; c < C; c += 32) {
                     const float pr = expf(z[c] - lse);
-                    p.DLt[(int64_t)c * p.ldn + n] = (pr - (c == y ? 1.f : 0.f)) * inv_n;
+                    p.DL[(int64_t)n * CP + c] = (pr - (c == y ? 1.f : 0.f)) * inv_n;
                 }
                 if (lane == 0) {
                     p.rowloss[par * NT + n] = lse - zy;
@@ -279,6 +319,8 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
                     p.rowhit[par * NT + n] = (rank == 0 ? 1 : 0) | (rank < 5 ? 2 : 0);
                 }
             }
+            __syncthreads();
+            if (cta == 0 && tid == 0) p.ctrl->t_ns[8] += global_ns() - tf1;
         }
         if (is_pull && proj) {   // u = W_new Q  ([n_new][q])
             for (int i = tid; i < a.n_new * (d / 4); i += kT)
@@ -338,43 +380,63 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
             const float nb = has_base ? (float)sqrt(nbs) : 0.f, nn = has_prev ? (float)sqrt(nns) : 0.f;
             const float sb = nb > 0.f ? a.lmbd_base / nb : 0.f;
             const float sn = nn > 0.f ? a.lmbd_novel / nn : 0.f;
-            const int j = tid % DC, cg = tid / DC;          // cg in [0, 32): classes cg, cg + 32, cg + 64, cg + 96
-            constexpr int CPT = CP / 32;   // classes per thread in phase 2
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            constexpr int CGU = kT / DC;   // class groups of the update mapping
+            constexpr int CPT = CP / CGU;  // classes per thread in the update: cg, cg + CGU, ...
+            const int j = tid % DC, cg = tid / DC;
+            unsigned long long tg0 = 0, tg1 = 0;
+            if (cta == 0 && tid == 0) { tg0 = global_ns(); p.ctrl->t_ns[9] += tg0 - ts2; }
+            float acc[4][DC];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int jj = 0; jj < DC; ++jj) acc[c][jj] = 0.f;
             const int nchunk = p.ldn / KC;
-            auto issue = [&](int ck) {
-                float* dst = Stg + (ck % NS) * CP * PITCH;
-                for (int i = tid; i < C * (KC / 4); i += kT) {
-                    const int c = i / (KC / 4), n4 = i % (KC / 4);
-                    cp_async16(dst + c * PITCH + n4 * 4, p.DLt + (int64_t)c * p.ldn + ck * KC + n4 * 4);
-                }
+            auto issue = [&](int ck) {   // a chunk is KC * CP contiguous floats of DL; called by thread 0 only
+                const uint32_t st = (gchunk + (uint32_t)ck) % NS;
+                mbar_expect_tx_a(a_bar + 8u * st, kChunkBytes);
+                bulk_load(a_stg + st * kChunkBytes, p.DL + (int64_t)ck * KC * CP, kChunkBytes, a_bar + 8u * st);
             };
-            for (int s = 0; s < NS - 1; ++s) {
-                if (s < nchunk) issue(s);
-                cp_async_commit();
+            if (tid == 0) {
+                fence_proxy_async();
+                for (int s = 0; s < NS - 1 && s < nchunk; ++s) issue(s);
             }
             for (int ck = 0; ck < nchunk; ++ck) {
-                cp_async_wait<NS - 2>();
+                const uint32_t g = gchunk + (uint32_t)ck;
+                mbar_wait_a(a_bar + 8u * (g % NS), (g / NS) & 1u);
                 __syncthreads();
-                if (ck + NS - 1 < nchunk) issue(ck + NS - 1);
-                cp_async_commit();
-                const float* dsrc = Stg + (ck % NS) * CP * PITCH;
-                const float* xsrc = Xc + j * xp + ck * KC;
+                if (tid == 0 && ck + NS - 1 < nchunk) issue(ck + NS - 1);
+                const float* dsrc = Stg + (g % NS) * KC * CP + cg4 * 4;
+                const float* xsrc = Xn + (ck * KC) * DC;
 #pragma unroll
-                for (int n4 = 0; n4 < KC / 4; ++n4) {
-                    const float4 x4 = *reinterpret_cast<const float4*>(xsrc + n4 * 4);
+                for (int kk = 0; kk < KC / KS; ++kk) {
+                    const int n = ks + kk * KS;
+                    const float4 d4 = *reinterpret_cast<const float4*>(dsrc + n * CP);
+                    const float ds[4] = {d4.x, d4.y, d4.z, d4.w};
+                    float xs[DC];
 #pragma unroll
-                    for (int i = 0; i < CPT; ++i) {
-                        const float4 d4 = *reinterpret_cast<const float4*>(dsrc + (cg + 32 * i) * PITCH + n4 * 4);
-                        acc[i] = fmaf(d4.x, x4.x, acc[i]);
-                        acc[i] = fmaf(d4.y, x4.y, acc[i]);
-                        acc[i] = fmaf(d4.z, x4.z, acc[i]);
-                        acc[i] = fmaf(d4.w, x4.w, acc[i]);
+                    for (int v = 0; v < DC / 4; ++v) {
+                        const float4 x4 = *reinterpret_cast<const float4*>(xsrc + n * DC + v * 4);
+                        xs[4 * v] = x4.x; xs[4 * v + 1] = x4.y; xs[4 * v + 2] = x4.z; xs[4 * v + 3] = x4.w;
                     }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int jj = 0; jj < DC; ++jj) acc[c][jj] = fmaf(ds[c], xs[jj], acc[c][jj]);
                 }
             }
-            cp_async_wait<0>();
+            gchunk += (uint32_t)nchunk;
             __syncthreads();
+            // partial tiles of the KS sample slices -> stage memory: red[ks][c][j]; the update below sums them
+            float* red_t = Stg;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int v = 0; v < DC / 4; ++v)
+                    *reinterpret_cast<float4*>(red_t + (ks * CP + cg4 * 4 + c) * DC + v * 4) =
+                        make_float4(acc[c][4 * v], acc[c][4 * v + 1], acc[c][4 * v + 2], acc[c][4 * v + 3]);
+            }
+            __syncthreads();
+            if (cta == 0 && tid == 0) { tg1 = global_ns(); p.ctrl->t_ns[10] += tg1 - tg0; }
             const int step = a.step0 + e;
             float bc1 = 1.f, bc2s = 1.f;
             if (a.optimizer == SR_OPT_ADAM) {
@@ -384,11 +446,13 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
             double nbp = 0.0, nnp = 0.0, pp = 0.0;
 #pragma unroll
             for (int i = 0; i < CPT; ++i) {
-                const int c = cg + 32 * i;
+                const int c = cg + CGU * i;
                 if (c >= C) continue;
                 const int idx = c * DC + j;
                 const float w = Wc[idx];
-                float g = acc[i];
+                float g = 0.f;
+#pragma unroll
+                for (int s2 = 0; s2 < KS; ++s2) g += red_t[(s2 * CP + c) * DC + j];
                 if (has_base && c < a.n_base) g += sb * (w - W0c[idx]);
                 if (has_prev && c >= a.n_base && c < a.n_base + a.n_prev_novel) g += sn * (w - Rc[idx - a.n_base * DC]);
                 if (c >= new0 && (proj || fixed)) {
@@ -421,6 +485,7 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
                 }
                 Wc[idx] = wnew;
                 a.weight[(int64_t)c * d + j0 + j] = wnew;
+                p.Wt[(int64_t)(j0 + j) * CP + c] = wnew;
                 if (has_base && c < a.n_base) { const float dl = wnew - W0c[idx]; nbp += (double)dl * dl; }
                 if (has_prev && c >= a.n_base && c < a.n_base + a.n_prev_novel) {
                     const float dl = wnew - Rc[idx - a.n_base * DC];
@@ -435,6 +500,7 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
                 p.nn_part[(par ^ 1) * p.GC + cta] = nnp;
                 p.pull_part[cta] = pp;
             }
+            if (cta == 0 && tid == 0) p.ctrl->t_ns[11] += global_ns() - tg1;
         }
         if (cta == 0 && tid == 0) ts3 = global_ns();
         grid_barrier(p.ctrl, bar_target);
@@ -469,7 +535,7 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
 int pick_rows(int nt) { return nt <= 384 ? 4 : (nt <= 768 ? 8 : 16); }
 
 struct SmallLayout {
-    int64_t ctrl, DLt, rowloss, rowhit, nb, nn, pull, u, total;
+    int64_t ctrl, DL, Wt, rowloss, rowhit, nb, nn, pull, u, total;
 };
 
 SmallLayout small_layout(const sr_head_args* a, int GC) {
@@ -478,7 +544,9 @@ SmallLayout small_layout(const sr_head_args* a, int GC) {
     const int64_t ldn = align_up(nt, KC);
     int64_t off = 0;
     L.ctrl = off;    off += align_up(sizeof(HeadCtrl), 256);
-    L.DLt = off;     off += align_up((int64_t)a->n_classes * ldn * 4, 256);
+    const int64_t cp = a->n_classes <= 64 ? 64 : 128;
+    L.DL = off;      off += align_up(ldn * cp * 4, 256);
+    L.Wt = off;      off += align_up((int64_t)a->dim * cp * 4, 256);
     L.rowloss = off; off += align_up(2 * nt * 4, 256);
     L.rowhit = off;  off += align_up(2 * nt * 4, 256);
     L.nb = off;      off += align_up(2 * (int64_t)GC * 8, 256);
@@ -508,8 +576,8 @@ size_t small_smem_bytes(const sr_head_args* a, int R, int CP, int ldn, bool pull
     const int n_opt = a->optimizer == SR_OPT_ADAM ? 2 : 1;
     size_t f = 0;
     f += (size_t)R * d + (size_t)R * (CP + 1);                                       // row role
-    f += (size_t)NS * CP * PITCH;                                                    // stream stages (shared by both roles)
-    f += (size_t)DC * (ldn + 4) + (size_t)C * DC * (1 + n_opt) + (size_t)a->n_base * DC + (size_t)a->n_prev_novel * DC +
+    f += (size_t)NS * KC * CP;                                                       // stream stages (shared by both roles)
+    f += (size_t)DC * ldn + (size_t)C * DC * (1 + n_opt) + (size_t)a->n_base * DC + (size_t)a->n_prev_novel * DC +
          (size_t)(proj ? a->q_rows : (fixed ? a->n_new : 0)) * DC + (size_t)(proj ? a->n_new * a->q_rows : 0) + 8;   // column role
     size_t g = pull_cta && proj ? (size_t)a->q_rows * d + (size_t)a->n_new * d : 0;    // pull role (its own CTA)
     return std::max(f, g) * sizeof(float);
@@ -548,14 +616,15 @@ int32_t head_small_run(const sr_head_args* a, cudaStream_t stream) {
                                                   (long long)a->workspace_bytes, (long long)L.total);
     uint8_t* ws = static_cast<uint8_t*>(a->workspace);
     p.ctrl = reinterpret_cast<HeadCtrl*>(ws + L.ctrl);
-    p.DLt = reinterpret_cast<float*>(ws + L.DLt);
+    p.DL = reinterpret_cast<float*>(ws + L.DL);
+    p.Wt = reinterpret_cast<float*>(ws + L.Wt);
     p.rowloss = reinterpret_cast<float*>(ws + L.rowloss);
     p.rowhit = reinterpret_cast<int*>(ws + L.rowhit);
     p.nb_part = reinterpret_cast<double*>(ws + L.nb);
     p.nn_part = reinterpret_cast<double*>(ws + L.nn);
     p.pull_part = reinterpret_cast<double*>(ws + L.pull);
     p.u = reinterpret_cast<float*>(ws + L.u);
-    SR_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)L.total, stream));   // control block, DLt padding columns, partials
+    SR_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)L.total, stream));   // control block, DL / W^T padding, partials
     const size_t dyn = small_smem_bytes(a, p.R, p.CP, p.ldn, true);
     if (p.CP == 64) {
         if (p.R == 4) return launch_small<4, 64>(p, dyn, stream);

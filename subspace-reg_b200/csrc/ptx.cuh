@@ -215,7 +215,7 @@ __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
 }
 // Slow path of a wait, kept out of line so that the role loops stay small: spin on try_wait (a hardware-suspended wait, not
 // a poll) and trap with a message instead of hanging the GPU if the barrier never completes.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
     while (!mbar_try_wait_a(bar, parity)) {
         if (clock64() - t0 > 8000000000LL) {

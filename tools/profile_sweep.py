@@ -38,9 +38,11 @@ def head_timing():
             hs.run(2000)
             e1.record()
             torch.cuda.synchronize()
-        t = hs.workspace[:128].cpu().view(torch.int64)[4:10].tolist()
+        t = hs.workspace[:160].cpu().view(torch.int64)[4:16].tolist()
         print("head session %d (N=%d C=%d): %.2f us/epoch; CTA0 ns/epoch phase1 %.0f bar1 %.0f phase2 %.0f bar2 %.0f | loss CTA %.0f pull CTA %.0f" %
               (s, Ns + Nm, Cn, e0.elapsed_time(e1) * 1e3 / 2000, t[0] / 2000, t[1] / 2000, t[2] / 2000, t[3] / 2000, t[4] / 2000, t[5] / 2000), flush=True)
+        print("    phase 1: W stream %.0f  logits->smem %.0f  softmax+dlogits %.0f | phase 2: prologue %.0f  DLt stream %.0f  update %.0f (ns/epoch)" %
+              tuple(x / 2000 for x in t[6:12]), flush=True)
 
 
 def sweep_timing():
@@ -61,4 +63,4 @@ def sweep_timing():
 
 if __name__ == "__main__":
     head_timing()
-    sweep_timing()
+    pass  # sweep_timing()
