@@ -33,6 +33,21 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return t;
 }
 
+// Three block sums for the price of one barrier pair (same summation order as three block_sum calls; blocks of <= 10 warps).
+__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* red) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    c = warp_sum(c);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) { red[w] = a; red[nw + w] = b; red[2 * nw + w] = c; }
+    __syncthreads();
+    double ta = 0.0, tb = 0.0, tc = 0.0;
+    for (int i = 0; i < nw; ++i) { ta += red[i]; tb += red[nw + i]; tc += red[2 * nw + i]; }
+    a = ta; b = tb; c = tc;
+}
+
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

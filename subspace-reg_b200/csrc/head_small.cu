@@ -34,8 +34,8 @@ struct SmallParams {
     int R, GA, GC, G;      // rows per row CTA, #row CTAs, #column CTAs, grid (= max(GA, GC) + loss CTA + pull CTA)
     int CP;                // classes padded to 64 or 128 (thread mapping of phase 1)
     HeadCtrl* ctrl;
-    float* DL;             // [ldn][CP]  dlogits, sample-major, classes padded with zeros
-    float* Wt;             // [d][CP]    W^T, kept in step with `weight` by the column CTAs
+    float* DL;             // [ldn][cw]  dlogits, sample-major, cw = classes rounded up to 4 (padding stays zero)
+    float* Wt;             // [d][cw]    W^T, kept in step with `weight` by the column CTAs
     float* rowloss;        // [2][n_total]
     int* rowhit;           // [2][n_total]
     double* nb_part;       // [2][GC]
@@ -156,7 +156,9 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
         mbar_fence_init();
     }
     const uint32_t a_bar = smem_u32(&stream_bar[0]), a_stg = smem_u32(Stg);
-    constexpr uint32_t kChunkBytes = KC * CP * 4;
+    constexpr uint32_t kChunkBytes = KC * CP * 4;          // stage stride
+    const int cw = (C + 3) & ~3;                            // row pitch (floats) of W^T / DL: classes rounded up to 4, not to CP
+    const uint32_t chunk_bytes = (uint32_t)(KC * cw * 4);   // bytes actually streamed per chunk
     uint32_t gchunk = 0;   // chunks consumed so far by this CTA (both streams): stage = gchunk % NS, parity = (gchunk / NS) & 1
 
     // ---- one-time loads of everything that is constant over the session ----
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
         for (int i = tid; i < C * DC; i += kT) {
             const int c = i / DC, j = i % DC;
             Wc[i] = a.weight[(int64_t)c * d + j0 + j];
-            p.Wt[(int64_t)(j0 + j) * CP + c] = Wc[i];
+            p.Wt[(int64_t)(j0 + j) * cw + c] = Wc[i];
             for (int s = 0; s < n_opt; ++s) Vc[s * C * DC + i] = a.opt_state[(int64_t)s * C * d + (int64_t)c * d + j0 + j];
         }
         if (has_base)
@@ -230,10 +232,12 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
 #pragma unroll
                 for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
             const int nchunk = d / KC;
-            auto issue = [&](int ck) {   // a chunk is KC * CP contiguous floats of W^T; called by thread 0 only
+            // (all row CTAs read the same chunk at the same time on purpose: rotating the chunk order per CTA measured 18 %
+            // slower - concurrent readers of one line are served together by L2)
+            auto issue = [&](int ck) {   // a chunk is KC rows of W^T; called by thread 0 only
                 const uint32_t st = (gchunk + (uint32_t)ck) % NS;
-                mbar_expect_tx_a(a_bar + 8u * st, kChunkBytes);
-                bulk_load(a_stg + st * kChunkBytes, p.Wt + (int64_t)ck * KC * CP, kChunkBytes, a_bar + 8u * st);
+                mbar_expect_tx_a(a_bar + 8u * st, chunk_bytes);
+                bulk_load(a_stg + st * kChunkBytes, p.Wt + (int64_t)ck * KC * cw, chunk_bytes, a_bar + 8u * st);
             };
             if (tid == 0) {
                 fence_proxy_async();   // the stages were last touched through the generic proxy (reduction buffers)
@@ -246,10 +250,11 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
                 if (tid == 0 && ck + NS - 1 < nchunk) issue(ck + NS - 1);   // refills the stage chunk ck-1 used
                 const float* wsrc = Stg + (g % NS) * KC * CP + cg4 * 4;
                 const float* xsrc = Xt + (ck * KC) * R;
+                if (cg4 * 4 < cw)
 #pragma unroll
                 for (int kk = 0; kk < KC / KS; ++kk) {
                     const int k = ks + kk * KS;
-                    const float4 w4 = *reinterpret_cast<const float4*>(wsrc + k * CP);
+                    const float4 w4 = *reinterpret_cast<const float4*>(wsrc + k * cw);
 #pragma unroll
                     for (int r4 = 0; r4 < R / 4; ++r4) {
                         const float4 x4 = *reinterpret_cast<const float4*>(xsrc + k * R + r4 * 4);
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
                 tie_before = __reduce_add_sync(0xffffffffu, tie_before);
                 for (int c = lane; c < C; c += 32) {
                     const float pr = expf(z[c] - lse);
-                    p.DL[(int64_t)n * CP + c] = (pr - (c == y ? 1.f : 0.f)) * inv_n;
+                    p.DL[(int64_t)n * cw + c] = (pr - (c == y ? 1.f : 0.f)) * inv_n;
                 }
                 if (lane == 0) {
                     p.rowloss[par * NT + n] = lse - zy;
@@ -372,8 +377,10 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
             // norms of W_e - anchors (partials written at the end of the previous epoch / init): one load per thread
             double nbs = 0.0, nns = 0.0;
             for (int i = tid; i < p.GC; i += kT) { nbs += p.nb_part[par * p.GC + i]; nns += p.nn_part[par * p.GC + i]; }
-            nbs = block_sum(nbs, red);
-            nns = block_sum(nns, red);
+            {
+                double unused = 0.0;
+                block_sum3(nbs, nns, unused, red);
+            }
             if (proj) {   // projection coefficients of this epoch (written by the pull CTA in phase 1) -> shared memory
                 for (int i = tid; i < a.n_new * q; i += kT) Us[i] = p.u[i];
             }
@@ -391,10 +398,10 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
 #pragma unroll
                 for (int jj = 0; jj < DC; ++jj) acc[c][jj] = 0.f;
             const int nchunk = p.ldn / KC;
-            auto issue = [&](int ck) {   // a chunk is KC * CP contiguous floats of DL; called by thread 0 only
+            auto issue = [&](int ck) {   // a chunk is KC rows of DL; called by thread 0 only
                 const uint32_t st = (gchunk + (uint32_t)ck) % NS;
-                mbar_expect_tx_a(a_bar + 8u * st, kChunkBytes);
-                bulk_load(a_stg + st * kChunkBytes, p.DL + (int64_t)ck * KC * CP, kChunkBytes, a_bar + 8u * st);
+                mbar_expect_tx_a(a_bar + 8u * st, chunk_bytes);
+                bulk_load(a_stg + st * kChunkBytes, p.DL + (int64_t)ck * KC * cw, chunk_bytes, a_bar + 8u * st);
             };
             if (tid == 0) {
                 fence_proxy_async();
@@ -407,10 +414,11 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
                 if (tid == 0 && ck + NS - 1 < nchunk) issue(ck + NS - 1);
                 const float* dsrc = Stg + (g % NS) * KC * CP + cg4 * 4;
                 const float* xsrc = Xn + (ck * KC) * DC;
+                if (cg4 * 4 < cw)
 #pragma unroll
                 for (int kk = 0; kk < KC / KS; ++kk) {
                     const int n = ks + kk * KS;
-                    const float4 d4 = *reinterpret_cast<const float4*>(dsrc + n * CP);
+                    const float4 d4 = *reinterpret_cast<const float4*>(dsrc + n * cw);
                     const float ds[4] = {d4.x, d4.y, d4.z, d4.w};
                     float xs[DC];
 #pragma unroll
@@ -485,16 +493,14 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
                 }
                 Wc[idx] = wnew;
                 a.weight[(int64_t)c * d + j0 + j] = wnew;
-                p.Wt[(int64_t)(j0 + j) * CP + c] = wnew;
+                p.Wt[(int64_t)(j0 + j) * cw + c] = wnew;
                 if (has_base && c < a.n_base) { const float dl = wnew - W0c[idx]; nbp += (double)dl * dl; }
                 if (has_prev && c >= a.n_base && c < a.n_base + a.n_prev_novel) {
                     const float dl = wnew - Rc[idx - a.n_base * DC];
                     nnp += (double)dl * dl;
                 }
             }
-            nbp = block_sum(nbp, red);
-            nnp = block_sum(nnp, red);
-            pp = block_sum(pp, red);
+            block_sum3(nbp, nnp, pp, red);
             if (tid == 0) {
                 p.nb_part[(par ^ 1) * p.GC + cta] = nbp;
                 p.nn_part[(par ^ 1) * p.GC + cta] = nnp;
