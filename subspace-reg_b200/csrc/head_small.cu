@@ -26,16 +26,15 @@ using namespace srb;
 constexpr int kT = 256;
 constexpr int DC = 8;     // feature columns per column CTA (16 measured slower: the update and the tile arithmetic double)
 constexpr int KC = 64;    // k-chunk of the W^T stream (phase 1) / n-chunk of the DL stream (phase 2): KC rows of CP floats
-constexpr int NSMAX = 4;  // most stages of the W^T / DL stream ring (one region, the two phases never overlap in a CTA);
-                          // measured: 6-8 stages are 10 % SLOWER than 4 (the streams are bound by how fast L2 serves the same
-                          // lines to ~90 SMs, not by the bytes in flight)
+constexpr int NS = 4;     // stages of the W^T / DL stream ring (one region, the two phases never overlap in a CTA).  Measured on
+                          // B200: a runtime depth of 6-8 stages, 128-row chunks, 512 threads per CTA, 16 columns per column CTA,
+                          // a per-CTA rotation of the chunk order and cluster-multicast copies are all 5-20 % slower than this.
 
 struct SmallParams {
     sr_head_args a;
     int n_total, ldn;      // ldn: row pitch of DLt (n_total rounded up to 32)
     int R, GA, GC, G;      // rows per row CTA, #row CTAs, #column CTAs, grid (= max(GA, GC) + loss CTA + pull CTA)
     int CP;                // classes padded to 64 or 128 (thread mapping of phase 1)
-    int ns;                // stream ring depth (2..NSMAX)
     HeadCtrl* ctrl;
     float* DL;             // [ldn][cw]  dlogits, sample-major, cw = classes rounded up to 4 (padding stays zero)
     float* Wt;             // [d][cw]    W^T, kept in step with `weight` by the column CTAs
@@ -149,19 +148,19 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
     float* Rc = sp;              sp += (is_col && has_prev) ? a.n_prev_novel * DC : 0;
     float* Pc = sp;              sp += (is_col && (proj || fixed)) ? (proj ? q : a.n_new) * DC : 0;  // Q^T or puller columns
     float* Us = sp;              sp += (is_col && proj) ? ((a.n_new * q + 3) & ~3) : 0;      // [n_new][q] projection coefficients
-    float* Stg = sp;             sp += (is_row || is_col) ? p.ns * KC * ((C + 3) & ~3) : 0;   // ns x [KC][cw] stream stages (>= the reduction buffers)
+    float* Stg = sp;             sp += (is_row || is_col) ? NS * KC * CP : 0;      // NS x [KC][CP] stream stages
     float* Qs = sp;              sp += (is_pull && proj) ? q * d : 0;      // [q][d]
     float* wn = sp;              sp += (is_pull && proj) ? a.n_new * d : 0;
 
-    __shared__ uint64_t stream_bar[NSMAX];   // "chunk landed" barriers of the W^T / DL stream ring
+    __shared__ uint64_t stream_bar[NS];   // "chunk landed" barriers of the W^T / DL stream ring
     if (tid == 0) {
-        for (int i = 0; i < NSMAX; ++i) mbar_init(&stream_bar[i], 1);
+        for (int i = 0; i < NS; ++i) mbar_init(&stream_bar[i], 1);
         mbar_fence_init();
     }
     const uint32_t a_bar = smem_u32(&stream_bar[0]), a_stg = smem_u32(Stg);
+    constexpr uint32_t kChunkBytes = KC * CP * 4;          // stage stride
     const int cw = (C + 3) & ~3;                            // row pitch (floats) of W^T / DL: classes rounded up to 4, not to CP
-    const uint32_t chunk_bytes = (uint32_t)(KC * cw * 4);   // bytes per chunk = stage stride
-    const uint32_t NS = (uint32_t)p.ns;
+    const uint32_t chunk_bytes = (uint32_t)(KC * cw * 4);   // bytes actually streamed per chunk
     uint32_t gchunk = 0;   // chunks consumed so far by this CTA (both streams): stage = gchunk % NS, parity = (gchunk / NS) & 1
 
     // ---- one-time loads of everything that is constant over the session ----
@@ -240,18 +239,18 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
             auto issue = [&](int ck) {   // a chunk is KC rows of W^T; called by thread 0 only
                 const uint32_t st = (gchunk + (uint32_t)ck) % NS;
                 mbar_expect_tx_a(a_bar + 8u * st, chunk_bytes);
-                bulk_load(a_stg + st * chunk_bytes, p.Wt + (int64_t)ck * KC * cw, chunk_bytes, a_bar + 8u * st);
+                bulk_load(a_stg + st * kChunkBytes, p.Wt + (int64_t)ck * KC * cw, chunk_bytes, a_bar + 8u * st);
             };
             if (tid == 0) {
                 fence_proxy_async();   // the stages were last touched through the generic proxy (reduction buffers)
-                for (int s = 0; s < (int)NS - 1 && s < nchunk; ++s) issue(s);
+                for (int s = 0; s < NS - 1 && s < nchunk; ++s) issue(s);
             }
             for (int ck = 0; ck < nchunk; ++ck) {
                 const uint32_t g = gchunk + (uint32_t)ck;
                 mbar_wait_a(a_bar + 8u * (g % NS), (g / NS) & 1u);   // chunk ck has landed
                 __syncthreads();                                      // everyone is done with chunk ck-1
-                if (tid == 0 && ck + (int)NS - 1 < nchunk) issue(ck + (int)NS - 1);   // refills the stage chunk ck-1 used
-                const float* wsrc = Stg + (g % NS) * KC * cw + cg4 * 4;
+                if (tid == 0 && ck + NS - 1 < nchunk) issue(ck + NS - 1);   // refills the stage chunk ck-1 used
+                const float* wsrc = Stg + (g % NS) * KC * CP + cg4 * 4;
                 const float* xsrc = Xt + (ck * KC) * R;
                 if (cg4 * 4 < cw)
 #pragma unroll
@@ -404,18 +403,18 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
             auto issue = [&](int ck) {   // a chunk is KC rows of DL; called by thread 0 only
                 const uint32_t st = (gchunk + (uint32_t)ck) % NS;
                 mbar_expect_tx_a(a_bar + 8u * st, chunk_bytes);
-                bulk_load(a_stg + st * chunk_bytes, p.DL + (int64_t)ck * KC * cw, chunk_bytes, a_bar + 8u * st);
+                bulk_load(a_stg + st * kChunkBytes, p.DL + (int64_t)ck * KC * cw, chunk_bytes, a_bar + 8u * st);
             };
             if (tid == 0) {
                 fence_proxy_async();
-                for (int s = 0; s < (int)NS - 1 && s < nchunk; ++s) issue(s);
+                for (int s = 0; s < NS - 1 && s < nchunk; ++s) issue(s);
             }
             for (int ck = 0; ck < nchunk; ++ck) {
                 const uint32_t g = gchunk + (uint32_t)ck;
                 mbar_wait_a(a_bar + 8u * (g % NS), (g / NS) & 1u);
                 __syncthreads();
-                if (tid == 0 && ck + (int)NS - 1 < nchunk) issue(ck + (int)NS - 1);
-                const float* dsrc = Stg + (g % NS) * KC * cw + cg4 * 4;
+                if (tid == 0 && ck + NS - 1 < nchunk) issue(ck + NS - 1);
+                const float* dsrc = Stg + (g % NS) * KC * CP + cg4 * 4;
                 const float* xsrc = Xn + (ck * KC) * DC;
                 if (cg4 * 4 < cw)
 #pragma unroll
@@ -578,34 +577,16 @@ int32_t launch_small(const SmallParams& p, size_t dyn, cudaStream_t stream) {
     return SR_OK;
 }
 
-// Shared memory of the roles without / with the stream ring.  The ring gets every stage that fits (at least enough to hold
-// the cross-warp reduction buffers that alias it).
-size_t small_fixed_floats(const sr_head_args* a, int R, int CP, int ldn) {
+size_t small_smem_bytes(const sr_head_args* a, int R, int CP, int ldn, bool pull_cta) {
     const int C = a->n_classes, d = a->dim;
     const bool proj = a->pull_mode == SR_PULL_PROJECT && a->q_rows < d;
     const bool fixed = a->pull_mode == SR_PULL_FIXED;
     const int n_opt = a->optimizer == SR_OPT_ADAM ? 2 : 1;
     size_t f = 0;
     f += (size_t)R * d + (size_t)R * (CP + 1);                                       // row role
+    f += (size_t)NS * KC * CP;                                                       // stream stages (shared by both roles)
     f += (size_t)DC * ldn + (size_t)C * DC * (1 + n_opt) + (size_t)a->n_base * DC + (size_t)a->n_prev_novel * DC +
          (size_t)(proj ? a->q_rows : (fixed ? a->n_new : 0)) * DC + (size_t)(proj ? a->n_new * a->q_rows : 0) + 8;   // column role
-    return f;
-}
-int small_ring_depth(const sr_head_args* a, int R, int CP, int ldn) {
-    const size_t budget = 200 * 1024 / sizeof(float);
-    const size_t fixed = small_fixed_floats(a, R, CP, ldn);
-    const size_t stride = (size_t)KC * ((a->n_classes + 3) & ~3);
-    const size_t red = (size_t)(kT / (CP / 4)) * CP * std::max(R, DC);   // KS x CP x max(R, DC) partial tiles
-    if (fixed + std::max(2 * stride, red) > budget) return 0;
-    int ns = (int)std::min<size_t>(NSMAX, (budget - fixed) / stride);
-    while ((size_t)ns * stride < red) ++ns;   // tiny class counts: the reduction buffers need the room
-    return ns <= NSMAX ? ns : 0;
-}
-size_t small_smem_bytes(const sr_head_args* a, int R, int CP, int ldn, bool pull_cta) {
-    const int d = a->dim;
-    const bool proj = a->pull_mode == SR_PULL_PROJECT && a->q_rows < d;
-    const int ns = small_ring_depth(a, R, CP, ldn);
-    size_t f = small_fixed_floats(a, R, CP, ldn) + (size_t)ns * KC * ((a->n_classes + 3) & ~3);
     size_t g = pull_cta && proj ? (size_t)a->q_rows * d + (size_t)a->n_new * d : 0;    // pull role (its own CTA)
     return std::max(f, g) * sizeof(float);
 }
@@ -623,7 +604,7 @@ bool head_small_applicable(const sr_head_args* a) {
     const int CP = a->n_classes <= 64 ? 64 : 128;
     const int ldn = (int)align_up(nt, KC);
     if ((nt + R - 1) / R > 146) return false;
-    return small_ring_depth(a, R, CP, ldn) >= 2 && small_smem_bytes(a, R, CP, ldn, true) <= 200 * 1024;
+    return small_smem_bytes(a, R, CP, ldn, true) <= 200 * 1024;
 }
 
 int64_t head_small_workspace_bytes(const sr_head_args* a) { return small_layout(a, a->dim / DC).total; }
@@ -638,7 +619,6 @@ int32_t head_small_run(const sr_head_args* a, cudaStream_t stream) {
     p.GC = a->dim / DC;
     p.G = std::max(p.GA, p.GC) + 2;   // + one CTA for the loss / stopping rule, one for the projection coefficients
     p.CP = a->n_classes <= 64 ? 64 : 128;
-    p.ns = small_ring_depth(a, p.R, p.CP, p.ldn);
     const SmallLayout L = small_layout(a, p.GC);
     if (a->workspace_bytes < L.total) return fail(SR_E_SMALLWS, "sr_head_run: workspace %lld < %lld",
                                                   (long long)a->workspace_bytes, (long long)L.total);

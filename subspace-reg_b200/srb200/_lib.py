@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsrb200.so")
+LIB_PATH = os.environ.get("SRB200_LIB", os.path.join(_HERE, "libsrb200.so"))   # override: A/B timing of library builds
 
 SR_EPI_ACT, SR_EPI_ACT_POOL2, SR_EPI_ACT_AVG, SR_EPI_RAW_STATS = 0, 1, 2, 3
 SR_PULL_NONE, SR_PULL_FIXED, SR_PULL_PROJECT = 0, 1, 2
