@@ -54,6 +54,17 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// Loads that stay where they are written (issued before the stream loop, consumed after it: the L2 latency hides behind it).
+__device__ __forceinline__ double ldg_early_f64(const double* p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];\n" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ldg_early_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];\n" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -376,19 +387,15 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
 
         // ======================= phase 2 =======================
         if (is_col) {
-            // norms of W_e - anchors (partials written at the end of the previous epoch / init): one load per thread
+            // norms of W_e - anchors (partials written at the end of the previous epoch / init) and the projection
+            // coefficients of this epoch (written by the pull CTA in phase 1): loaded NOW into registers, reduced / staged
+            // after the stream loop, so that their L2 latency and the block sum are off the path to the first chunk
             double nbs = 0.0, nns = 0.0;
-            for (int i = tid; i < p.GC; i += kT) { nbs += p.nb_part[par * p.GC + i]; nns += p.nn_part[par * p.GC + i]; }
-            {
-                double unused = 0.0;
-                block_sum3(nbs, nns, unused, red);
-            }
-            if (proj) {   // projection coefficients of this epoch (written by the pull CTA in phase 1) -> shared memory
-                for (int i = tid; i < a.n_new * q; i += kT) Us[i] = p.u[i];
-            }
-            const float nb = has_base ? (float)sqrt(nbs) : 0.f, nn = has_prev ? (float)sqrt(nns) : 0.f;
-            const float sb = nb > 0.f ? a.lmbd_base / nb : 0.f;
-            const float sn = nn > 0.f ? a.lmbd_novel / nn : 0.f;
+            if (tid < p.GC) { nbs = ldg_early_f64(p.nb_part + par * p.GC + tid); nns = ldg_early_f64(p.nn_part + par * p.GC + tid); }
+            const int n_u = proj ? a.n_new * q : 0;
+            float u_early[2] = {0.f, 0.f};
+            if (tid < n_u) u_early[0] = ldg_early_f32(p.u + tid);
+            if (tid + kT < n_u) u_early[1] = ldg_early_f32(p.u + tid + kT);
             constexpr int CGU = kT / DC;   // class groups of the update mapping
             constexpr int CPT = CP / CGU;  // classes per thread in the update: cg, cg + CGU, ...
             const int j = tid % DC, cg = tid / DC;
@@ -447,6 +454,16 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
             }
             __syncthreads();
             if (cta == 0 && tid == 0) { tg1 = global_ns(); p.ctrl->t_ns[10] += tg1 - tg0; }
+            if (tid < n_u) Us[tid] = u_early[0];
+            if (tid + kT < n_u) Us[tid + kT] = u_early[1];
+            for (int i = tid + 2 * kT; i < n_u; i += kT) Us[i] = p.u[i];
+            {
+                double unused = 0.0;
+                block_sum3(nbs, nns, unused, red);   // (its barriers also publish Us)
+            }
+            const float nb = has_base ? (float)sqrt(nbs) : 0.f, nn = has_prev ? (float)sqrt(nns) : 0.f;
+            const float sb = nb > 0.f ? a.lmbd_base / nb : 0.f;
+            const float sn = nn > 0.f ? a.lmbd_novel / nn : 0.f;
             const int step = a.step0 + e;
             float bc1 = 1.f, bc2s = 1.f;
             if (a.optimizer == SR_OPT_ADAM) {
@@ -468,10 +485,18 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
                 if (c >= new0 && (proj || fixed)) {
                     float r;
                     if (proj) {
-                        float pw = 0.f;
+                        // four independent partial sums: one dependent chain of q FMAs sat on the epoch's critical path
+                        float pw0 = 0.f, pw1 = 0.f, pw2 = 0.f, pw3 = 0.f;
                         const float* ui = Us + (c - new0) * q;
-                        for (int jq = 0; jq < q; ++jq) pw = fmaf(ui[jq], Pc[jq * DC + j], pw);
-                        r = pw - w;
+                        int jq = 0;
+                        for (; jq + 4 <= q; jq += 4) {
+                            pw0 = fmaf(ui[jq], Pc[jq * DC + j], pw0);
+                            pw1 = fmaf(ui[jq + 1], Pc[(jq + 1) * DC + j], pw1);
+                            pw2 = fmaf(ui[jq + 2], Pc[(jq + 2) * DC + j], pw2);
+                            pw3 = fmaf(ui[jq + 3], Pc[(jq + 3) * DC + j], pw3);
+                        }
+                        for (; jq < q; ++jq) pw0 = fmaf(ui[jq], Pc[jq * DC + j], pw0);
+                        r = ((pw0 + pw1) + (pw2 + pw3)) - w;
                     } else {
                         r = Pc[(c - new0) * DC + j] - w;
                     }
