@@ -18,6 +18,7 @@ DROP_RATE = 0.1
 
 
 _PINNED_POOL = {}
+_SCRATCH_POOL = {}
 
 
 def _pad16(c):
@@ -159,6 +160,17 @@ class BackboneEngine(object):
     def mask_prefetch_alive(self):
         return self._prefetch is not None and self._prefetch.alive()
 
+    def _scratch(self, key, shape):
+        """Reusable pageable uint8 host buffer (process-wide pool, power-of-two capacity)."""
+        n = 1
+        for d in shape:
+            n *= int(d)
+        flat = _SCRATCH_POOL.get(key)
+        if flat is None or flat.numel() < n:
+            flat = torch.empty(1 << max(int(n - 1).bit_length(), 12), dtype=torch.uint8)
+            _SCRATCH_POOL[key] = flat
+        return flat[:n].view(shape)
+
     def _pinned(self, key, shape, sync=True):
         """Reusable pinned staging buffer (uint8) + the event of its last H2D copy."""
         n = 1
@@ -195,7 +207,8 @@ class BackboneEngine(object):
             keep_rate = max(1.0 - DROP_RATE / (20 * 2000) * nbt, 1.0 - DROP_RATE)
             gamma = (1 - keep_rate) / bs ** 2 * size ** 2 / (size - bs + 1) ** 2
             seed_shape = (batch, b['cout'], size - (bs - 1), size - (bs - 1))
-            seeds, n_seed = host_rng.bernoulli_u8(seed_shape, gamma, 1)        # Bernoulli(gamma).sample(...)
+            seed_buf = self._scratch(('seed', bi), seed_shape)                 # reused: a fresh tensor page-faults every time
+            seeds, n_seed = host_rng.bernoulli_u8(seed_shape, gamma, 1, out=seed_buf)   # Bernoulli(gamma).sample(...)
             # alternate staging buffers: the second forward of a session must not wait for the H2D copy of the first
             ent = self._pinned(('m', bi, self._cur_fwd & 1), shape)
             kept = host_rng.dropblock_keep(seeds, bs, ent[0])                  # _compute_block_mask, 1 - mask, .sum()

@@ -63,4 +63,4 @@ def sweep_timing():
 
 if __name__ == "__main__":
     head_timing()
-    pass  # sweep_timing()
+    sweep_timing()
