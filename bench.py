@@ -89,7 +89,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "250"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("SRB_BENCH_SMI_MS", "250")], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -133,6 +133,7 @@ def prepare(world):
     from srb200 import synthetic
     opt = world.opt
     opt.n_sessions_override = len(world.meta_valloader.batches)
+    opt.light_record = True   # no per-session parity snapshots (W / BN / probe features clones): test-only bookkeeping
     net = synthetic.init_model(create_model, opt, world.seed)
     ckpt = synthetic.make_ckpt(net, world)
     return world, net.cuda(), ckpt
@@ -271,8 +272,11 @@ def main():
     timed_seeds = [1 + rank + world_size * k for k in range(args.steps)]
 
     # ---- warm-up (HBM-resident arm), untimed ----
+    # (all warm-up worlds resident at once, like the timed ones: the caching allocator then reaches the timed region's
+    # footprint before the clock starts - cudaMalloc inside a sweep cost up to 25 % of a step)
+    warm = [prepare(place_world(w, 'gpu')) for w in warm]
     for w in warm:
-        run_sweep(prepare(place_world(w, 'gpu')))
+        run_sweep(w)
     del warm
 
     # ---- value: inputs already resident in HBM ----

@@ -17,6 +17,7 @@ from __future__ import print_function
 
 import copy
 import itertools
+import sys
 import time
 
 import numpy as np
@@ -261,11 +262,19 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         torch.cuda.synchronize()
         tm['train_s'] += time.perf_counter() - t_train0
         tm['steps'] += head.epochs
-        for e in range(10, head.epochs + 1, 10):
-            if use_pull:
-                print("PULL: ", float(trace[e - 1, 5]))
-            print('Novel Epoch {:4d}\tTrain Loss {:10.4f}\tAcc@1 {:10.3f}\tAcc@5 {:10.3f}'.format(
-                e, float(trace[e - 1, 0]), percent(trace[e - 1, 6], n_sup)[0], percent(trace[e - 1, 7], n_sup)[0]))
+        # the reference's every-10th-epoch log lines, formatted in one go (fp32 percentages like `percent`)
+        es = np.arange(10, head.epochs + 1, 10)
+        if es.size:
+            to_pct = np.float32(100.0 / n_sup)
+            acc1 = trace[es - 1, 6].astype(np.float32) * to_pct
+            acc5 = trace[es - 1, 7].astype(np.float32) * to_pct
+            lines = []
+            for k, e in enumerate(es):
+                if use_pull:
+                    lines.append("PULL:  %s\n" % float(trace[e - 1, 5]))
+                lines.append('Novel Epoch {:4d}\tTrain Loss {:10.4f}\tAcc@1 {:10.3f}\tAcc@5 {:10.3f}\n'.format(
+                    int(e), float(trace[e - 1, 0]), acc1[k], acc5[k]))
+            sys.stdout.write("".join(lines))
 
         # ---- the reference's forward-call count, for DropBlock's schedule ----
         n_calls = head.epochs * (1 + (1 if has_mem else 0) + len(novel_query_collection)) + 1
@@ -315,13 +324,16 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         print(f"***Running weighted avg: {weighted_avg}")
         log_episode(novel_labels, vocab_novel, epoch, test_acc, acc_base_, acc_base.avg, acc_novel.avg)
 
-        record['sessions'].append(dict(
-            epochs=head.epochs, terms=trace.astype(np.float64), W=net.classifier.weight.detach().clone(),
+        sess = dict(
+            epochs=head.epochs, terms=trace.astype(np.float64),
             novel_session_acc=novel_session_acc, query_pred=[torch.from_numpy(p) for p in query_ys_pred],
             query_logits=query_logits, base_pred=torch.from_numpy(base_pred), acc_base=float(acc_base_),
-            memory_inds=inds.copy() if opt.memory_replay else None, vocab_novel=list(vocab_novel),
-            probe_feat=cache[:8].clone(), train_feat=f_train[:8].clone(),
-            bn={k: v.detach().clone() for k, v in net.state_dict().items() if 'running_' in k or 'num_batches_tracked' in k}))
+            memory_inds=inds.copy() if opt.memory_replay else None, vocab_novel=list(vocab_novel))
+        if not getattr(opt, 'light_record', False):   # snapshots for the parity tests (~100 small device copies per session)
+            sess.update(W=net.classifier.weight.detach().clone(), probe_feat=cache[:8].clone(), train_feat=f_train[:8].clone(),
+                        bn={k: v.detach().clone() for k, v in net.state_dict().items()
+                            if 'running_' in k or 'num_batches_tracked' in k})
+        record['sessions'].append(sess)
 
     record.update(weighted=weighted_avg_l, novel=acc_novel_list, base=acc_base_list, acc_novel_avg=acc_novel.avg,
                   acc_base_avg=acc_base.avg, counters=net.block_counters())

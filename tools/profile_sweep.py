@@ -47,7 +47,7 @@ def head_timing():
 
 def sweep_timing():
     wdir = bench.word_embed_dir()
-    for it in range(2):
+    for it in range(int(os.environ.get('SWEEPS', '2'))):
         t0 = time.perf_counter()
         world = synthetic.make_world(10 + it, n_sessions=8, n_base_batch=1000, word_embed_path=wdir)
         t1 = time.perf_counter()
