@@ -176,6 +176,20 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         if base_support_loader is not None:
             support_ys_id = torch.cat([support_ys_id, torch.from_numpy(base_support_ys)])
 
+        if (idx == 0 and not net.engine().mask_prefetch_alive()
+                and getattr(opt, 'attraction_override', None) != "mapping_linear_label2image"):
+            # Start drawing the dropout masks of the WHOLE run on the host thread right away: from here on the CPU
+            # generator is only consumed by each session's nn.Linear(640, n_ways) init and by the masks themselves (a
+            # wrong guess is detected when a mask is taken and costs nothing but the prefetch).  Session 1's own masks
+            # then overlap its set-up and the first convolutions instead of being drawn in line.
+            skip = opt.n_ways * W_cols
+            fwds = [(skip, support_xs.shape[0])]
+            for j in range(1, iter_num):
+                fwds.append((skip, support_xs.shape[0]))
+                if opt.memory_replay == 1:
+                    fwds.append((0, 25 * j))
+            net.engine().start_mask_prefetch(fwds)
+
         net.train()
         net.augment_base_classifier_(len(novel_labels))
 
