@@ -14,7 +14,14 @@ _checked_devices = set()
 LAUNCHES = [0]   # number of srb200 kernels enqueued through this module (bench.py's gpu_launches)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    # the raw handle of torch's current stream (the private accessor skips building a Stream object: this runs ~100
+    # times per train-mode forward, which is host-bound)
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
