@@ -92,6 +92,13 @@ typedef struct sr_conv_args {
 
 int32_t sr_conv(const sr_conv_args* a, void* stream);
 
+/* Host-only (no device work, pointers in `a` are not dereferenced): the launch plan sr_conv would use for these shapes -
+ * out16 = { TW, TH, TN, row_stacked, tiles_w, tiles_h, n_cta, n_splits, tmem_stages, tap_reuse(panel 0),
+ *           row_bytes(panel 0), ring_stages, stage_bytes, dynamic_smem_bytes, channel_blocks(panel 0), last_ksteps(panel 0) }.
+ * There is no reference counterpart (cuDNN chooses its own algorithms behind nn.Conv2d, resnet_language.py:268-301);
+ * it exists so that tests can pin the tile / pipeline choice per layer shape. */
+int32_t sr_conv_plan(const sr_conv_args* a, int32_t* out16);
+
 /* ------------------------------------------------------------------------------------------------
  * Backbone: train-mode BatchNorm (epoch 1 of every session, language_eval.py:211,252,257)
  * ---------------------------------------------------------------------------------------------- */

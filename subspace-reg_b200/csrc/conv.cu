@@ -681,19 +681,19 @@ bool pick_tile(int H, int W, int epi, Tile* out) {
 // there is multiplied by zero); 64-byte rows halve the bytes per L2 request and measured 25 % vs 43 % tensor-active.
 int kc_bytes_for(int cin_pad) { return cin_pad >= 64 ? 128 : (cin_pad >= 32 ? 64 : 32); }
 
-}  // namespace
+// Everything sr_conv decides on the host before it touches the device: channel split, tile geometry, tap reuse, row width,
+// ring depth.  `max_dyn` = dynamic shared memory available to the kernel.  Shared by sr_conv and sr_conv_plan.
+struct ConvPlan {
+    ConvParams p;
+    Tile tile;
+    int staging, shift_bytes, dyn_smem;
+};
 
-extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+int32_t plan_conv(const sr_conv_args* a, int max_dyn, ConvPlan* plan) {
     if (!a) return fail(SR_E_ARG, "sr_conv: null args");
     if (a->n_panels < 1 || a->n_panels > 2) return fail(SR_E_ARG, "sr_conv: n_panels must be 1 or 2");
     if (a->batch < 1 || a->height < 1 || a->width < 1) return fail(SR_E_ARG, "sr_conv: empty input");
     if (a->epilogue < SR_EPI_ACT || a->epilogue > SR_EPI_RAW_STATS) return fail(SR_E_ARG, "sr_conv: bad epilogue");
-    if (a->epilogue == SR_EPI_RAW_STATS && !a->stats) return fail(SR_E_ARG, "sr_conv: RAW_STATS needs stats");
-    if (!a->out) return fail(SR_E_ARG, "sr_conv: null out");
-    EncodeTiledFn encode = get_encode_fn();
-    if (!encode) return fail(SR_E_DEVICE, "sr_conv: cuTensorMapEncodeTiled not available from the driver");
-
     // N split
     int ns = 0;
     for (int c = 1; c <= 16; ++c) {
@@ -706,9 +706,9 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
     }
     if (!ns) return fail(SR_E_ARG, "sr_conv: cout=%d cannot be split into multiples of 32 <= 256", a->cout);
 
-    ConvParams p;
+    ConvParams& p = plan->p;
     memset(&p, 0, sizeof(p));
-    Tile tile;
+    Tile& tile = plan->tile;
     if (!pick_tile(a->height, a->width, a->epilogue, &tile))
         return fail(SR_E_ARG, "sr_conv: no tile for %dx%d epilogue %d", a->height, a->width, a->epilogue);
     p.n_panels = a->n_panels;
@@ -741,30 +741,14 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
     int staging = 0;   // the producer prefetches the next tile during the epilogue: staging cannot alias the pipeline
     if (a->epilogue == SR_EPI_ACT_POOL2 || a->epilogue == SR_EPI_ACT) staging = 2 * kSubRows * kStagePitchBf16;
     if (a->epilogue == SR_EPI_ACT_AVG) staging = 2 * kSubRows * kStagePitchF32 * 4;
-
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    static int max_dyn = 0;
-    std::call_once(attr_once, [] {
-        cudaFuncAttributes fa;
-        attr_err = cudaFuncGetAttributes(&fa, conv_umma_kernel);
-        if (attr_err != cudaSuccess) return;
-        max_dyn = 227 * 1024 - (int)fa.sharedSizeBytes;  // static + dynamic <= 227 KB per CTA
-        attr_err = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
-    });
-    if (attr_err != cudaSuccess)
-        return fail(SR_E_CUDA, "sr_conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
     p.staging_bytes = staging;
     const int shift_bytes = a->epilogue == SR_EPI_RAW_STATS ? 0 : (int)align_up((int64_t)a->cout * 4, 16);
     const int budget = max_dyn - 1024 - staging - shift_bytes;
 
     for (int i = 0; i < a->n_panels; ++i) {
         const sr_conv_panel& sp = a->panel[i];
-        if (!sp.act || !sp.wgt) return fail(SR_E_ARG, "sr_conv: null panel pointer");
         if (sp.cin_pad < 16 || sp.cin_pad % 16) return fail(SR_E_ARG, "sr_conv: cin_pad must be a multiple of 16");
         if (sp.taps != 9 && sp.taps != 1) return fail(SR_E_ARG, "sr_conv: taps must be 9 or 1");
-        if ((reinterpret_cast<uintptr_t>(sp.act) | reinterpret_cast<uintptr_t>(sp.wgt)) & 15)
-            return fail(SR_E_ARG, "sr_conv: operand pointers must be 16-byte aligned");
         // Tap reuse: a row-stacked tile of one image (84x84 / 42x42 maps) covers 2*TH consecutive image rows, so one tall
         // box with a one-row halo above and below holds every dh tap of a given dw.
         p.panel[i].reuse = (sp.taps == 9 && tile.stack_h && tile.TN == 1 && !getenv("SRB_NO_TAP_REUSE")) ? 1 : 0;
@@ -801,7 +785,6 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
     p.n_stages = std::min(8, budget / p.stage_bytes);
     if (p.n_stages < 2) return fail(SR_E_ARG, "sr_conv: pipeline does not fit in shared memory");
     p.sub_stride = kSubRows * kc0;
-
     for (int i = 0; i < a->n_panels; ++i) {
         const sr_conv_panel& sp = a->panel[i];
         PanelDev& pd = p.panel[i];
@@ -810,6 +793,70 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
         pd.kc_bytes = std::min(kc0, kc_bytes_for(sp.cin_pad));
         pd.ncb = (sp.cin_pad * 2 + pd.kc_bytes - 1) / pd.kc_bytes;
         pd.last_ksteps = (sp.cin_pad * 2 - (pd.ncb - 1) * pd.kc_bytes) / 32;   // cin_pad is a multiple of 16 channels
+    }
+    const int tiles_n = tile.stack_h ? a->batch : (a->batch + 2 * tile.TN - 1) / (2 * tile.TN);
+    p.total_tiles = tile.tiles_w * tile.tiles_h * tiles_n * ns;
+    plan->staging = staging;
+    plan->shift_bytes = shift_bytes;
+    plan->dyn_smem = p.n_stages * p.stage_bytes + staging + shift_bytes + 1024;
+    return SR_OK;
+}
+
+constexpr int kStaticSmemEstimate = 3072;   // conv_umma_kernel's static shared memory (ptxas -v); used when no device is present
+
+}  // namespace
+
+// Host-only view of the plan (no device needed): lets tests pin the tile / pipeline choices per layer shape.
+extern "C" int32_t sr_conv_plan(const sr_conv_args* a, int32_t* out16) {
+    if (!out16) return fail(SR_E_ARG, "sr_conv_plan: null output");
+    ConvPlan plan;
+    const int32_t rc = plan_conv(a, 227 * 1024 - kStaticSmemEstimate, &plan);
+    if (rc != SR_OK) return rc;
+    const ConvParams& p = plan.p;
+    const int32_t v[16] = {p.TW, p.TH, p.TN, p.stack_h, p.tiles_w, p.tiles_h, p.n_cta, p.n_splits, p.acc_stages,
+                           p.panel[0].reuse, p.panel[0].kc_bytes, p.n_stages, p.stage_bytes, plan.dyn_smem,
+                           p.panel[0].ncb, p.panel[0].last_ksteps};
+    memcpy(out16, v, sizeof(v));
+    return SR_OK;
+}
+
+extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (!a) return fail(SR_E_ARG, "sr_conv: null args");
+    if (a->n_panels < 1 || a->n_panels > 2) return fail(SR_E_ARG, "sr_conv: n_panels must be 1 or 2");
+    if (a->batch < 1 || a->height < 1 || a->width < 1) return fail(SR_E_ARG, "sr_conv: empty input");
+    if (a->epilogue < SR_EPI_ACT || a->epilogue > SR_EPI_RAW_STATS) return fail(SR_E_ARG, "sr_conv: bad epilogue");
+    if (a->epilogue == SR_EPI_RAW_STATS && !a->stats) return fail(SR_E_ARG, "sr_conv: RAW_STATS needs stats");
+    if (!a->out) return fail(SR_E_ARG, "sr_conv: null out");
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) return fail(SR_E_DEVICE, "sr_conv: cuTensorMapEncodeTiled not available from the driver");
+
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    static int max_dyn = 0;
+    std::call_once(attr_once, [] {
+        cudaFuncAttributes fa;
+        attr_err = cudaFuncGetAttributes(&fa, conv_umma_kernel);
+        if (attr_err != cudaSuccess) return;
+        max_dyn = 227 * 1024 - (int)fa.sharedSizeBytes;  // static + dynamic <= 227 KB per CTA
+        attr_err = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+    });
+    if (attr_err != cudaSuccess)
+        return fail(SR_E_CUDA, "sr_conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+
+    ConvPlan plan;
+    {
+        const int32_t rc = plan_conv(a, max_dyn, &plan);
+        if (rc != SR_OK) return rc;
+    }
+    ConvParams& p = plan.p;
+    const Tile& tile = plan.tile;
+    for (int i = 0; i < a->n_panels; ++i) {
+        const sr_conv_panel& sp = a->panel[i];
+        PanelDev& pd = p.panel[i];
+        if (!sp.act || !sp.wgt) return fail(SR_E_ARG, "sr_conv: null panel pointer");
+        if ((reinterpret_cast<uintptr_t>(sp.act) | reinterpret_cast<uintptr_t>(sp.wgt)) & 15)
+            return fail(SR_E_ARG, "sr_conv: operand pointers must be 16-byte aligned");
         const int kc = pd.kc_bytes / 2;
         {
             cuuint64_t gdim[4] = {(cuuint64_t)sp.cin_pad, (cuuint64_t)a->width, (cuuint64_t)a->height, (cuuint64_t)a->batch};
@@ -834,10 +881,9 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
             if (r != CUDA_SUCCESS) return fail(SR_E_CUDA, "sr_conv: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
         }
     }
-    const int dyn_smem = p.n_stages * p.stage_bytes + staging + shift_bytes + 1024;
+    const int dyn_smem = plan.dyn_smem;
 
-    const int tiles_n = tile.stack_h ? a->batch : (a->batch + 2 * tile.TN - 1) / (2 * tile.TN);
-    p.total_tiles = tile.tiles_w * tile.tiles_h * tiles_n * ns;
+
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;

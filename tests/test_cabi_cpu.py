@@ -93,3 +93,49 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dp, f)
+
+
+def _conv_plan(lib, B, H, cin, cout, epi=0, taps=9, second=None):
+    from srb200 import _lib as L
+    a = L.ConvArgs()
+    a.batch, a.height, a.width, a.cout = B, H, H, cout
+    a.n_panels = 1 if second is None else 2
+    a.panel[0].cin_pad, a.panel[0].taps = (cin + 15) // 16 * 16, taps
+    if second is not None:
+        a.panel[1].cin_pad, a.panel[1].taps = (second + 15) // 16 * 16, 1
+    a.epilogue = epi
+    out = (ctypes.c_int32 * 16)()
+    assert lib.sr_conv_plan(ctypes.byref(a), out) == 0, lib.sr_last_error()
+    keys = "TW TH TN stacked tiles_w tiles_h n_cta n_splits tmem_stages reuse row_bytes ring stage_bytes dyn_smem ncb last_k".split()
+    return dict(zip(keys, list(out)))
+
+
+def test_conv_plan_for_every_backbone_layer(lib):
+    """The host-side launch plan (no GPU needed) for every conv shape of the RFS ResNet-18 at the bench batch: the large
+    maps must get the row-stacked one-image tile that tap reuse needs (a utilisation-first picker once chose 4x4x8 boxes
+    there and silently disabled reuse), rows are 128 bytes from 64 channels up, the ring has >= 3 stages, >= 90 % of the
+    UMMA rows are real pixels, pooled tiles keep their 2x2 windows inside a CTA, and everything fits in 227 KB."""
+    ACT, POOL, AVG, RAW = 0, 1, 2, 3
+    layers = [(84, 3, 64, ACT, None), (84, 64, 64, ACT, None), (84, 64, 64, POOL, 3),
+              (42, 64, 160, ACT, None), (42, 160, 160, ACT, None), (42, 160, 160, POOL, 64),
+              (21, 160, 320, ACT, None), (21, 320, 320, ACT, None), (21, 320, 320, POOL, 160),
+              (10, 320, 320, ACT, None), (10, 320, 640, ACT, None), (10, 640, 640, ACT, None), (10, 640, 640, POOL, 320),
+              (5, 640, 640, ACT, None), (5, 640, 640, AVG, None)]
+    for B in (1024, 185, 2):
+        for H, cin, cout, epi, second in layers:
+            for mode in (epi, RAW):
+                p = _conv_plan(lib, B, H, cin, cout, mode, 9, second if mode == epi else None)
+                tag = (B, H, cin, cout, mode)
+                assert p['n_cta'] * p['n_splits'] == cout and p['n_cta'] % 32 == 0 and p['n_cta'] <= 256, tag
+                assert p['tmem_stages'] * 2 * p['n_cta'] <= 512, tag
+                assert p['TW'] * p['TH'] * p['TN'] >= 115 and p['TW'] * p['TH'] * p['TN'] <= 128, tag
+                assert p['ring'] >= 3 and p['dyn_smem'] <= 227 * 1024 - 3072, tag
+                assert p['row_bytes'] == (128 if cin >= 64 else 32), tag
+                if mode == POOL:
+                    assert p['stacked'] or p['TH'] % 2 == 0, tag
+                if H >= 42:
+                    assert (p['TW'], p['TH'], p['TN'], p['stacked']) == (42, 3, 1, 1), tag
+                if H == 84:
+                    assert p['reuse'] == 1, tag
+                if cin == 160:
+                    assert (p['ncb'], p['last_k']) == (3, 2), tag      # 64 + 64 + 32 channels: the zero K-steps are skipped
