@@ -29,6 +29,33 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
     }
 }
 
+// ---- uint8 HWC image store -> ToTensor (x / 255) -> Normalize ((x - mean) / std) -> NHWC bf16, channels zero-padded ----
+// Same fp32 operations, in the same order, as torchvision's ToTensor + Normalize followed by pack_input_kernel.
+struct NormParams {
+    float mean[4], stdev[4];
+};
+__global__ void pack_input_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t npix_total, int C,
+                                     int cpad, NormParams np) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // pixel index over (n, h, w)
+    if (i >= npix_total) return;
+    const uint8_t* src = x + i * C;
+    __nv_bfloat16* dst = y + i * cpad;
+    for (int c0 = 0; c0 < cpad; c0 += 8) {
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            float f = 0.f;
+            if (c < C) {
+                f = __fdiv_rn((float)src[c], 255.0f);
+                f = __fdiv_rn(__fsub_rn(f, np.mean[c]), np.stdev[c]);
+            }
+            v[j] = __float2bfloat16_rn(f);
+        }
+        *reinterpret_cast<uint4*>(dst + c0) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
 __global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
                                float* scale, float* shift, int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -234,6 +261,26 @@ extern "C" int32_t sr_pack_input(const float* x, void* y, int32_t batch, int32_t
     const int threads = 256;
     pack_input_kernel<<<(unsigned)((npix + threads - 1) / threads), threads, 0, stream>>>(
         x, static_cast<__nv_bfloat16*>(y), npix, channels, height * width, cpad);
+    SR_CUDA_OK(cudaGetLastError());
+    return SR_OK;
+}
+
+extern "C" int32_t sr_pack_input_u8(const uint8_t* x, void* y, int32_t batch, int32_t channels, int32_t height,
+                                    int32_t width, const float* mean_host, const float* std_host, int32_t cpad,
+                                    void* stream_v) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    if (!x || !y || !mean_host || !std_host || batch < 1 || channels < 1 || channels > 4 || cpad < channels || cpad % 8)
+        return fail(SR_E_ARG, "sr_pack_input_u8: bad arguments");
+    NormParams np;
+    for (int c = 0; c < 4; ++c) {
+        np.mean[c] = c < channels ? mean_host[c] : 0.f;
+        np.stdev[c] = c < channels ? std_host[c] : 1.f;
+        if (c < channels && !(np.stdev[c] > 0.f)) return fail(SR_E_ARG, "sr_pack_input_u8: std must be positive");
+    }
+    const int64_t npix = (int64_t)batch * height * width;
+    const int threads = 256;
+    pack_input_u8_kernel<<<(unsigned)((npix + threads - 1) / threads), threads, 0, stream>>>(
+        x, static_cast<__nv_bfloat16*>(y), npix, channels, cpad, np);
     SR_CUDA_OK(cudaGetLastError());
     return SR_OK;
 }

@@ -213,8 +213,10 @@ class ResNet(nn.Module):
         running-stat update + dropout / DropBlock; eval: folded BN)."""
         if not x.is_cuda:
             raise RuntimeError("srb200: ResNet.forward needs CUDA tensors on a B200 (no CPU path)")
-        if x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != 84 or x.shape[3] != 84:
-            raise RuntimeError("srb200: expected fp32 [B,3,84,84] input, got %s %s" % (x.dtype, tuple(x.shape)))
+        raw_u8 = x.dtype == torch.uint8 and x.dim() == 4 and tuple(x.shape[1:]) == (84, 84, 3)   # image store, NHWC
+        if not raw_u8 and (x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != 84 or x.shape[3] != 84):
+            raise RuntimeError("srb200: expected fp32 [B,3,84,84] (or uint8 [B,84,84,3]) input, got %s %s" %
+                               (x.dtype, tuple(x.shape)))
         self.advance_block_counters(1)
         eng = self.engine()
         if self.training:

@@ -18,7 +18,7 @@ EXPORTS = [
     "sr_last_error", "sr_version", "sr_check_device", "sr_pack_input", "sr_bn_fold", "sr_pack_weight", "sr_conv",
     "sr_bn_finalize", "sr_bn_apply", "sr_subspace_factor_workspace_bytes", "sr_subspace_factor",
     "sr_head_workspace_bytes", "sr_head_run", "sr_eval_logits", "sr_semantic_pullers", "sr_linear_fwd",
-    "sr_linear_bwd", "sr_sqdist", "sr_diff_scale", "sr_project_rows", "sr_score_logits", "sr_host_bernoulli", "sr_host_dropblock", "sr_conv_plan", "sr_global_avg", "sr_mse_grad", "sr_sgd_update",
+    "sr_linear_bwd", "sr_sqdist", "sr_diff_scale", "sr_project_rows", "sr_score_logits", "sr_host_bernoulli", "sr_host_dropblock", "sr_conv_plan", "sr_pack_input_u8", "sr_global_avg", "sr_mse_grad", "sr_sgd_update",
 ]
 
 
@@ -121,6 +121,8 @@ def load():
     lib.sr_global_avg.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.sr_host_bernoulli.restype = i64
     lib.sr_host_bernoulli.argtypes = [vp, i64, i32, C.c_double, i64, vp]
+    lib.sr_pack_input_u8.restype = i32
+    lib.sr_pack_input_u8.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), i32, vp]
     lib.sr_conv_plan.restype = i32
     lib.sr_conv_plan.argtypes = [C.POINTER(ConvArgs), C.POINTER(C.c_int32)]
     lib.sr_host_dropblock.restype = i64

@@ -107,8 +107,17 @@ class BackboneEngine(object):
             outs.append(self._eval_chunk(x[i0:i0 + step].contiguous(), taps))
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
+    @staticmethod
+    def pack(x):
+        """fp32 NCHW (already normalised, the reference's loader output) or uint8 NHWC (the raw image store: ToTensor +
+        Normalize are fused into the packing kernel) -> NHWC bf16, 16 channels."""
+        if x.dtype == torch.uint8:
+            from dataset import transform_cfg
+            return ops.pack_input_u8(x.contiguous(), transform_cfg.mean, transform_cfg.std, 16)
+        return ops.pack_input(x.contiguous(), 16)
+
     def _eval_chunk(self, x, taps):
-        h = ops.pack_input(x, 16)
+        h = self.pack(x)
         nb = len(self.blocks)
         for bi, (b, w) in enumerate(zip(self.blocks, self._folded)):
             cout = b['cout']
@@ -226,10 +235,10 @@ class BackboneEngine(object):
         raw_w = self._raw[1]
         B = x.shape[0]
         dev = x.device
-        size = x.shape[2]
+        size = x.shape[2] if x.dtype != torch.uint8 else x.shape[1]
         self._cur_fwd = self._pf_fwd
         self._pf_fwd += 1
-        h = ops.pack_input(x.contiguous(), 16)
+        h = self.pack(x)
         nb = len(self.blocks)
 
         # one zeroed fp64 scratch for the (sum, sum of squares) of every conv of this forward, one fused counter bump at

@@ -62,6 +62,18 @@ def bn_fold(gamma, beta, running_mean, running_var, eps=1e-5):
     return scale, shift
 
 
+def pack_input_u8(x_nhwc_u8, mean, std, cpad=16):
+    """uint8 NHWC images -> ToTensor + Normalize(mean, std) -> NHWC bf16 with channels zero-padded to cpad (one kernel)."""
+    B, H, W, Cc = x_nhwc_u8.shape
+    y = torch.empty((B, H, W, cpad), dtype=torch.bfloat16, device=x_nhwc_u8.device)
+    m = (C.c_float * Cc)(*[float(v) for v in mean])
+    s = (C.c_float * Cc)(*[float(v) for v in std])
+    rc = L.load().sr_pack_input_u8(_ptr(x_nhwc_u8, torch.uint8, "x"), _ptr(y), B, Cc, H, W, m, s, cpad, _stream())
+    L.check(rc, "sr_pack_input_u8")
+    LAUNCHES[0] += 1
+    return y
+
+
 def pack_weight(w_oihw, scale=None, cin_pad=None, out=None):
     """OIHW fp32 -> bf16 [cout, kh*kw, cin_pad] (optionally scaled per output channel)."""
     co, ci, kh, kw = w_oihw.shape

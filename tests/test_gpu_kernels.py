@@ -95,3 +95,29 @@ def test_backbone_features_and_taps_vs_oracle(model):
     assert [tuple(f.shape[1:]) for f in feats] == [(64, 42, 42), (160, 21, 21), (320, 10, 10), (640, 5, 5), (640,)]
     assert ((feats[-1].cpu() - want).norm() / want.norm()).item() < 1e-2
     assert logits.shape == (12, 60)
+
+
+@pytest.mark.gpu
+def test_uint8_image_front_end_is_bit_exact():
+    """sr_pack_input_u8 (uint8 HWC store -> ToTensor -> Normalize -> NHWC bf16, one kernel) against the reference's
+    preprocessing done by torch on the CPU (x / 255, then (x - mean) / std, transform_cfg.py:8-10, 42-45) followed by
+    sr_pack_input: identical bits, hence identical features.  Ragged batch, every byte value present."""
+    import torch
+    from dataset import transform_cfg
+    from models.util import create_model
+    from srb200 import ops, synthetic
+    g = torch.Generator().manual_seed(7)
+    x8 = torch.randint(0, 256, (37, 84, 84, 3), dtype=torch.uint8, generator=g)
+    x8[0, :2].view(-1)[:256] = torch.arange(256).to(torch.uint8)
+    t = x8.permute(0, 3, 1, 2).to(torch.float32).div(255)                       # ToTensor
+    mean = torch.tensor(transform_cfg.mean, dtype=torch.float32).view(1, 3, 1, 1)
+    std = torch.tensor(transform_cfg.std, dtype=torch.float32).view(1, 3, 1, 1)
+    t = t.sub(mean).div(std).contiguous()                                       # Normalize
+    want = ops.pack_input(t.cuda(), 16)
+    got = ops.pack_input_u8(x8.cuda(), transform_cfg.mean, transform_cfg.std, 16)
+    assert torch.equal(want.view(torch.int16), got.view(torch.int16))
+    net = synthetic.init_model(create_model, synthetic.default_opt(1), 1).cuda().eval()
+    with torch.no_grad():
+        f_ref = net.features(t.cuda())
+        f_u8 = net.features(x8.cuda())
+    assert torch.equal(f_ref, f_u8)
