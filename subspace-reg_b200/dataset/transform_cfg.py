@@ -1,9 +1,36 @@
-"""Normalisation constants of the reference's image pipeline (dataset/transform_cfg.py:8-10).
+"""Image transforms of the incremental evaluation (reference dataset/transform_cfg.py).
 
-Only the deterministic tail of its test-time transform is on the incremental-session path: ToTensor (uint8 HWC -> x / 255)
-and Normalize(mean, std).  Here both are fused into the first kernel of the backbone (`sr_pack_input_u8`): pass uint8
-NHWC CUDA images to `ResNet.features` / `BackboneEngine.eval_features` instead of normalised fp32 NCHW tensors.  The
-PIL / torchvision augmentations of the support set (RandomCrop, ColorJitter, flip) stay outside.
+Only the deterministic tail of the test-time transform is on the hot path: ToTensor (uint8 HWC -> x / 255) and
+Normalize(mean, std), with the constants of :8-10.  Here both are fused into the first kernel of the backbone
+(`sr_pack_input_u8`): pass uint8 NHWC CUDA images (`MetaImageNet(..., raw=True)`) to `ResNet.features` /
+`BackboneEngine.eval_features` instead of normalised fp32 NCHW tensors.
+
+`transforms_test_options` / `transforms_options` / `transforms_list` keep `eval_incremental.py:18,50` working when this
+package shadows the reference's `dataset`: option 'A' (miniImageNet) is the (support, query) pair of the reference -
+random crop with 8-pixel padding + horizontal flip (+ colour jitter in the training variant) on the support copies,
+plain normalisation on the queries - built from torchvision when it is installed; without torchvision the pair is
+(None, None), which `dataset.mini_imagenet` reads as "normalise only" on both branches.  The CIFAR option 'D' belongs to
+datasets outside this path.
 """
 mean = [120.39586422 / 255.0, 115.59361427 / 255.0, 104.54012653 / 255.0]
 std = [70.68188272 / 255.0, 68.27635443 / 255.0, 72.54505529 / 255.0]
+
+
+def _option_a(jitter):
+    try:
+        import numpy as np
+        import torchvision.transforms as T
+        from PIL import Image
+    except ImportError:
+        return [None, None]
+    norm = T.Normalize(mean=mean, std=std)
+    aug = [T.RandomCrop(84, padding=8)] + ([T.ColorJitter(brightness=0.4, contrast=0.4, saturation=0.4)] if jitter else []) + \
+          [T.RandomHorizontalFlip()]
+    support = T.Compose([Image.fromarray] + aug + [np.array, T.ToTensor(), norm])
+    query = T.Compose([Image.fromarray, T.ToTensor(), norm])
+    return [support, query]
+
+
+transforms_list = ['A']
+transforms_options = {'A': _option_a(jitter=True)}
+transforms_test_options = {'A': _option_a(jitter=False)}

@@ -155,3 +155,36 @@ def write_word_embeds(npz_path, out_dir, dataset='miniImageNet', dim=500):
     with open(path, 'wb') as f:
         pickle.dump({w: vecs[i] for i, w in enumerate(words)}, f)
     return path
+
+
+def write_image_store(out_dir, n_classes=100, per_class=600, side=4, seed=0):
+    """A miniImageNet-format store for the data front-end tests: ``all.pickle`` ({'data': uint8 [N,side,side,3], 'labels',
+    'catname2label'}, the layout dataset/mini_imagenet.py reads with --continual) + ``class_labels.txt``.  Images are
+    tiny; pixel (0,0) encodes (class, index // 256, index % 256) so a sampled image can be identified, the rest is noise.
+    Class names are LABELS-like single tokens so that get_vocabs works."""
+    rng = np.random.RandomState(seed)
+    n = n_classes * per_class
+    data = rng.randint(0, 256, size=(n, side, side, 3)).astype(np.uint8)
+    labels = []
+    order = rng.permutation(n)                     # classes interleaved like a real store
+    cls_of = np.repeat(np.arange(n_classes), per_class)[order]
+    counters = np.zeros(n_classes, dtype=np.int64)
+    for i in range(n):
+        c = int(cls_of[i])
+        k = int(counters[c])
+        counters[c] += 1
+        data[i, 0, 0] = (c, k // 256, k % 256)
+        labels.append(c)
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "all.pickle"), 'wb') as f:
+        pickle.dump({'data': data, 'labels': labels, 'catname2label': {"n%08d" % c: c for c in range(n_classes)}}, f)
+    with open(os.path.join(out_dir, "class_labels.txt"), 'w') as f:
+        for c in range(n_classes):
+            f.write("n%08d class_%d\n" % (c, c))
+    return out_dir
+
+
+def image_ids(imgs_u8_nhwc):
+    """(class, index) of images written by write_image_store, from pixel (0,0)."""
+    a = np.asarray(imgs_u8_nhwc).astype(np.int64)
+    return np.stack([a[:, 0, 0, 0], a[:, 0, 0, 1] * 256 + a[:, 0, 0, 2]], 1)

@@ -135,3 +135,51 @@ def test_unsupported_options_fail_loudly():
     w.opt.freeze_backbone_at = 3
     with pytest.raises(NotImplementedError):
         few_shot_finetune_incremental_test(net, {}, None, w.meta_valloader, w.base_val_loader, w.opt)
+
+
+def test_episode_front_end_matches_the_reference_sampler(tmp_path):
+    """dataset/mini_imagenet.py (image store split + episode sampler, no PIL) against tests/golden/episodes.pt, recorded by
+    oracle/make_episode_golden.py from the UNMODIFIED reference classes on the same synthetic store: same base test set,
+    same base exemplars, same eight disjoint novel sessions (which images, in which order, with which labels), and
+    bit-identical normalised pixels; the raw uint8 path returns the same images."""
+    import argparse
+    import numpy as np
+    import torch
+    from dataset.mini_imagenet import ImageNet, MetaImageNet
+    from srb200 import synthetic
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "episodes.pt"), weights_only=False)
+    root = synthetic.write_image_store(str(tmp_path / "store"))
+    for seed, g in gold.items():
+        a = argparse.Namespace(data_root=root, data_aug=False, set_seed=seed, continual=True, n_ways=5, n_shots=5, n_queries=15,
+                               n_test_runs=8, eval_mode="few-shot-incremental-fine-tune", n_aug_support_samples=5,
+                               n_base_aug_support_samples=1, n_base_support_samples=1)
+        base = ImageNet(args=a, split='train', phase='test')
+        assert len(base) == g['base_len'] and np.array_equal(np.asarray(base.labels), g['base_labels'])
+        assert list(base.label2human) == g['label2human']
+        probe = list(range(0, len(base), 97))
+        raw_base = ImageNet(args=a, split='train', phase='test', raw=True)
+        ids = synthetic.image_ids(torch.stack([raw_base[i][0] for i in probe]).numpy())
+        assert np.array_equal(ids, g['base_probe_ids'])
+        assert torch.equal(torch.stack([base[i][0] for i in probe[:3]]), g['base_probe_x'])
+        assert all(base[i][1] == base.labels[i] - min(base.labels) and base[i][2] == i for i in probe[:5])
+
+        for raw in (False, True):
+            sup = MetaImageNet(args=a, split='train', phase='train', fix_seed=True, use_episodes=False, raw=raw)
+            assert len(sup) == g['exemplar_len']
+            for item, want in zip((0, 3), g['exemplars']):
+                sx, sy, qx, qy = sup[item]
+                assert np.array_equal(np.asarray(sy), want['ys']) and np.array_equal(np.asarray(qy), want['ys'])
+                if raw:
+                    assert sx.dtype == torch.uint8 and np.array_equal(synthetic.image_ids(sx.numpy()), want['ids'])
+                else:
+                    assert sx.dtype == torch.float32 and tuple(sx.shape[1:]) == (3, 4, 4)
+            val = MetaImageNet(args=a, split='val', fix_seed=True, use_episodes=False, disjoint_classes=True, raw=raw)
+            assert len(val) == g['val_len'] and list(val.label2human) == g['val_label2human']
+            for item, want in enumerate(g['sessions']):
+                sx, sy, qx, qy = val[item]
+                assert np.array_equal(np.asarray(sy), want['sup_ys']) and np.array_equal(np.asarray(qy), want['qry_ys'])
+                if raw:
+                    assert np.array_equal(synthetic.image_ids(sx.numpy()), want['sup_ids'])
+                    assert np.array_equal(synthetic.image_ids(qx.numpy()), want['qry_ids'])
+                elif item == 0:
+                    assert torch.equal(sx[:10], want['sup_x'])
