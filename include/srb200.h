@@ -48,9 +48,14 @@ int32_t sr_pack_input(const float* x_nchw, void* y_nhwc_bf16, int32_t batch, int
 /* uint8 HWC images (the reference's image store, dataset/mini_imagenet.py:278-350) -> NHWC bf16 with the channel
  * dimension zero-padded to `cpad`, applying ToTensor (x / 255) and Normalize ((x - mean) / std, transform_cfg.py:8-10,
  * 42-45) on the way: the same fp32 operations in the same order, so the result is bit-identical to the reference's
- * preprocessing followed by sr_pack_input.  mean / std: HOST float[channels]. */
+ * preprocessing followed by sr_pack_input.  mean / std: HOST float[channels].
+ * Optional augmentation of the support transform (transform_cfg.py:32-40), with parameters drawn by the caller:
+ * crop_ij: DEVICE int32 [batch,2] = top-left corner of the height x width crop inside the image zero-padded by `pad`
+ * on every side (RandomCrop(size, padding=pad)), or NULL; flip: DEVICE uint8 [batch] (RandomHorizontalFlip, applied
+ * after the crop), or NULL. */
 int32_t sr_pack_input_u8(const uint8_t* x_nhwc_u8, void* y_nhwc_bf16, int32_t batch, int32_t channels, int32_t height,
-                         int32_t width, const float* mean_host, const float* std_host, int32_t cpad, void* stream);
+                         int32_t width, const float* mean_host, const float* std_host, int32_t cpad,
+                         const int32_t* crop_ij, const uint8_t* flip, int32_t pad, void* stream);
 
 /* BatchNorm eval-mode fold (resnet_language.py:250-255,148; nn.BatchNorm2d eval semantics):
  *   scale[c] = gamma[c] / sqrt(running_var[c] + eps),  shift[c] = beta[c] - running_mean[c] * scale[c]. */

@@ -35,10 +35,27 @@ struct NormParams {
     float mean[4], stdev[4];
 };
 __global__ void pack_input_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t npix_total, int C,
-                                     int cpad, NormParams np) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // pixel index over (n, h, w)
+                                     int H, int W, int cpad, NormParams np, const int32_t* __restrict__ crop_ij,
+                                     const uint8_t* __restrict__ flip, int pad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // output pixel index over (n, h, w)
     if (i >= npix_total) return;
-    const uint8_t* src = x + i * C;
+    // RandomCrop(size, padding=pad) + RandomHorizontalFlip of the reference's support transform, applied while reading:
+    // output (h, w) of image n comes from input (h + i0 - pad, w' + j0 - pad), w' = W-1-w when flipped; outside the image
+    // the zero padding (a 0 byte BEFORE ToTensor / Normalize, like PIL's constant fill).
+    const int64_t hw = (int64_t)H * W;
+    const int64_t n = i / hw;
+    const int r = (int)(i - n * hw);
+    int h = r / W, w = r - h * W;
+    bool inside = true;
+    if (crop_ij != nullptr || flip != nullptr) {
+        if (flip != nullptr && flip[n]) w = W - 1 - w;
+        if (crop_ij != nullptr) {
+            h += crop_ij[2 * n] - pad;
+            w += crop_ij[2 * n + 1] - pad;
+        }
+        inside = h >= 0 && h < H && w >= 0 && w < W;
+    }
+    const uint8_t* src = x + (n * hw + (int64_t)h * W + w) * C;
     __nv_bfloat16* dst = y + i * cpad;
     for (int c0 = 0; c0 < cpad; c0 += 8) {
         __align__(16) __nv_bfloat16 v[8];
@@ -47,7 +64,7 @@ __global__ void pack_input_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat1
             const int c = c0 + j;
             float f = 0.f;
             if (c < C) {
-                f = __fdiv_rn((float)src[c], 255.0f);
+                f = __fdiv_rn(inside ? (float)src[c] : 0.f, 255.0f);
                 f = __fdiv_rn(__fsub_rn(f, np.mean[c]), np.stdev[c]);
             }
             v[j] = __float2bfloat16_rn(f);
@@ -267,7 +284,7 @@ extern "C" int32_t sr_pack_input(const float* x, void* y, int32_t batch, int32_t
 
 extern "C" int32_t sr_pack_input_u8(const uint8_t* x, void* y, int32_t batch, int32_t channels, int32_t height,
                                     int32_t width, const float* mean_host, const float* std_host, int32_t cpad,
-                                    void* stream_v) {
+                                    const int32_t* crop_ij, const uint8_t* flip, int32_t pad, void* stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     if (!x || !y || !mean_host || !std_host || batch < 1 || channels < 1 || channels > 4 || cpad < channels || cpad % 8)
         return fail(SR_E_ARG, "sr_pack_input_u8: bad arguments");
@@ -279,8 +296,9 @@ extern "C" int32_t sr_pack_input_u8(const uint8_t* x, void* y, int32_t batch, in
     }
     const int64_t npix = (int64_t)batch * height * width;
     const int threads = 256;
+    if (pad < 0 || (crop_ij && pad > 64)) return fail(SR_E_ARG, "sr_pack_input_u8: bad padding");
     pack_input_u8_kernel<<<(unsigned)((npix + threads - 1) / threads), threads, 0, stream>>>(
-        x, static_cast<__nv_bfloat16*>(y), npix, channels, cpad, np);
+        x, static_cast<__nv_bfloat16*>(y), npix, channels, height, width, cpad, np, crop_ij, flip, pad);
     SR_CUDA_OK(cudaGetLastError());
     return SR_OK;
 }

@@ -16,6 +16,22 @@ mean = [120.39586422 / 255.0, 115.59361427 / 255.0, 104.54012653 / 255.0]
 std = [70.68188272 / 255.0, 68.27635443 / 255.0, 72.54505529 / 255.0]
 
 
+def draw_crop_flip(n, size=84, padding=8, p=0.5):
+    """Parameters of the reference's test-time SUPPORT augmentation for n images, drawn from torch's CPU generator in the
+    order torchvision draws them per image - RandomCrop.get_params (two torch.randint) then RandomHorizontalFlip (one
+    torch.rand) - so that `sr_pack_input_u8(crop_ij, flip, pad=padding)` reproduces `transforms_test_options['A'][0]` bit
+    for bit while leaving the generator in the same state.  -> (int32 [n,2] crop corner in the padded image, uint8 [n])."""
+    import torch
+    ij = torch.empty((n, 2), dtype=torch.int32)
+    flip = torch.empty(n, dtype=torch.uint8)
+    span = 2 * padding + 1            # (size + 2 * padding) - size + 1 possible corners per axis
+    for k in range(n):
+        ij[k, 0] = torch.randint(0, span, size=(1,)).item()
+        ij[k, 1] = torch.randint(0, span, size=(1,)).item()
+        flip[k] = 1 if torch.rand(1) < p else 0
+    return ij, flip
+
+
 def _option_a(jitter):
     try:
         import numpy as np

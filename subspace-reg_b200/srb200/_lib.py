@@ -122,7 +122,7 @@ def load():
     lib.sr_host_bernoulli.restype = i64
     lib.sr_host_bernoulli.argtypes = [vp, i64, i32, C.c_double, i64, vp]
     lib.sr_pack_input_u8.restype = i32
-    lib.sr_pack_input_u8.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), i32, vp]
+    lib.sr_pack_input_u8.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), i32, vp, vp, i32, vp]
     lib.sr_conv_plan.restype = i32
     lib.sr_conv_plan.argtypes = [C.POINTER(ConvArgs), C.POINTER(C.c_int32)]
     lib.sr_host_dropblock.restype = i64

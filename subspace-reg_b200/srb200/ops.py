@@ -62,13 +62,20 @@ def bn_fold(gamma, beta, running_mean, running_var, eps=1e-5):
     return scale, shift
 
 
-def pack_input_u8(x_nhwc_u8, mean, std, cpad=16):
-    """uint8 NHWC images -> ToTensor + Normalize(mean, std) -> NHWC bf16 with channels zero-padded to cpad (one kernel)."""
+def pack_input_u8(x_nhwc_u8, mean, std, cpad=16, crop_ij=None, flip=None, pad=0):
+    """uint8 NHWC images -> [RandomCrop(padding=pad) at crop_ij, horizontal flip where flip] -> ToTensor +
+    Normalize(mean, std) -> NHWC bf16 with channels zero-padded to cpad (one kernel).  crop_ij: CUDA int32 [B,2],
+    flip: CUDA uint8 [B] (see dataset.transform_cfg.draw_crop_flip), or None."""
     B, H, W, Cc = x_nhwc_u8.shape
     y = torch.empty((B, H, W, cpad), dtype=torch.bfloat16, device=x_nhwc_u8.device)
     m = (C.c_float * Cc)(*[float(v) for v in mean])
     s = (C.c_float * Cc)(*[float(v) for v in std])
-    rc = L.load().sr_pack_input_u8(_ptr(x_nhwc_u8, torch.uint8, "x"), _ptr(y), B, Cc, H, W, m, s, cpad, _stream())
+    if crop_ij is not None and tuple(crop_ij.shape) != (B, 2):
+        raise RuntimeError("srb200: crop_ij must be [batch, 2]")
+    if flip is not None and flip.numel() != B:
+        raise RuntimeError("srb200: flip must be [batch]")
+    rc = L.load().sr_pack_input_u8(_ptr(x_nhwc_u8, torch.uint8, "x"), _ptr(y), B, Cc, H, W, m, s, cpad,
+                                   _ptr(crop_ij, torch.int32, "crop_ij"), _ptr(flip, torch.uint8, "flip"), int(pad), _stream())
     L.check(rc, "sr_pack_input_u8")
     LAUNCHES[0] += 1
     return y

@@ -121,3 +121,28 @@ def test_uint8_image_front_end_is_bit_exact():
         f_ref = net.features(t.cuda())
         f_u8 = net.features(x8.cuda())
     assert torch.equal(f_ref, f_u8)
+
+
+@pytest.mark.gpu
+def test_support_augmentation_on_device_matches_torchvision():
+    """RandomCrop(84, padding=8) + RandomHorizontalFlip + ToTensor + Normalize of the reference's support transform
+    (transform_cfg.py:32-40), applied by torchvision / PIL on the CPU, against the fused kernel fed with parameters that
+    dataset.transform_cfg.draw_crop_flip draws from the same generator: identical bits, identical generator state."""
+    import torch
+    from dataset import transform_cfg
+    from srb200 import ops
+    support_tf = transform_cfg.transforms_test_options['A'][0]
+    if support_tf is None:
+        pytest.skip("torchvision / PIL not installed")
+    g = torch.Generator().manual_seed(3)
+    x8 = torch.randint(0, 256, (40, 84, 84, 3), dtype=torch.uint8, generator=g)
+    torch.manual_seed(123)
+    want_f = torch.stack([support_tf(img.numpy()) for img in x8])
+    state_ref = torch.get_rng_state()
+    torch.manual_seed(123)
+    ij, flip = transform_cfg.draw_crop_flip(40)
+    assert torch.equal(torch.get_rng_state(), state_ref)
+    assert int(flip.sum()) not in (0, 40) and int(ij.min()) >= 0 and int(ij.max()) <= 16
+    want = ops.pack_input(want_f.cuda().contiguous(), 16)
+    got = ops.pack_input_u8(x8.cuda(), transform_cfg.mean, transform_cfg.std, 16, crop_ij=ij.cuda(), flip=flip.cuda(), pad=8)
+    assert torch.equal(want.view(torch.int16), got.view(torch.int16))
