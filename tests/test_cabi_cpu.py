@@ -139,3 +139,10 @@ def test_conv_plan_for_every_backbone_layer(lib):
                     assert p['reuse'] == 1, tag
                 if cin == 160:
                     assert (p['ncb'], p['last_k']) == (3, 2), tag      # 64 + 64 + 32 channels: the zero K-steps are skipped
+
+
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md names every function include/srb200.h declares (with the reference call site it replaces)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [f for f in declared_functions() if f not in doc and f.replace("sr_linear_", "sr_linear_") not in doc]
+    assert not missing, missing
