@@ -193,6 +193,15 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
                     fwds.append((0, 25 * j))
             net.engine().start_mask_prefetch(fwds)
 
+        # DropBlock masks of this session's train-mode forward(s): their gamma is known now (it depends on the epochs the
+        # previous sessions ran), so a second host thread draws them while this thread sets the session up and launches
+        # the first blocks (each mask is checked against the live generator when it is consumed).
+        nbt0 = next(iter(net.block_counters().values()))
+        ahead = [(support_xs.shape[0], nbt0 + 1)]
+        if opt.memory_replay and len(memory) > 0:
+            ahead.append((len(memory), nbt0 + 2))
+        net.engine().start_dropblock_ahead(ahead)
+
         net.train()
         net.augment_base_classifier_(len(novel_labels))
 

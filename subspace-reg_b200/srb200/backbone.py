@@ -4,6 +4,8 @@ The arithmetic is in libsrb200.so (sr_pack_input / sr_pack_weight / sr_bn_fold /
 sr_bn_apply); this module only owns buffers and launch order.  Reference semantics: BasicBlock.forward
 (models/resnet_language.py:268-301), ResNet.forward (:170-181), nn.BatchNorm2d eval/train.
 """
+import threading
+
 import torch
 import torch.nn.functional as F
 
@@ -39,6 +41,9 @@ class BackboneEngine(object):
         self._fold_key = None
         self._staging = {}
         self._prefetch = None     # host_rng.MaskPrefetch for upcoming train-mode forwards
+        self._db_ready = None     # DropBlock masks drawn ahead by start_dropblock_ahead: key -> (before, after, entry, kept, ...)
+        self._db_done = True
+        self._db_cv = threading.Condition()
         self._pf_fwd = 0          # index of the next train-mode forward relative to the prefetch plan
 
     # ---------------------------------------------------------------- weight packing
@@ -158,13 +163,84 @@ class BackboneEngine(object):
                 size = size // b['pool']
                 if b['drop_block']:
                     bs = b['block_size']
-                    steps.append(('skip', batch * b['cout'] * (size - (bs - 1)) ** 2))
+                    steps.append(('hold', (f, bi), batch * b['cout'] * (size - (bs - 1)) ** 2))
                 else:
                     shape = (batch, b['cout'], size, size)
                     ent = self._pinned(('pf', f, bi), shape)      # waits for the last H2D out of this buffer
                     steps.append(('draw', (f, bi), ent[0], 1 - DROP_RATE))
         self._prefetch = host_rng.MaskPrefetch(steps)
         self._pf_fwd = 0
+
+    @staticmethod
+    def _dropblock_gamma(nbt, bs, size):
+        keep_rate = max(1.0 - DROP_RATE / (20 * 2000) * nbt, 1.0 - DROP_RATE)
+        return (1 - keep_rate) / bs ** 2 * size ** 2 / (size - bs + 1) ** 2
+
+    def start_dropblock_ahead(self, forwards):
+        """DropBlock keep-masks of the upcoming train-mode forwards on a second host thread.  forwards: [(batch,
+        num_batches_tracked at that forward), ...] for the forwards the prefetch plan numbers self._pf_fwd, +1, ...  Their
+        gamma depends on how many epochs the previous session ran, so they cannot be drawn with the dropout masks; but the
+        prefetch thread keeps the generator state in front of every DropBlock region ('hold'), and from that state the
+        seeds can be drawn off the live generator as soon as gamma is known - while the main thread is busy launching the
+        first blocks.  Consumed (and verified against the live generator) in draw_mask."""
+        t = getattr(self, '_db_thread', None)
+        if t is not None:
+            t.join()
+        self._db_ready = {}
+        self._db_done = False
+        if self._prefetch is None or not self._prefetch.alive():
+            self._db_done = True
+            return
+        plan = [(self._pf_fwd + k, batch, nbt) for k, (batch, nbt) in enumerate(forwards)]
+        pf = self._prefetch
+
+        def work():
+            try:
+                for f, batch, nbt in plan:
+                    size = 84
+                    for bi, b in enumerate(self.blocks):
+                        size = size // b['pool']
+                        if not b['drop_block']:
+                            continue
+                        st = pf.hold_state((f, bi))
+                        if st is None:
+                            return
+                        bs = b['block_size']
+                        gamma = self._dropblock_gamma(nbt, bs, size)
+                        shape = (batch, b['cout'], size, size)
+                        seed_shape = (batch, b['cout'], size - (bs - 1), size - (bs - 1))
+                        seeds = self._scratch(('seed_ahead', f & 1, bi), seed_shape)
+                        state = st[0].clone()
+                        if host_rng.replay_into(state, gamma, 1, seeds) < 0 or not torch.equal(state, st[1]):
+                            return
+                        ent = self._pinned(('dbm', f & 1, bi), shape)
+                        kept = host_rng.dropblock_keep(seeds, bs, ent[0])
+                        with self._db_cv:
+                            self._db_ready[(f, bi)] = (st[0], st[1], ent, kept, gamma, shape)
+                            self._db_cv.notify_all()
+            finally:
+                with self._db_cv:
+                    self._db_done = True
+                    self._db_cv.notify_all()
+
+        self._db_thread = threading.Thread(target=work, daemon=True)
+        self._db_thread.start()
+
+    def _dropblock_take(self, key, gamma, shape):
+        """-> (pinned entry, kept) drawn ahead for `key`, after moving the live generator past it; or None."""
+        if getattr(self, '_db_ready', None) is None:
+            return None
+        with self._db_cv:
+            while key not in self._db_ready and not self._db_done:
+                self._db_cv.wait()
+            got = self._db_ready.pop(key, None)
+        if got is None:
+            return None
+        before, after, ent, kept, g, shp = got
+        if g != gamma or tuple(shp) != tuple(shape) or not torch.equal(torch.get_rng_state(), before):
+            return None
+        torch.set_rng_state(after)
+        return ent, kept
 
     def mask_prefetch_alive(self):
         return self._prefetch is not None and self._prefetch.alive()
@@ -213,14 +289,17 @@ class BackboneEngine(object):
         else:
             bs = b['block_size']
             nbt = counters[b['prefix']]
-            keep_rate = max(1.0 - DROP_RATE / (20 * 2000) * nbt, 1.0 - DROP_RATE)
-            gamma = (1 - keep_rate) / bs ** 2 * size ** 2 / (size - bs + 1) ** 2
-            seed_shape = (batch, b['cout'], size - (bs - 1), size - (bs - 1))
-            seed_buf = self._scratch(('seed', bi), seed_shape)                 # reused: a fresh tensor page-faults every time
-            seeds, n_seed = host_rng.bernoulli_u8(seed_shape, gamma, 1, out=seed_buf)   # Bernoulli(gamma).sample(...)
-            # alternate staging buffers: the second forward of a session must not wait for the H2D copy of the first
-            ent = self._pinned(('m', bi, self._cur_fwd & 1), shape)
-            kept = host_rng.dropblock_keep(seeds, bs, ent[0])                  # _compute_block_mask, 1 - mask, .sum()
+            gamma = self._dropblock_gamma(nbt, bs, size)
+            ahead = self._dropblock_take((self._cur_fwd, bi), gamma, shape)
+            if ahead is not None:                                              # drawn on the second host thread
+                ent, kept = ahead
+            else:
+                seed_shape = (batch, b['cout'], size - (bs - 1), size - (bs - 1))
+                seed_buf = self._scratch(('seed', bi), seed_shape)             # reused: a fresh tensor page-faults every time
+                seeds, n_seed = host_rng.bernoulli_u8(seed_shape, gamma, 1, out=seed_buf)   # Bernoulli(gamma).sample(...)
+                # alternate staging buffers: the second forward of a session must not wait for the H2D copy of the first
+                ent = self._pinned(('m', bi, self._cur_fwd & 1), shape)
+                kept = host_rng.dropblock_keep(seeds, bs, ent[0])              # _compute_block_mask, 1 - mask, .sum()
             # countM / count_ones: python int over an fp32 0-d tensor -> fp32 division
             scale = float(torch.tensor(float(ent[0].numel()), dtype=torch.float32) / torch.tensor(float(kept), dtype=torch.float32))
         keep = ent[0].to(device, non_blocking=True)

@@ -38,6 +38,13 @@ def _replay_draw(shape, p, kind, out=None):
     return out, int(ones)
 
 
+def replay_into(state_blob, p, kind, out):
+    """Draw out.numel() Bernoulli(p) values of `kind` from the generator state `state_blob` (a uint8 tensor like
+    torch.get_rng_state(), advanced in place) WITHOUT touching torch's live generator.  -> number of ones, or -1."""
+    return int(L.load().sr_host_bernoulli(C.c_void_p(state_blob.data_ptr()), state_blob.numel(), kind, float(p), out.numel(),
+                                          C.c_void_p(out.data_ptr())))
+
+
 def _self_check():
     saved = torch.get_rng_state()
     ok = True
@@ -107,9 +114,13 @@ class MaskPrefetch(object):
     and `take` only waits for the mask it asks for."""
 
     def __init__(self, steps):
-        """steps: list of ('skip', n_words) | ('draw', key, uint8 CPU buffer [shape], p)."""
+        """steps: list of ('skip', n_words) | ('draw', key, uint8 CPU buffer [shape], p) | ('hold', key, n_words): like
+        'skip', but the generator states before / after the skipped words are kept under `key` so that somebody else can
+        draw those words later, off the live generator (DropBlock seeds: their probability is known only when the
+        session starts)."""
         self.ok = replay_available()
         self.results = {}
+        self.holds = {}
         self.thread = None
         self.dead = False          # the live stream diverged from the guess (or the replay failed): nothing is usable
         self.finished = False
@@ -137,6 +148,13 @@ class MaskPrefetch(object):
                 if st[0] == 'skip':
                     if lib.sr_host_bernoulli(C.c_void_p(blob.data_ptr()), blob.numel(), 2, 0.0, int(st[1]), None) < 0:
                         raise RuntimeError("skip failed")
+                elif st[0] == 'hold':
+                    before = blob.clone()
+                    if lib.sr_host_bernoulli(C.c_void_p(blob.data_ptr()), blob.numel(), 2, 0.0, int(st[2]), None) < 0:
+                        raise RuntimeError("skip failed")
+                    with self._cv:
+                        self.holds[st[1]] = (before, blob.clone())
+                        self._cv.notify_all()
                 else:
                     _, key, buf, p = st
                     before = blob.clone()
@@ -152,6 +170,15 @@ class MaskPrefetch(object):
         with self._cv:
             self.finished = True
             self._cv.notify_all()
+
+    def hold_state(self, key):
+        """-> (state before, state after) of a held region once the thread has passed it, or None."""
+        if self.thread is None or self.dead:
+            return None
+        with self._cv:
+            while key not in self.holds and not self.finished and not self.dead:
+                self._cv.wait()
+            return self.holds.get(key)
 
     def take(self, key, shape):
         """-> (uint8 buffer, ones) or None.  Advances torch's live generator exactly as the draw would have."""
