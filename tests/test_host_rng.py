@@ -106,3 +106,28 @@ def test_dropblock_keep_matches_the_torch_formulation():
     # no seeds at all: everything is kept
     out = torch.zeros(2, 3, 7, 7, dtype=torch.uint8)
     assert host_rng.dropblock_keep(torch.zeros(2, 3, 5, 5, dtype=torch.uint8), 3, out) == out.numel() and bool(out.all())
+
+
+def test_held_regions_can_be_drawn_off_the_live_generator():
+    """A 'hold' step keeps the generator states around a region whose probability is not known yet (DropBlock seeds);
+    drawing that region later from the held state gives exactly what torch draws live at that point, and the masks after
+    it are still accepted."""
+    torch.manual_seed(77)
+    torch.rand(3)
+    shape_a, shape_h, shape_b = (2, 8, 21, 21), (2, 320, 6, 6), (2, 16, 10, 10)
+    bufs = [torch.empty(shape_a, dtype=torch.uint8), torch.empty(shape_b, dtype=torch.uint8)]
+    n_h = 2 * 320 * 6 * 6
+    pf = host_rng.MaskPrefetch([('draw', 'a', bufs[0], 0.9), ('hold', 'h', n_h), ('draw', 'b', bufs[1], 0.9)])
+    if not pf.ok:
+        pytest.skip("replay not available on this torch build")
+    assert pf.take('a', shape_a) is not None
+    before, after = pf.hold_state('h')
+    assert torch.equal(torch.get_rng_state(), before)
+    seeds = torch.empty(shape_h, dtype=torch.uint8)
+    state = before.clone()
+    ones = host_rng.replay_into(state, 0.0123, 1, seeds)
+    assert torch.equal(state, after) and torch.equal(torch.get_rng_state(), before)      # the live generator did not move
+    live = torch.bernoulli(torch.tensor(0.0123).expand(shape_h)).to(torch.uint8)            # what the reference draws here
+    assert torch.equal(live, seeds) and ones == int(live.sum())
+    assert torch.equal(torch.get_rng_state(), after)
+    assert pf.take('b', shape_b) is not None
