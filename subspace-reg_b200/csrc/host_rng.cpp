@@ -336,8 +336,10 @@ extern "C" int64_t sr_host_dropblock(const uint8_t* seeds, int64_t planes, int32
         return kept;
     };
     int workers = 4;
+    if (const char* e = getenv("SRB_RNG_THREADS")) workers = atoi(e);
     const int hw = (int)std::thread::hardware_concurrency();
     if (hw > 0 && workers > hw - 1) workers = hw - 1;
+    if (workers > 8) workers = 8;
     if (workers < 2 || planes * plane_out < (1 << 20)) return run(0, planes);
     std::vector<int64_t> part((size_t)workers, 0);
     std::vector<std::thread> pool;

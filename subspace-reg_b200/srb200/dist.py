@@ -19,6 +19,17 @@ def env_rank_world():
 def init(backend=None):
     """Initialise torch.distributed from the torchrun environment (no-op for a single process)."""
     rank, world, local = env_rank_world()
+    # Host threads of the mask generator (sr_host_bernoulli / sr_host_dropblock walkers): share the node's cores between
+    # the ranks instead of letting every rank assume it owns the machine.
+    if "SRB_RNG_THREADS" not in os.environ:
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        per_rank = cores // max(local_world, 1)
+        # main thread + prefetch thread + DropBlock thread come first; walkers get what is left, at most 4
+        os.environ["SRB_RNG_THREADS"] = str(max(0, min(4, per_rank - 3)))
     if world > 1 and not dist.is_initialized():
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
