@@ -234,8 +234,7 @@ def main():
         if rank != 0:
             return
         wdir = word_embed_dir()
-        for _ in range(0):   # the CPU path has no warm-up dependence worth minutes of wall time
-            pass
+        # (no warm-up: the CPU path has no warm-up dependence worth minutes of wall time)
         t_steps, n_steps, scored, t_score = 0.0, 0, 0, 0.0
         for k in range(args.steps):
             r = cpu_reference_sample(1 + k, 1, 64, args.cpu_epochs, wdir)
