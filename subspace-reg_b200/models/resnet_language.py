@@ -220,8 +220,8 @@ class ResNet(nn.Module):
         self.advance_block_counters(1)
         eng = self.engine()
         if self.training:
-            if torch.is_grad_enabled() and any(p.requires_grad for n, p in self.named_parameters()
-                                               if not n.startswith('classifier')):
+            head = {id(p) for p in self.classifier.parameters()} if self.num_classes > 0 else ()
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters() if id(p) not in head):
                 raise NotImplementedError("backbone training is outside the incremental-session path "
                                           "(use --freeze_backbone_at 1)")
             return eng.train_features(x, self.block_counters())
