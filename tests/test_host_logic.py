@@ -183,3 +183,42 @@ def test_episode_front_end_matches_the_reference_sampler(tmp_path):
                     assert np.array_equal(synthetic.image_ids(qx.numpy()), want['qry_ids'])
                 elif item == 0:
                     assert torch.equal(sx[:10], want['sup_x'])
+
+
+def test_crop_flip_parameters_reproduce_torchvision_on_the_host():
+    """dataset.transform_cfg.draw_crop_flip draws what torchvision's RandomCrop(84, padding=8) + RandomHorizontalFlip draw
+    (same order, same generator): applying its parameters with plain NumPy indexing gives the pixels of the reference's
+    support transform, and both leave torch's CPU generator in the same state.  (The GPU kernel applies the same
+    parameters: tests/test_gpu_kernels.py::test_support_augmentation_on_device_matches_torchvision.)"""
+    from dataset import transform_cfg
+    from dataset.mini_imagenet import _normalise
+    support_tf = transform_cfg.transforms_test_options['A'][0]
+    if support_tf is None:
+        pytest.skip("torchvision / PIL not installed")
+    rng = np.random.RandomState(1)
+    x8 = rng.randint(0, 256, size=(12, 84, 84, 3)).astype(np.uint8)
+    torch.manual_seed(99)
+    want = torch.stack([support_tf(img) for img in x8])
+    state = torch.get_rng_state()
+    torch.manual_seed(99)
+    ij, flip = transform_cfg.draw_crop_flip(12)
+    assert torch.equal(torch.get_rng_state(), state)
+    padded = np.zeros((12, 100, 100, 3), dtype=np.uint8)
+    padded[:, 8:92, 8:92] = x8
+    out = np.stack([padded[k, ij[k, 0]:ij[k, 0] + 84, ij[k, 1]:ij[k, 1] + 84] for k in range(12)])
+    out = np.stack([o[:, ::-1] if flip[k] else o for k, o in enumerate(out)])
+    assert torch.equal(_normalise(out), want)
+
+
+def test_rng_thread_share_between_local_ranks(monkeypatch):
+    """dist.init() divides the host cores between the local ranks for the mask-generator walkers."""
+    from srb200 import dist as sdist
+    monkeypatch.delenv("SRB_RNG_THREADS", raising=False)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(32)), raising=False)
+    sdist.init()
+    assert os.environ["SRB_RNG_THREADS"] == "1"          # 32 cores / 8 ranks = 4 per rank, 3 of them spoken for
+    monkeypatch.setenv("SRB_RNG_THREADS", "3")
+    sdist.init()
+    assert os.environ["SRB_RNG_THREADS"] == "3"          # an explicit setting wins
