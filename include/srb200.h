@@ -42,8 +42,10 @@ int32_t sr_check_device(int32_t dev);
 
 /* NCHW fp32 images -> NHWC bf16 with the channel dimension zero-padded to `cpad` (multiple of 16).
  * Replaces the implicit layout PyTorch's conv2d consumes (resnet_language.py:170-171). */
-int32_t sr_pack_input(const float* x_nchw, void* y_nhwc_bf16, int32_t batch, int32_t channels, int32_t height,
-                      int32_t width, int32_t cpad, void* stream);
+int32_t sr_pack_input(const float* x_nchw, void* y_nhwc_bf16, void* y_lo, int32_t batch, int32_t channels,
+                      int32_t height, int32_t width, int32_t cpad, void* stream);
+/* y_lo / w_lo / x_lo / out_lo below: the low bf16 plane of an error-compensated operand pair (see sr_conv_panel), same
+ * shape as the main output; NULL = plain bf16. */
 
 /* uint8 HWC images (the reference's image store, dataset/mini_imagenet.py:278-350) -> NHWC bf16 with the channel
  * dimension zero-padded to `cpad`, applying ToTensor (x / 255) and Normalize ((x - mean) / std, transform_cfg.py:8-10,
@@ -53,8 +55,8 @@ int32_t sr_pack_input(const float* x_nchw, void* y_nhwc_bf16, int32_t batch, int
  * crop_ij: DEVICE int32 [batch,2] = top-left corner of the height x width crop inside the image zero-padded by `pad`
  * on every side (RandomCrop(size, padding=pad)), or NULL; flip: DEVICE uint8 [batch] (RandomHorizontalFlip, applied
  * after the crop), or NULL. */
-int32_t sr_pack_input_u8(const uint8_t* x_nhwc_u8, void* y_nhwc_bf16, int32_t batch, int32_t channels, int32_t height,
-                         int32_t width, const float* mean_host, const float* std_host, int32_t cpad,
+int32_t sr_pack_input_u8(const uint8_t* x_nhwc_u8, void* y_nhwc_bf16, void* y_lo, int32_t batch, int32_t channels,
+                         int32_t height, int32_t width, const float* mean_host, const float* std_host, int32_t cpad,
                          const int32_t* crop_ij, const uint8_t* flip, int32_t pad, void* stream);
 
 /* BatchNorm eval-mode fold (resnet_language.py:250-255,148; nn.BatchNorm2d eval semantics):
@@ -64,13 +66,13 @@ int32_t sr_bn_fold(const float* gamma, const float* beta, const float* running_m
 
 /* Conv weight repack: OIHW fp32 [cout,cin,kh,kw] -> bf16 [cout][kh*kw][cin_pad] (zero padded), each output
  * channel optionally multiplied by scale[cout] (NULL = 1) before rounding (folded BN scale). */
-int32_t sr_pack_weight(const float* w_oihw, const float* scale, void* w_packed_bf16, int32_t cout, int32_t cin,
-                       int32_t kh, int32_t kw, int32_t cin_pad, void* stream);
+int32_t sr_pack_weight(const float* w_oihw, const float* scale, void* w_packed_bf16, void* w_lo, int32_t cout,
+                       int32_t cin, int32_t kh, int32_t kw, int32_t cin_pad, void* stream);
 
 /* AdaptiveAvgPool2d(1) on a bf16 NHWC map -> fp32 [batch, channels] (resnet_language.py:179-181 when the last block is
  * pooled, i.e. resnet12; resnet18's last block averages inside sr_conv / sr_bn_apply). */
-int32_t sr_global_avg(const void* x_nhwc_bf16, float* y, int32_t batch, int32_t height, int32_t width, int32_t channels,
-                      void* stream);
+int32_t sr_global_avg(const void* x_nhwc_bf16, const void* x_lo, float* y, int32_t batch, int32_t height, int32_t width,
+                      int32_t channels, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Backbone: implicit-GEMM convolution on tcgen05 / TMEM fed by TMA
@@ -88,6 +90,12 @@ typedef struct sr_conv_panel {
     const void* wgt;  /* bf16 [cout][taps][cin_pad] from sr_pack_weight                           */
     int32_t cin_pad;  /* channel pitch, multiple of 16                                            */
     int32_t taps;     /* 9 = 3x3 stride 1 pad 1,  1 = 1x1 stride 1                                */
+    /* Error-compensated ("bf16x3") mode, selected by act_lo != NULL on every panel: each operand is a PAIR of bf16
+     * tensors, hi = rn(x) and lo = rn(x - hi) (~17 mantissa bits together); the kernel accumulates hi*hi + hi*lo +
+     * lo*hi in fp32.  This is the parity tier for north_star's "bit-exact class predictions" against the reference's
+     * fp32 nn.Conv2d (resnet_language.py:249-254); 3x the tensor work of the plain bf16 mode. */
+    const void* act_lo; /* same shape as act, or NULL                                             */
+    const void* wgt_lo; /* same shape as wgt, or NULL                                             */
 } sr_conv_panel;
 
 typedef struct sr_conv_args {
@@ -96,9 +104,11 @@ typedef struct sr_conv_args {
     sr_conv_panel panel[2];
     const float* shift;      /* [cout] fp32 added to the accumulator (folded BN shift); NULL = 0        */
     const void* residual;    /* bf16 NHWC [batch,height,width,cout] added before the activation; or NULL */
+    const void* residual_lo; /* error-compensated mode: low plane of the residual                        */
     float slope;             /* LeakyReLU negative slope (0.1 in the reference)                          */
     int32_t epilogue;        /* SR_EPI_*                                                                 */
     void* out;               /* see SR_EPI_*                                                             */
+    void* out_lo;            /* error-compensated mode, bf16 outputs: low plane (same shape as out)      */
     double* stats;           /* SR_EPI_RAW_STATS only                                                    */
 } sr_conv_args;
 
@@ -127,12 +137,14 @@ typedef struct sr_bn_apply_args {
     const float* res_raw;   /* optional: fp32 NHWC raw output of the 1x1 downsample conv ...             */
     const float *res_mean, *res_invstd, *res_gamma, *res_beta; /* ... with its own batch-norm            */
     const void* res_act;    /* optional: bf16 NHWC identity residual                                     */
+    const void* res_act_lo; /* optional: its low plane (error-compensated mode)                          */
     int32_t lrelu;          /* apply LeakyReLU(slope) after the (optional) residual add                  */
     float slope;
     int32_t pool;           /* 0 none, 2 = MaxPool2d(2), -1 = global average (-> fp32 [B,C] in `out`)    */
     const uint8_t* keep;    /* optional NCHW uint8 [B,C,Ho,Wo] keep-mask applied AFTER pooling           */
     float keep_scale;       /* multiplier for kept elements (1/(1-p) for dropout, numel/kept for DropBlock) */
     void* out;              /* bf16 NHWC [B,Ho,Wo,C], or fp32 [B,C] when pool == -1                      */
+    void* out_lo;           /* optional: low plane of the bf16 output (error-compensated mode)           */
 } sr_bn_apply_args;
 
 int32_t sr_bn_apply(const sr_bn_apply_args* a, void* stream);
@@ -204,7 +216,13 @@ typedef struct sr_head_args {
     /* outputs */
     float* loss_trace;        /* [max_epochs][SR_TRACE_COLS]: total, ce_support, ce_memory, reg_base,     */
                               /*   reg_novel, pull, support top-1 hits, support top-5 hits (pre-update W) */
-    int32_t* status;          /* [4]: epochs run in this call, stopped flag, stable counter, reserved      */
+    int32_t* status;          /* [8]: epochs run in this call, stopped flag, stable counter, error flag,   */
+                              /*   epochs run in total (epoch0 + [0]), last loss (float bits), 0, 0        */
+    const int32_t* resume_status; /* optional: the `status` block of the PREVIOUS sr_head_run of this session, */
+                              /*   still on the device.  epoch0 / step0 / stable_count0 / prev_loss are then */
+                              /*   taken from it instead of the host values (and nothing runs if it says the */
+                              /*   stopping rule already fired), so consecutive calls chain without a host   */
+                              /*   read-back in between.  Must differ from `status`.                         */
     float* logits_support;    /* optional [n_support, n_classes]: logits of the LAST epoch (pre-update W)  */
     void* workspace;
     int64_t workspace_bytes;

@@ -27,6 +27,9 @@ CASES = {
                                      temperature=3.0)),
     "mapping_s2e2": (3, 2, 32, dict(max_novel_epochs=2, attraction_override="mapping_linear_label2image", glove=True,
                                     label_pull=0.1)),
+    # DropBlock with the reference's default block_size = 5 (no --no_dropblock), and the Adam branch of get_optim
+    "dropblock_s2e3": (4, 2, 32, dict(max_novel_epochs=3, no_dropblock=False)),
+    "adam_s2e3": (5, 2, 32, dict(max_novel_epochs=3, adam=True, weight_decay=5e-3)),
 }
 
 

@@ -26,9 +26,12 @@ def reference_modules():
     for k in list(saved_mods):
         del sys.modules[k]
     saved = (torch.Tensor.cuda, torch.nn.Module.cuda, torch.cuda.is_available)
+    saved_capturing = torch.cuda.is_current_stream_capturing
     torch.Tensor.cuda = lambda self, *a, **k: self
     torch.nn.Module.cuda = lambda self, *a, **k: self
     torch.cuda.is_available = lambda: True
+    # torch.optim.Adam.step asks whether a CUDA graph is being captured whenever "CUDA is available" (the shim above)
+    torch.cuda.is_current_stream_capturing = lambda: False
     sys.path.insert(0, REF)
     try:
         models_util = importlib.import_module('models.util')
@@ -46,6 +49,7 @@ def reference_modules():
     finally:
         sys.path.remove(REF)
         torch.Tensor.cuda, torch.nn.Module.cuda, torch.cuda.is_available = saved
+        torch.cuda.is_current_stream_capturing = saved_capturing
         for k in [k for k in sys.modules if k.split('.')[0] in ('models', 'eval', 'dataset', 'util', 'configs')]:
             del sys.modules[k]
         sys.modules.update(saved_mods)

@@ -78,9 +78,9 @@ def run_sessions(sd, world, n_sessions=None, schedule='literal', ckpt=None, mode
             acc1 = accuracy(out, base_y, (1, 5))[0]
         T.score_s += time.perf_counter() - t0
         T.images_scored += base_x.shape[0]
-        return float(np.mean([acc1[0].item()])), torch.argmax(out, 1)
+        return float(np.mean([acc1[0].item()])), torch.argmax(out, 1), out
 
-    acc_base0, _ = eval_base_imgs()                                    # :128
+    acc_base0, _, _ = eval_base_imgs()                                    # :128
     rec['weighted'].append(acc_base0)
     rec['base0'] = acc_base0
     iter_num = n_sessions if n_sessions is not None else (8 if opt.continual else opt.neval_episodes)   # :132-136
@@ -238,7 +238,7 @@ def run_sessions(sd, world, n_sessions=None, schedule='literal', ckpt=None, mode
                 mem_x = torch.cat((mem_x, support_xs[inds, :]), 0)
                 mem_y = torch.cat((mem_y, support_ys_id[inds]), 0)
         sd['classifier.weight'] = W.detach()
-        acc_base_, base_pred = eval_base_imgs()                        # :362-367
+        acc_base_, base_pred, base_logits = eval_base_imgs()                        # :362-367
         test_acc_r = [round(i.item(), 2) for i in test_acc]            # :370-376
         test_acc_m = float(np.array(test_acc_r).mean())
         acc_base_sum += acc_base_
@@ -251,7 +251,8 @@ def run_sessions(sd, world, n_sessions=None, schedule='literal', ckpt=None, mode
         rec['base'].append(round(acc_base_, 2))
         srec = dict(epochs=epoch - 1, terms=np.asarray(terms, dtype=np.float64), W=W.detach().clone(),
                     novel_session_acc=test_acc_r, query_pred=[p.clone() for p in test_preds],
-                    query_logits=[q.clone() for q in q_logits], base_pred=base_pred.clone(), acc_base=acc_base_,
+                    query_logits=[q.clone() for q in q_logits], base_pred=base_pred.clone(), base_logits=base_logits.clone(),
+                    acc_base=acc_base_,
                     memory_inds=inds.copy() if opt.memory_replay else None, vocab_novel=list(vocab_novel))
         if keep_w_trajectory:
             srec['W_traj'] = torch.stack(w_traj)

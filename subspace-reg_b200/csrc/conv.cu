@@ -44,6 +44,8 @@ constexpr int kEpiThreads = 256;
 constexpr int kSubRows = 128;       // UMMA M
 constexpr int kStagePitchBf16 = 80; // bytes per staged row (32 bf16 + pad, conflict-free 16-byte accesses)
 constexpr int kStagePitchF32 = 33;  // floats per staged row (32 fp32 + 1)
+constexpr int kMaxPanels = 6;       // 2 for plain bf16; 2 x 3 in the error-compensated mode (hi*hi + hi*lo + lo*hi)
+constexpr int kLoStaging = 2 * kSubRows * kStagePitchBf16;   // byte offset of the "lo" half rows in the staging tile
 
 struct PanelDev {
     CUtensorMap tmA;  // rank 4: (C, W, H, N); box (KC, TW, TH, TN), or the tall box (KC, TW, 2*TH+2, 1) when `reuse`
@@ -57,7 +59,7 @@ struct PanelDev {
 };
 
 struct ConvParams {
-    PanelDev panel[2];
+    PanelDev panel[kMaxPanels];
     int n_panels;
     int B, H, W, Cout;
     int TW, TH, TN, stack_h;
@@ -77,7 +79,9 @@ struct ConvParams {
     int Ho, Wo;
     const float* shift;
     const __nv_bfloat16* residual;
+    const __nv_bfloat16* residual_lo;   // error-compensated mode: low halves of the residual / the outputs
     void* out;
+    void* out_lo;
     double* stats;
     long long* trace;   // SRB_CONV_DBG & 16: clock64 stamps of CTA 0, [tile][8 events]
 };
@@ -167,7 +171,14 @@ struct TileIter {
 // Persistent kernel: one CTA per SM loops over (pixel tile, channel split) work items.  The TMA producer runs ahead across
 // tile boundaries, the MMA warp only waits for a free TMEM accumulator stage, so the epilogue of tile i overlaps the
 // loads (and, when TMEM has room for a second accumulator, the MMAs) of tile i+1.
+//
+// kPrecise: error-compensated operands.  Every activation / weight tensor is a pair of bf16 planes (hi = rn(x),
+// lo = rn(x - hi), together ~17 mantissa bits); each input panel is issued as three (hi*hi, hi*lo, lo*hi) into the same
+// fp32 TMEM accumulator and the epilogue splits its fp32 result into the two output planes.  Same pipeline, 3x the MMAs:
+// this is the parity tier (north_star: predictions bit-exact against the fp32 reference), not the throughput path.
+template <bool kPrecise>
 __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
+    constexpr int kPanelUnroll = kPrecise ? 1 : 2;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // Dynamic shared memory is only guaranteed 16-byte aligned; swizzle-128B tiles need 1024.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -227,8 +238,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl, it.next(p)) {
             const TileCoord tc = it.coord(p);
             SRB_TRACE(0);
-#pragma unroll
-            for (int pi = 0; pi < 2; ++pi) {
+#pragma unroll kPanelUnroll
+            for (int pi = 0; pi < (kPrecise ? kMaxPanels : 2); ++pi) {
                 if (pi >= p.n_panels) break;
                 const PanelDev& pn = p.panel[pi];
                 const int kc = pn.kc_bytes >> 1;
@@ -290,8 +301,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             if (warp == 1) SRB_TRACE(3);
             const uint32_t acc = tmem_base + (uint32_t)(as * acc_cols + sub * p.n_cta);
             uint32_t accum = 0u;
-#pragma unroll
-            for (int pi = 0; pi < 2; ++pi) {
+#pragma unroll kPanelUnroll
+            for (int pi = 0; pi < (kPrecise ? kMaxPanels : 2); ++pi) {
                 if (pi >= p.n_panels) break;
                 const PanelDev& pn = p.panel[pi];
                 const int reuse = pn.reuse;
@@ -400,6 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             const size_t origin = ((size_t)tc.n0 * p.H + tc.h0) * p.W + tc.w0;   // pixel index of the tile origin
             const size_t pix = origin + own_rel;
             __nv_bfloat16* const t_base = reinterpret_cast<__nv_bfloat16*>(p.out) + origin * p.Cout + tc.co0;
+            __nv_bfloat16* const t_base_lo = reinterpret_cast<__nv_bfloat16*>(p.out_lo) + origin * p.Cout + tc.co0;
             bool t_ok[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) t_ok[i] = (tc.n0 + t_nl[i] < p.B) && (tc.h0 + t_hl[i] < p.H) && !(p.dbg & 1);
@@ -456,6 +468,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                             v[8 * j + 2 * k + 1] += __bfloat162float(b2.y);
                         }
                     }
+                    if (kPrecise) {
+                        const uint4* rl = reinterpret_cast<const uint4*>(p.residual_lo + pix * p.Cout + cbase);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint4 r = __ldg(rl + j);
+                            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[k]);
+                                v[8 * j + 2 * k] += __bfloat162float(b2.x);
+                                v[8 * j + 2 * k + 1] += __bfloat162float(b2.y);
+                            }
+                        }
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = lrelu(v[j], p.slope);
@@ -470,6 +496,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                         sts128(my_row + (uint32_t)((c16 & 16) * 2 + 16 * j),
                                make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                                           pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7])));
+                    if (kPrecise) {   // what bf16 rounding dropped, as a second bf16 plane
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] -= __bfloat162float(__float2bfloat16_rn(v[j]));
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            sts128(my_row + (uint32_t)(kLoStaging + (c16 & 16) * 2 + 16 * j),
+                                   make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                              pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7])));
+                    }
                 }
             };
 
@@ -495,6 +530,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         if (t_ok[i]) *reinterpret_cast<uint4*>(t_base + t_rel[i] + c32) = x[i];
+                    if (kPrecise) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) x[i] = lds128(t_rows + (uint32_t)(kLoStaging + 8 * i * kStagePitchBf16));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (t_ok[i]) *reinterpret_cast<uint4*>(t_base_lo + t_rel[i] + c32) = x[i];
+                    }
                     __syncwarp();   // the rows are rewritten by the next chunk
                 } else if (p.epi == SR_EPI_ACT_POOL2) {
                     named_bar_sync(1, kEpiThreads);
@@ -514,6 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                         const int wp = (tc.w0 >> 1) + pw;
                         if (pn >= p.B || hp >= p.Ho || wp >= p.Wo) continue;
                         uint4 acc4 = make_uint4(0, 0, 0, 0);
+                        float best[8];   // kPrecise: the window maximum of hi + lo
 #pragma unroll
                         for (int dy = 0; dy < 2; ++dy) {
 #pragma unroll
@@ -532,7 +575,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                                 }
                                 const int mrow = psub * kSubRows + (nloc * p.TH + hloc) * p.TW + ww;
                                 const uint4 x = lds128(stg_s + (uint32_t)(mrow * kStagePitchBf16 + g * 16));
-                                if (dy == 0 && dx == 0) {
+                                if (kPrecise) {
+                                    const uint4 xl = lds128(stg_s + (uint32_t)(kLoStaging + mrow * kStagePitchBf16 + g * 16));
+                                    const uint32_t hh[4] = {x.x, x.y, x.z, x.w}, ll[4] = {xl.x, xl.y, xl.z, xl.w};
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&hh[k]);
+                                        const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&ll[k]);
+                                        const float f0 = __bfloat162float(h2.x) + __bfloat162float(l2.x);
+                                        const float f1 = __bfloat162float(h2.y) + __bfloat162float(l2.y);
+                                        best[2 * k] = (dy == 0 && dx == 0) ? f0 : fmaxf(best[2 * k], f0);
+                                        best[2 * k + 1] = (dy == 0 && dx == 0) ? f1 : fmaxf(best[2 * k + 1], f1);
+                                    }
+                                } else if (dy == 0 && dx == 0) {
                                     acc4 = x;
                                 } else {
                                     acc4.x = max_bf16x2(acc4.x, x.x);
@@ -542,8 +597,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                                 }
                             }
                         }
-                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                           (((size_t)pn * p.Ho + hp) * p.Wo + wp) * p.Cout + tc.co0 + c32 + g * 8;
+                        const size_t o_off = (((size_t)pn * p.Ho + hp) * p.Wo + wp) * p.Cout + tc.co0 + c32 + g * 8;
+                        if (kPrecise) {
+                            acc4 = make_uint4(pack_bf16(best[0], best[1]), pack_bf16(best[2], best[3]),
+                                              pack_bf16(best[4], best[5]), pack_bf16(best[6], best[7]));
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) best[k] -= __bfloat162float(__float2bfloat16_rn(best[k]));
+                            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out_lo) + o_off) =
+                                make_uint4(pack_bf16(best[0], best[1]), pack_bf16(best[2], best[3]),
+                                           pack_bf16(best[4], best[5]), pack_bf16(best[6], best[7]));
+                        }
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + o_off;
                         *reinterpret_cast<uint4*>(o) = acc4;
                     }
                     named_bar_sync(1, kEpiThreads);
@@ -689,11 +753,47 @@ struct ConvPlan {
     int staging, shift_bytes, dyn_smem;
 };
 
-int32_t plan_conv(const sr_conv_args* a, int max_dyn, ConvPlan* plan) {
+// One internal K panel: plain mode = the caller's panels; error-compensated mode = three per caller panel.
+struct PanelIn {
+    const void* act;
+    const void* wgt;
+    int cin_pad, taps;
+};
+
+int expand_panels(const sr_conv_args* a, PanelIn* out) {
+    int n = 0;
+    const bool precise = a->panel[0].act_lo != nullptr;
+    for (int i = 0; i < a->n_panels; ++i) {
+        const sr_conv_panel& sp = a->panel[i];
+        out[n++] = PanelIn{sp.act, sp.wgt, sp.cin_pad, sp.taps};
+        if (precise) {
+            out[n++] = PanelIn{sp.act, sp.wgt_lo, sp.cin_pad, sp.taps};
+            out[n++] = PanelIn{sp.act_lo, sp.wgt, sp.cin_pad, sp.taps};
+        }
+    }
+    return n;
+}
+
+int32_t check_conv_args(const sr_conv_args* a) {
     if (!a) return fail(SR_E_ARG, "sr_conv: null args");
     if (a->n_panels < 1 || a->n_panels > 2) return fail(SR_E_ARG, "sr_conv: n_panels must be 1 or 2");
     if (a->batch < 1 || a->height < 1 || a->width < 1) return fail(SR_E_ARG, "sr_conv: empty input");
     if (a->epilogue < SR_EPI_ACT || a->epilogue > SR_EPI_RAW_STATS) return fail(SR_E_ARG, "sr_conv: bad epilogue");
+    const bool precise = a->panel[0].act_lo != nullptr;
+    for (int i = 0; i < a->n_panels; ++i)
+        if ((a->panel[i].act_lo != nullptr) != precise || (a->panel[i].wgt_lo != nullptr) != precise)
+            return fail(SR_E_ARG, "sr_conv: error-compensated mode needs act_lo and wgt_lo on every panel");
+    return SR_OK;
+}
+
+int32_t plan_conv(const sr_conv_args* a, int max_dyn, ConvPlan* plan) {
+    {
+        const int32_t rc = check_conv_args(a);
+        if (rc != SR_OK) return rc;
+    }
+    const bool precise = a->panel[0].act_lo != nullptr;
+    PanelIn pin[kMaxPanels];
+    const int n_in = expand_panels(a, pin);
     // N split
     int ns = 0;
     for (int c = 1; c <= 16; ++c) {
@@ -711,7 +811,7 @@ int32_t plan_conv(const sr_conv_args* a, int max_dyn, ConvPlan* plan) {
     Tile& tile = plan->tile;
     if (!pick_tile(a->height, a->width, a->epilogue, &tile))
         return fail(SR_E_ARG, "sr_conv: no tile for %dx%d epilogue %d", a->height, a->width, a->epilogue);
-    p.n_panels = a->n_panels;
+    p.n_panels = n_in;
     p.B = a->batch;
     p.H = a->height;
     p.W = a->width;
@@ -730,7 +830,9 @@ int32_t plan_conv(const sr_conv_args* a, int max_dyn, ConvPlan* plan) {
     p.Wo = a->epilogue == SR_EPI_ACT_POOL2 ? a->width / 2 : a->width;
     p.shift = a->shift;
     p.residual = static_cast<const __nv_bfloat16*>(a->residual);
+    p.residual_lo = static_cast<const __nv_bfloat16*>(a->residual_lo);
     p.out = a->out;
+    p.out_lo = a->out_lo;
     p.stats = a->stats;
     if (2 * p.n_cta > 512) return fail(SR_E_ARG, "sr_conv: accumulators need %d TMEM columns", 2 * p.n_cta);
     p.acc_stages = std::min(4, 512 / (2 * p.n_cta));   // as many accumulator stages as TMEM holds
@@ -739,14 +841,14 @@ int32_t plan_conv(const sr_conv_args* a, int max_dyn, ConvPlan* plan) {
     p.n_splits = ns;
 
     int staging = 0;   // the producer prefetches the next tile during the epilogue: staging cannot alias the pipeline
-    if (a->epilogue == SR_EPI_ACT_POOL2 || a->epilogue == SR_EPI_ACT) staging = 2 * kSubRows * kStagePitchBf16;
+    if (a->epilogue == SR_EPI_ACT_POOL2 || a->epilogue == SR_EPI_ACT) staging = (precise ? 2 : 1) * kLoStaging;
     if (a->epilogue == SR_EPI_ACT_AVG) staging = 2 * kSubRows * kStagePitchF32 * 4;
     p.staging_bytes = staging;
     const int shift_bytes = a->epilogue == SR_EPI_RAW_STATS ? 0 : (int)align_up((int64_t)a->cout * 4, 16);
     const int budget = max_dyn - 1024 - staging - shift_bytes;
 
-    for (int i = 0; i < a->n_panels; ++i) {
-        const sr_conv_panel& sp = a->panel[i];
+    for (int i = 0; i < n_in; ++i) {
+        const PanelIn& sp = pin[i];
         if (sp.cin_pad < 16 || sp.cin_pad % 16) return fail(SR_E_ARG, "sr_conv: cin_pad must be a multiple of 16");
         if (sp.taps != 9 && sp.taps != 1) return fail(SR_E_ARG, "sr_conv: taps must be 9 or 1");
         // Tap reuse: a row-stacked tile of one image (84x84 / 42x42 maps) covers 2*TH consecutive image rows, so one tall
@@ -757,7 +859,7 @@ int32_t plan_conv(const sr_conv_args* a, int max_dyn, ConvPlan* plan) {
     // that starts at its last tap offset) followed by one weight tile per tap of the stage.
     auto stage_bytes_for = [&](int kcb, int* b_off) {
         int a_rows = 0, b_tiles = 0;
-        for (int i = 0; i < a->n_panels; ++i) {
+        for (int i = 0; i < n_in; ++i) {
             const int rows = p.panel[i].reuse ? std::max(2 * kSubRows, (tile.TH + 2) * tile.TW + kSubRows) : 2 * kSubRows;
             a_rows = std::max(a_rows, rows);
             b_tiles = std::max(b_tiles, p.panel[i].reuse ? 3 : 1);
@@ -770,12 +872,12 @@ int32_t plan_conv(const sr_conv_args* a, int max_dyn, ConvPlan* plan) {
     // quarter of the shared-memory bandwidth of 128-byte rows (two / one rows per 128-byte wavefront instead of four), so
     // the widest rows always win; if the tall-box stage does not leave three stages in flight at that width (N = 160
     // layers: 103 KB per stage), give up tap reuse rather than row width.
-    const int kc_cap = kc_bytes_for(a->panel[0].cin_pad);
+    const int kc_cap = kc_bytes_for(pin[0].cin_pad);
     int kc0 = kc_cap;
     {
         int off;
         if (budget / stage_bytes_for(kc_cap, &off) < 3 && !getenv("SRB_KEEP_REUSE"))
-            for (int i = 0; i < a->n_panels; ++i) p.panel[i].reuse = 0;
+            for (int i = 0; i < n_in; ++i) p.panel[i].reuse = 0;
     }
     if (const char* e = getenv("SRB_KC_BYTES")) {
         const int v = atoi(e);
@@ -785,8 +887,8 @@ int32_t plan_conv(const sr_conv_args* a, int max_dyn, ConvPlan* plan) {
     p.n_stages = std::min(8, budget / p.stage_bytes);
     if (p.n_stages < 2) return fail(SR_E_ARG, "sr_conv: pipeline does not fit in shared memory");
     p.sub_stride = kSubRows * kc0;
-    for (int i = 0; i < a->n_panels; ++i) {
-        const sr_conv_panel& sp = a->panel[i];
+    for (int i = 0; i < n_in; ++i) {
+        const PanelIn& sp = pin[i];
         PanelDev& pd = p.panel[i];
         pd.taps = sp.taps;
         pd.cin_pad = sp.cin_pad;
@@ -803,6 +905,38 @@ int32_t plan_conv(const sr_conv_args* a, int max_dyn, ConvPlan* plan) {
 }
 
 constexpr int kStaticSmemEstimate = 3072;   // conv_umma_kernel's static shared memory (ptxas -v); used when no device is present
+
+// Per-device launch state (function attributes are per context; the SM count is per device): no process-wide assumption
+// that every GPU is the one first seen.
+struct DeviceState {
+    std::once_flag once;
+    cudaError_t err = cudaSuccess;
+    int max_dyn = 0;
+    int num_sms = 0;
+    long long* trace_buf = nullptr;   // SRB_CONV_DBG & 16 only
+};
+constexpr int kMaxDevices = 64;
+DeviceState g_dev[kMaxDevices];
+
+DeviceState* device_state() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    DeviceState* st = &g_dev[dev];
+    std::call_once(st->once, [st, dev] {
+        cudaFuncAttributes fa, fb;
+        st->err = cudaFuncGetAttributes(&fa, conv_umma_kernel<false>);
+        if (st->err != cudaSuccess) return;
+        st->err = cudaFuncGetAttributes(&fb, conv_umma_kernel<true>);
+        if (st->err != cudaSuccess) return;
+        st->max_dyn = 227 * 1024 - (int)std::max(fa.sharedSizeBytes, fb.sharedSizeBytes);  // static + dynamic <= 227 KB per CTA
+        st->err = cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_dyn);
+        if (st->err != cudaSuccess) return;
+        st->err = cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st->max_dyn);
+        if (st->err != cudaSuccess) return;
+        st->err = cudaDeviceGetAttribute(&st->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    });
+    return st;
+}
 
 }  // namespace
 
@@ -822,37 +956,36 @@ extern "C" int32_t sr_conv_plan(const sr_conv_args* a, int32_t* out16) {
 
 extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-    if (!a) return fail(SR_E_ARG, "sr_conv: null args");
-    if (a->n_panels < 1 || a->n_panels > 2) return fail(SR_E_ARG, "sr_conv: n_panels must be 1 or 2");
-    if (a->batch < 1 || a->height < 1 || a->width < 1) return fail(SR_E_ARG, "sr_conv: empty input");
-    if (a->epilogue < SR_EPI_ACT || a->epilogue > SR_EPI_RAW_STATS) return fail(SR_E_ARG, "sr_conv: bad epilogue");
+    {
+        const int32_t rc = check_conv_args(a);
+        if (rc != SR_OK) return rc;
+    }
     if (a->epilogue == SR_EPI_RAW_STATS && !a->stats) return fail(SR_E_ARG, "sr_conv: RAW_STATS needs stats");
     if (!a->out) return fail(SR_E_ARG, "sr_conv: null out");
+    const bool precise = a->panel[0].act_lo != nullptr;
+    if (precise && (a->epilogue == SR_EPI_ACT || a->epilogue == SR_EPI_ACT_POOL2) && !a->out_lo)
+        return fail(SR_E_ARG, "sr_conv: error-compensated mode needs out_lo for bf16 outputs");
+    if (precise && a->residual && !a->residual_lo)
+        return fail(SR_E_ARG, "sr_conv: error-compensated mode needs residual_lo with residual");
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) return fail(SR_E_DEVICE, "sr_conv: cuTensorMapEncodeTiled not available from the driver");
 
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    static int max_dyn = 0;
-    std::call_once(attr_once, [] {
-        cudaFuncAttributes fa;
-        attr_err = cudaFuncGetAttributes(&fa, conv_umma_kernel);
-        if (attr_err != cudaSuccess) return;
-        max_dyn = 227 * 1024 - (int)fa.sharedSizeBytes;  // static + dynamic <= 227 KB per CTA
-        attr_err = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
-    });
-    if (attr_err != cudaSuccess)
-        return fail(SR_E_CUDA, "sr_conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+    DeviceState* ds = device_state();
+    if (!ds) return fail(SR_E_DEVICE, "sr_conv: no current CUDA device");
+    if (ds->err != cudaSuccess)
+        return fail(SR_E_CUDA, "sr_conv: kernel attribute set-up failed: %s", cudaGetErrorString(ds->err));
 
     ConvPlan plan;
     {
-        const int32_t rc = plan_conv(a, max_dyn, &plan);
+        const int32_t rc = plan_conv(a, ds->max_dyn, &plan);
         if (rc != SR_OK) return rc;
     }
     ConvParams& p = plan.p;
     const Tile& tile = plan.tile;
-    for (int i = 0; i < a->n_panels; ++i) {
-        const sr_conv_panel& sp = a->panel[i];
+    PanelIn pin[kMaxPanels];
+    const int n_in = expand_panels(a, pin);
+    for (int i = 0; i < n_in; ++i) {
+        const PanelIn& sp = pin[i];
         PanelDev& pd = p.panel[i];
         if (!sp.act || !sp.wgt) return fail(SR_E_ARG, "sr_conv: null panel pointer");
         if ((reinterpret_cast<uintptr_t>(sp.act) | reinterpret_cast<uintptr_t>(sp.wgt)) & 15)
@@ -883,28 +1016,23 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
     }
     const int dyn_smem = plan.dyn_smem;
 
-
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    dim3 grid((unsigned)std::min(p.total_tiles, num_sms), 1, 1);
-    static long long* trace_buf = nullptr;
+    dim3 grid((unsigned)std::min(p.total_tiles, ds->num_sms), 1, 1);
     if (p.dbg & 16) {
-        if (!trace_buf) cudaMalloc(&trace_buf, 96 * 8 * sizeof(long long));
-        cudaMemsetAsync(trace_buf, 0, 96 * 8 * sizeof(long long), stream);
-        p.trace = trace_buf;
+        if (!ds->trace_buf) cudaMalloc(&ds->trace_buf, 96 * 8 * sizeof(long long));   // debugging aid only (SRB_CONV_DBG)
+        cudaMemsetAsync(ds->trace_buf, 0, 96 * 8 * sizeof(long long), stream);
+        p.trace = ds->trace_buf;
     }
-    conv_umma_kernel<<<grid, kThreads, dyn_smem, stream>>>(p);
+    if (precise)
+        conv_umma_kernel<true><<<grid, kThreads, dyn_smem, stream>>>(p);
+    else
+        conv_umma_kernel<false><<<grid, kThreads, dyn_smem, stream>>>(p);
     SR_CUDA_OK(cudaGetLastError());
     if (p.dbg & 16) {
         static int dumped = 0;
         if (dumped++ == 4) {   // a warm launch
             long long h[96 * 8];
             cudaStreamSynchronize(stream);
-            cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+            cudaMemcpy(h, ds->trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
             fprintf(stderr, "trace (cycles since first event; stages %d x %d B, acc stages %d, tiles/CTA %d)\n", p.n_stages,
                     p.stage_bytes, p.acc_stages, p.total_tiles / (int)grid.x);
             fprintf(stderr, "tile  prod_start prod_end | mma_wait mma_go mma_done | epi_wait epi_go epi_done\n");

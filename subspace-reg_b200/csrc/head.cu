@@ -229,6 +229,11 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) 
     const int n_tasksA = n_gemmA + n_pull + has_base + has_prev;
     const int tilesC_m = (C + BT - 1) / BT, tilesC_n = (d + BT - 1) / BT;
     const int n_tasksC = tilesC_m * tilesC_n;
+    const HeadStart st = head_start(a);
+    if (st.already_stopped) {   // chained launch after the stopping rule fired: nothing to do (every CTA takes this exit)
+        if (blockIdx.x == 0 && tid == 0) head_write_status(a, st, 0, 1, st.stable_count0, st.prev_loss, 0);
+        return;
+    }
 
     for (int e = 0; e < a.max_epochs; ++e) {
         // ============================ phase A ============================
@@ -331,13 +336,13 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) 
                 tr[0] = loss; tr[1] = ce_s; tr[2] = ce_m; tr[3] = reg_b; tr[4] = reg_n; tr[5] = pull;
                 tr[6] = (float)h1; tr[7] = (float)h5;
                 int stop = 0;
-                int sc = e == 0 ? a.stable_count0 : p.ctrl->stable_count;
-                const float prev = e == 0 ? a.prev_loss : p.ctrl->prev_loss;
+                int sc = e == 0 ? st.stable_count0 : p.ctrl->stable_count;
+                const float prev = e == 0 ? st.prev_loss : p.ctrl->prev_loss;
                 if (a.stable) {
                     if (fabs((double)loss - (double)prev) < a.convergence_epsilon) sc += 1; else sc = 0;
                     if (sc == a.stable_epochs) stop = 1;
                 }
-                const int epoch = a.epoch0 + e + 1;
+                const int epoch = st.epoch0 + e + 1;
                 if (epoch >= a.max_novel_epochs ||
                     ((double)loss <= a.target_train_loss && epoch >= a.min_novel_epochs + 1))
                     stop = 1;
@@ -353,11 +358,11 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) 
             const float np_ = has_prev ? (float)sqrt(p.ctrl->norm_prev_sq) : 0.f;
             const float sb = nb > 0.f ? a.lmbd_base / nb : 0.f;    // d||x||/dx = x/||x||, 0 at x = 0 (as torch)
             const float sn = np_ > 0.f ? a.lmbd_novel / np_ : 0.f;
-            const int step = a.step0 + e;  // optimiser steps already taken
+            const int step = st.step0 + e;  // optimiser steps already taken
             float bc1 = 1.f, bc2s = 1.f;
             if (a.optimizer == SR_OPT_ADAM) {
-                bc1 = 1.f - powf(a.beta1, (float)(step + 1));
-                bc2s = sqrtf(1.f - powf(a.beta2, (float)(step + 1)));
+                bc1 = (float)(1.0 - pow((double)a.beta1, (double)(step + 1)));
+                bc2s = (float)sqrt(1.0 - pow((double)a.beta2, (double)(step + 1)));
             }
             const int64_t wsize = (int64_t)C * d;
             for (int t = blockIdx.x; t < n_tasksC; t += gridDim.x) {
@@ -402,10 +407,9 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) 
         if (s_flag) break;
     }
     if (blockIdx.x == 0 && tid == 0) {
-        a.status[0] = p.ctrl->epochs_done;
-        a.status[1] = p.ctrl->stop;
-        a.status[2] = p.ctrl->stable_count;
-        a.status[3] = p.ctrl->error;
+        const int done = p.ctrl->epochs_done;
+        head_write_status(a, st, done, p.ctrl->stop, done > 0 ? p.ctrl->stable_count : st.stable_count0,
+                          done > 0 ? p.ctrl->prev_loss : st.prev_loss, p.ctrl->error);
     }
 }
 
@@ -618,6 +622,8 @@ extern "C" int32_t sr_head_run(const sr_head_args* a, void* stream_v) {
         return fail(SR_E_ARG, "sr_head_run: reserve rows exceed n_classes");
     if (a->optimizer != SR_OPT_SGD && a->optimizer != SR_OPT_ADAM) return fail(SR_E_ARG, "sr_head_run: bad optimizer");
     if (reinterpret_cast<uintptr_t>(a->workspace) & 255) return fail(SR_E_ARG, "sr_head_run: workspace must be 256-byte aligned");
+    if (a->resume_status && a->resume_status == a->status)
+        return fail(SR_E_ARG, "sr_head_run: resume_status must be a different block than status");
     // Paper-sized problems: everything constant over the session stays in shared memory (head_small.cu).
     if (srb::head_small_applicable(a)) return srb::head_small_run(a, stream);
     const HeadLayout L = head_layout(a);

@@ -68,6 +68,40 @@ struct HeadCtrl {          // lives at the start of the workspace (zeroed by the
     double norm_prev_sq;   // ||W[nb:nb+np] - Wres||_F^2
 };
 
+// Where this launch starts: the host's values, or - chained launches - the previous launch's status block on the device.
+struct HeadStart {
+    int epoch0, step0, stable_count0;
+    float prev_loss;
+    bool already_stopped;
+};
+} // namespace srb
+#include "../../include/srb200.h"
+namespace srb {
+__device__ __forceinline__ HeadStart head_start(const sr_head_args& a) {
+    HeadStart s;
+    s.epoch0 = a.epoch0; s.step0 = a.step0; s.stable_count0 = a.stable_count0; s.prev_loss = a.prev_loss;
+    s.already_stopped = false;
+    if (a.resume_status != nullptr) {
+        s.already_stopped = a.resume_status[1] != 0;
+        s.stable_count0 = a.resume_status[2];
+        s.epoch0 = a.resume_status[4];
+        s.step0 = a.resume_status[4];
+        s.prev_loss = __int_as_float(a.resume_status[5]);
+    }
+    return s;
+}
+__device__ __forceinline__ void head_write_status(const sr_head_args& a, const HeadStart& st, int epochs_done, int stop,
+                                                  int stable_count, float last_loss, int error) {
+    a.status[0] = epochs_done;
+    a.status[1] = stop;
+    a.status[2] = stable_count;
+    a.status[3] = error;
+    a.status[4] = st.epoch0 + epochs_done;
+    a.status[5] = __float_as_int(last_loss);
+    a.status[6] = 0;
+    a.status[7] = 0;
+}
+
 __device__ __forceinline__ void grid_barrier(HeadCtrl* ctrl, unsigned int& target) {
     __syncthreads();
     if (threadIdx.x == 0) {

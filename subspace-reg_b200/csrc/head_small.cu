@@ -80,7 +80,7 @@ __device__ __forceinline__ int64_t feat_row(const sr_head_args& a, int r) {
 }
 
 // Loss of epoch `e` from the partial results in the workspace + the reference's stopping rule.  One CTA.
-__device__ void assemble_loss(const SmallParams& p, int e, double* red) {
+__device__ void assemble_loss(const SmallParams& p, const HeadStart& st, int e, double* red) {
     const sr_head_args& a = p.a;
     const int par = e & 1;
     const int tid = threadIdx.x;
@@ -115,13 +115,13 @@ __device__ void assemble_loss(const SmallParams& p, int e, double* red) {
         float* tr = a.loss_trace + (int64_t)e * SR_TRACE_COLS;
         tr[0] = loss; tr[1] = ce_s; tr[2] = ce_m; tr[3] = reg_b; tr[4] = reg_n; tr[5] = pull; tr[6] = (float)h1; tr[7] = (float)h5;
         int stop = 0;
-        int sc = e == 0 ? a.stable_count0 : p.ctrl->stable_count;
-        const float prev = e == 0 ? a.prev_loss : p.ctrl->prev_loss;
+        int sc = e == 0 ? st.stable_count0 : p.ctrl->stable_count;
+        const float prev = e == 0 ? st.prev_loss : p.ctrl->prev_loss;
         if (a.stable) {
             if (fabs((double)loss - (double)prev) < a.convergence_epsilon) sc += 1; else sc = 0;
             if (sc == a.stable_epochs) stop = 1;
         }
-        const int epoch = a.epoch0 + e + 1;
+        const int epoch = st.epoch0 + e + 1;
         if (epoch >= a.max_novel_epochs || ((double)loss <= a.target_train_loss && epoch >= a.min_novel_epochs + 1)) stop = 1;
         p.ctrl->stable_count = sc;
         p.ctrl->prev_loss = loss;
@@ -147,6 +147,11 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
     const bool fixed = a.pull_mode == SR_PULL_FIXED;
     const int new0 = C - a.n_new;
     const int n_opt = a.optimizer == SR_OPT_ADAM ? 2 : 1;
+    const HeadStart st = head_start(a);
+    if (st.already_stopped) {   // chained launch after the stopping rule fired: nothing to do (every CTA takes this exit)
+        if (is_loss && tid == 0) head_write_status(a, st, 0, 1, st.stable_count0, st.prev_loss, 0);
+        return;
+    }
 
     // ---- shared memory carve-up ----
     float* sp = reinterpret_cast<float*>(dyn);
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
         unsigned long long ts0 = 0, ts1 = 0, ts2 = 0, ts3 = 0;
         if ((cta == 0 || is_loss || is_pull) && tid == 0) ts0 = global_ns();
         // ======================= phase 1 =======================
-        if (is_loss && e > 0) assemble_loss(p, e - 1, red);   // a CTA of its own: off the row CTAs' critical path
+        if (is_loss && e > 0) assemble_loss(p, st, e - 1, red);   // a CTA of its own: off the row CTAs' critical path
         if (is_row) {
             float acc[R][4];
 #pragma unroll
@@ -464,7 +469,7 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
             const float nb = has_base ? (float)sqrt(nbs) : 0.f, nn = has_prev ? (float)sqrt(nns) : 0.f;
             const float sb = nb > 0.f ? a.lmbd_base / nb : 0.f;
             const float sn = nn > 0.f ? a.lmbd_novel / nn : 0.f;
-            const int step = a.step0 + e;
+            const int step = st.step0 + e;
             float bc1 = 1.f, bc2s = 1.f;
             if (a.optimizer == SR_OPT_ADAM) {
                 bc1 = (float)(1.0 - pow((double)a.beta1, (double)(step + 1)));
@@ -545,7 +550,7 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
         }
     }
     // ---- tail: loss of the last applied epoch when the loop ran out of epochs; write back optimiser state ----
-    if (!stopped && is_loss && e > 0) assemble_loss(p, e - 1, red);
+    if (!stopped && is_loss && e > 0) assemble_loss(p, st, e - 1, red);
     if (is_col) {
         for (int i = tid; i < C * DC; i += kT) {
             const int c = i / DC, j = i % DC;
@@ -555,10 +560,9 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
     if (is_loss) {
         __syncthreads();
         if (tid == 0) {
-            a.status[0] = p.ctrl->epochs_done;
-            a.status[1] = p.ctrl->stop;
-            a.status[2] = p.ctrl->stable_count;
-            a.status[3] = p.ctrl->error;
+            const int done = p.ctrl->epochs_done;
+            head_write_status(a, st, done, p.ctrl->stop, done > 0 ? p.ctrl->stable_count : st.stable_count0,
+                              done > 0 ? p.ctrl->prev_loss : st.prev_loss, p.ctrl->error);
         }
     }
 }

@@ -9,9 +9,22 @@ using namespace srb;
 
 __device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
 
+// Error-compensated operands (see sr_conv_panel): hi = rn(x), lo = rn(x - hi).
+__device__ __forceinline__ void store8_split(const float* v, __nv_bfloat16* hi, __nv_bfloat16* lo) {
+    __align__(16) __nv_bfloat16 h[8];
+    __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        h[j] = __float2bfloat16_rn(v[j]);
+        l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+    }
+    *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(h);
+    if (lo) *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(l);
+}
+
 // ---- NCHW fp32 -> NHWC bf16, channels zero-padded to cpad ----------------------------------------------------
-__global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t npix_total,
-                                  int C, int HW, int cpad) {
+__global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                  __nv_bfloat16* __restrict__ y_lo, int64_t npix_total, int C, int HW, int cpad) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // pixel index over (n, h, w)
     if (i >= npix_total) return;
     const int64_t n = i / HW;
@@ -19,13 +32,13 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
     const float* src = x + n * C * HW + hw;
     __nv_bfloat16* dst = y + i * cpad;
     for (int c0 = 0; c0 < cpad; c0 += 8) {
-        __align__(16) __nv_bfloat16 v[8];
+        float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = c0 + j;
-            v[j] = __float2bfloat16_rn(c < C ? src[(int64_t)c * HW] : 0.f);
+            v[j] = c < C ? src[(int64_t)c * HW] : 0.f;
         }
-        *reinterpret_cast<uint4*>(dst + c0) = *reinterpret_cast<const uint4*>(v);
+        store8_split(v, dst + c0, y_lo ? y_lo + i * cpad + c0 : nullptr);
     }
 }
 
@@ -34,9 +47,10 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __nv_bfloat16* __
 struct NormParams {
     float mean[4], stdev[4];
 };
-__global__ void pack_input_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t npix_total, int C,
-                                     int H, int W, int cpad, NormParams np, const int32_t* __restrict__ crop_ij,
-                                     const uint8_t* __restrict__ flip, int pad) {
+__global__ void pack_input_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                     __nv_bfloat16* __restrict__ y_lo, int64_t npix_total, int C, int H, int W, int cpad,
+                                     NormParams np, const int32_t* __restrict__ crop_ij, const uint8_t* __restrict__ flip,
+                                     int pad) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // output pixel index over (n, h, w)
     if (i >= npix_total) return;
     // RandomCrop(size, padding=pad) + RandomHorizontalFlip of the reference's support transform, applied while reading:
@@ -58,7 +72,7 @@ __global__ void pack_input_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat1
     const uint8_t* src = x + (n * hw + (int64_t)h * W + w) * C;
     __nv_bfloat16* dst = y + i * cpad;
     for (int c0 = 0; c0 < cpad; c0 += 8) {
-        __align__(16) __nv_bfloat16 v[8];
+        float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = c0 + j;
@@ -67,9 +81,9 @@ __global__ void pack_input_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat1
                 f = __fdiv_rn(inside ? (float)src[c] : 0.f, 255.0f);
                 f = __fdiv_rn(__fsub_rn(f, np.mean[c]), np.stdev[c]);
             }
-            v[j] = __float2bfloat16_rn(f);
+            v[j] = f;
         }
-        *reinterpret_cast<uint4*>(dst + c0) = *reinterpret_cast<const uint4*>(v);
+        store8_split(v, dst + c0, y_lo ? y_lo + i * cpad + c0 : nullptr);
     }
 }
 
@@ -84,7 +98,8 @@ __global__ void bn_fold_kernel(const float* gamma, const float* beta, const floa
 
 // ---- OIHW fp32 -> [cout][taps][cin_pad] bf16 (optionally scaled per output channel) ---------------------------
 __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale,
-                                   __nv_bfloat16* __restrict__ out, int cout, int cin, int taps, int cin_pad) {
+                                   __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo, int cout, int cin,
+                                   int taps, int cin_pad) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t total = (int64_t)cout * taps * cin_pad;
     if (i >= total) return;
@@ -96,7 +111,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
         v = w[((int64_t)co * cin + ci) * taps + tap];
         if (scale) v *= scale[co];
     }
-    out[i] = __float2bfloat16_rn(v);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = h;
+    if (out_lo) out_lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
 // ---- train-mode BN statistics -> mean / invstd, running-stat EMA ---------------------------------------------
@@ -146,6 +163,17 @@ __device__ __forceinline__ void bn_pixel(const sr_bn_apply_args& a, int64_t pix,
             const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rr[k]);
             y[2 * k] += __bfloat162float(b2.x);
             y[2 * k + 1] += __bfloat162float(b2.y);
+        }
+        if (a.res_act_lo) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(a.res_act_lo) +
+                                                                  pix * a.channels + c0));
+            const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&qq[k]);
+                y[2 * k] += __bfloat162float(b2.x);
+                y[2 * k + 1] += __bfloat162float(b2.y);
+            }
         }
     }
     if (a.lrelu) {
@@ -204,11 +232,9 @@ __global__ void bn_apply_kernel(const BnApplyParams p) {
             y[j] = k ? y[j] * a.keep_scale : 0.f;
         }
     }
-    __align__(16) __nv_bfloat16 o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(y[j]);
-    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out) + (((int64_t)n * p.Ho + ho) * p.Wo + wo) * a.channels + c0) =
-        *reinterpret_cast<const uint4*>(o);
+    const int64_t o_off = (((int64_t)n * p.Ho + ho) * p.Wo + wo) * a.channels + c0;
+    store8_split(y, static_cast<__nv_bfloat16*>(a.out) + o_off,
+                 a.out_lo ? static_cast<__nv_bfloat16*>(a.out_lo) + o_off : nullptr);
 }
 
 // pool -1: one thread per (n, 8-channel group): mask, then mean over H x W -> fp32 [B, C]
@@ -245,44 +271,50 @@ __global__ void bn_apply_avg_kernel(const BnApplyParams p) {
 }
 
 // bf16 NHWC [B,H,W,C] -> fp32 [B,C] mean over H x W (AdaptiveAvgPool2d(1) after a pooled last block: resnet12)
-__global__ void global_avg_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int B, int HW, int C) {
+__global__ void global_avg_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ x_lo,
+                                  float* __restrict__ y, int B, int HW, int C) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * C) return;
     const int c = (int)(i % C);
     const int64_t n = i / C;
     float acc = 0.f;
-    for (int q = 0; q < HW; ++q) acc += __bfloat162float(x[(n * HW + q) * C + c]);
+    for (int q = 0; q < HW; ++q) {
+        float v = __bfloat162float(x[(n * HW + q) * C + c]);
+        if (x_lo) v += __bfloat162float(x_lo[(n * HW + q) * C + c]);
+        acc += v;
+    }
     y[i] = acc / (float)HW;
 }
 
 }  // namespace
 
-extern "C" int32_t sr_global_avg(const void* x_nhwc_bf16, float* y, int32_t batch, int32_t height, int32_t width,
-                                 int32_t channels, void* stream_v) {
+extern "C" int32_t sr_global_avg(const void* x_nhwc_bf16, const void* x_lo, float* y, int32_t batch, int32_t height,
+                                 int32_t width, int32_t channels, void* stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     if (!x_nhwc_bf16 || !y || batch < 1 || height < 1 || width < 1 || channels < 1)
         return fail(SR_E_ARG, "sr_global_avg: bad arguments");
     const int64_t total = (int64_t)batch * channels;
-    global_avg_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x_nhwc_bf16), y,
-                                                                          batch, height * width, channels);
+    global_avg_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x_nhwc_bf16), static_cast<const __nv_bfloat16*>(x_lo), y, batch, height * width,
+        channels);
     SR_CUDA_OK(cudaGetLastError());
     return SR_OK;
 }
 
-extern "C" int32_t sr_pack_input(const float* x, void* y, int32_t batch, int32_t channels, int32_t height, int32_t width,
-                                 int32_t cpad, void* stream_v) {
+extern "C" int32_t sr_pack_input(const float* x, void* y, void* y_lo, int32_t batch, int32_t channels, int32_t height,
+                                 int32_t width, int32_t cpad, void* stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     if (!x || !y || batch < 1 || channels < 1 || cpad < channels || cpad % 8)
         return fail(SR_E_ARG, "sr_pack_input: bad arguments");
     const int64_t npix = (int64_t)batch * height * width;
     const int threads = 256;
     pack_input_kernel<<<(unsigned)((npix + threads - 1) / threads), threads, 0, stream>>>(
-        x, static_cast<__nv_bfloat16*>(y), npix, channels, height * width, cpad);
+        x, static_cast<__nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(y_lo), npix, channels, height * width, cpad);
     SR_CUDA_OK(cudaGetLastError());
     return SR_OK;
 }
 
-extern "C" int32_t sr_pack_input_u8(const uint8_t* x, void* y, int32_t batch, int32_t channels, int32_t height,
+extern "C" int32_t sr_pack_input_u8(const uint8_t* x, void* y, void* y_lo, int32_t batch, int32_t channels, int32_t height,
                                     int32_t width, const float* mean_host, const float* std_host, int32_t cpad,
                                     const int32_t* crop_ij, const uint8_t* flip, int32_t pad, void* stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
@@ -298,7 +330,8 @@ extern "C" int32_t sr_pack_input_u8(const uint8_t* x, void* y, int32_t batch, in
     const int threads = 256;
     if (pad < 0 || (crop_ij && pad > 64)) return fail(SR_E_ARG, "sr_pack_input_u8: bad padding");
     pack_input_u8_kernel<<<(unsigned)((npix + threads - 1) / threads), threads, 0, stream>>>(
-        x, static_cast<__nv_bfloat16*>(y), npix, channels, height, width, cpad, np, crop_ij, flip, pad);
+        x, static_cast<__nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(y_lo), npix, channels, height, width, cpad, np, crop_ij,
+        flip, pad);
     SR_CUDA_OK(cudaGetLastError());
     return SR_OK;
 }
@@ -312,15 +345,15 @@ extern "C" int32_t sr_bn_fold(const float* gamma, const float* beta, const float
     return SR_OK;
 }
 
-extern "C" int32_t sr_pack_weight(const float* w, const float* scale, void* out, int32_t cout, int32_t cin, int32_t kh,
-                                  int32_t kw, int32_t cin_pad, void* stream_v) {
+extern "C" int32_t sr_pack_weight(const float* w, const float* scale, void* out, void* out_lo, int32_t cout, int32_t cin,
+                                  int32_t kh, int32_t kw, int32_t cin_pad, void* stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     if (!w || !out || cout < 1 || cin < 1 || cin_pad < cin || kh != kw || (kh != 1 && kh != 3))
         return fail(SR_E_ARG, "sr_pack_weight: bad arguments");
     const int64_t total = (int64_t)cout * kh * kw * cin_pad;
     const int threads = 256;
     pack_weight_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
-        w, scale, static_cast<__nv_bfloat16*>(out), cout, cin, kh * kw, cin_pad);
+        w, scale, static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo), cout, cin, kh * kw, cin_pad);
     SR_CUDA_OK(cudaGetLastError());
     return SR_OK;
 }

@@ -82,17 +82,25 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
     if opt.freeze_backbone_at != 1:
         raise NotImplementedError("freeze_backbone_at != 1 trains the backbone, which is outside the incremental-session path")
     record = dict(sessions=[], timers=dict(train_s=0.0, score_s=0.0, backbone_imgs=0, steps=0, images_scored=0),
-                  phases=dict(setup=0.0, train_pass=0.0, head1=0.0, cache=0.0, head=0.0, score=0.0, memory=0.0))
+                  phases=dict(setup=0.0, train_pass=0.0, head1=0.0, cache=0.0, head=0.0, score=0.0))
     ph = record['phases']
+    # Phase times are DEVICE times between CUDA events on the current stream, resolved once at the end of the run: a
+    # session is queued without any host synchronisation (the host only waits once per session, for its results).
+    phase_events = []
 
-    def _tick():
-        torch.cuda.synchronize()
-        return time.perf_counter()
+    def _mark():
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
     few_shot_finetune_incremental_test.last_record = record
+    net._last_record = record            # (the function attribute is shared between threads; this one is not)
     tm = record['timers']
 
     acc_novel, acc_base = [AverageMeter() for _ in range(2)]
     weighted_avg_l, acc_novel_list, acc_base_list = [[] for _ in range(3)]
+
+    if getattr(opt, 'conv_precision', None):     # 'bf16' | 'bf16x3' (not a reference flag: the B200 precision tier)
+        net.set_conv_precision(opt.conv_precision)
 
     torch.manual_seed(opt.set_seed)
     np.random.seed(opt.set_seed)
@@ -121,10 +129,12 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         memory = Memory()
 
     # Initial validation on base samples.
-    t0 = time.perf_counter()
+    ev0 = _mark()
     acc_base_ = eval_base(net, (base_x, base_y), criterion)
-    tm['score_s'] += time.perf_counter() - t0
+    phase_events.append(('score', ev0, _mark()))
     tm['images_scored'] += base_x.shape[0]
+    base_y_host = base_batch[1].squeeze(0).cpu().numpy()
+    confusion_run = torch.zeros((100, 100), dtype=torch.int64, device=dev)   # (gold, predicted) over every scoring of the run
     weighted_avg_l.append(acc_base_)
     record['base0'] = acc_base_
 
@@ -171,10 +181,12 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         query_xs_d = query_xs.cuda(non_blocking=True)
         if novel_query_collection_id is None:
             novel_query_collection = [query_xs_d]
-            novel_query_collection_id = [query_ys_id.cuda()]
+            novel_query_collection_id = [query_ys_id.cuda(non_blocking=True)]
+            query_ids_host = [query_ys_id.numpy()]
         else:
             novel_query_collection.append(query_xs_d)
-            novel_query_collection_id.append(query_ys_id.cuda())
+            novel_query_collection_id.append(query_ys_id.cuda(non_blocking=True))
+            query_ids_host.append(query_ys_id.numpy())
 
         if base_support_loader is not None:
             support_ys_id = torch.cat([support_ys_id, torch.from_numpy(base_support_ys)])
@@ -232,8 +244,8 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         counters0 = next(iter(net.block_counters().values()))
 
         # ---- epoch 1: the session's only train-mode forward(s); BN running statistics move here ----
-        tp0 = _tick()
-        ph['setup'] += tp0 - t_train0
+        tp0 = _mark()
+        ph['setup'] += time.perf_counter() - t_train0
         f_train = net.features(support_xs_d)
         if has_mem:
             f_train = torch.cat([f_train, net.features(memory.data)], 0)
@@ -250,8 +262,7 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
                 if opt.memory_replay == 1:
                     fwds.append((0, n_mem + 25 * (j - idx)))
             net.engine().start_mask_prefetch(fwds)
-        tp1 = _tick()
-        ph['train_pass'] += tp1 - tp0
+        tp1 = _mark()
         W = net.classifier.weight.data
         reserve = novel_weight_to_reserve.contiguous() if (opt.lmbd_reg_novel is not None and idx > 0) else None
         head = ops.HeadSession(
@@ -261,31 +272,51 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
             pull_mode=pull_mode, pull=pull_t, q_rows=q_rows,
             lmbd_base=opt.lmbd_reg_transform_w or 0.0, lmbd_novel=opt.lmbd_reg_novel or 0.0,
             gamma=opt.label_pull if use_pull else 0.0, adam=bool(opt.adam), lr=opt.learning_rate, momentum=opt.momentum,
-            weight_decay=opt.weight_decay, stable=opt.stable, convergence_epsilon=opt.convergence_epsilon,
+            weight_decay=0.0005 if opt.adam else opt.weight_decay,   # get_optim (eval/util.py:92-102) hard-codes Adam's
+            stable=opt.stable, convergence_epsilon=opt.convergence_epsilon,
             stable_epochs=opt.stable_epochs, target_train_loss=opt.target_train_loss,
             min_novel_epochs=opt.min_novel_epochs, max_novel_epochs=opt.max_novel_epochs)
-        head.run(1)
+        head.run(1, defer=True)
         net.eval()                                  # validate()'s side effect after epoch 1
-        tp2 = _tick()
-        ph['head1'] += tp2 - tp1
+        tp2 = _mark()
 
         # ---- eval-mode feature cache: support | memory | queries of sessions 1..idx+1 | base batch ----
         parts = [support_xs_d] + ([memory.data] if has_mem else []) + novel_query_collection + [base_x]
         with torch.no_grad():
             cache = net.engine().eval_features(torch.cat(parts, 0))
         tm['backbone_imgs'] += cache.shape[0]
-        tp3 = _tick()
-        ph['cache'] += tp3 - tp2
+        tp3 = _mark()
         q_row0 = n_sup + n_mem
-        b_row0 = q_row0 + sum(q.shape[0] for q in novel_query_collection)
+        n_query = sum(q.shape[0] for q in novel_query_collection)
+        b_row0 = q_row0 + n_query
 
-        # ---- epochs 2.. on the device until the stopping rule fires ----
-        while not head.stopped:
-            head.run(max(opt.max_novel_epochs - head.epochs, 1), feat=cache, support_row0=0, memory_row0=n_sup)
-        ph['head'] += _tick() - tp3
+        # ---- epochs 2.. on the device until the stopping rule fires (chained to epoch 1 on the device) ----
+        head.run(max(opt.max_novel_epochs - 1, 1), feat=cache, support_row0=0, memory_row0=n_sup, defer=True)
+        tp4 = _mark()
+
+        # ---- scoring of the last epoch: validate (:321-326) + eval_base (:362-367) on cached features, ONE launch over
+        # the queries of every session so far and the base batch (contiguous rows of the cache) ----
+        labels_all = torch.cat(novel_query_collection_id + [base_y])
+        confusion = torch.zeros((100, 100), dtype=torch.int64, device=dev)   # (gold id, predicted id) of this session
+        scored = ops.eval_logits(cache[q_row0:b_row0 + base_x.shape[0]], net.classifier.weight.detach(), labels_all, confusion)
+        confusion_run += confusion
+        tp5 = _mark()
+        phase_events += [('train_pass', tp0, tp1), ('head1', tp1, tp2), ('cache', tp2, tp3), ('head', tp3, tp4),
+                         ('score', tp4, tp5)]
+
+        # ---- the session's one host synchronisation: epoch counts, loss trace, predictions ----
+        head.collect()
+        while not head.stopped:                     # (only if the chained launch ran out of epochs before the rule fired)
+            head.run(max(opt.max_novel_epochs - head.epochs, 1))
+            scored = None
+        if scored is None:
+            confusion_run -= confusion
+            confusion.zero_()
+            scored = ops.eval_logits(cache[q_row0:b_row0 + base_x.shape[0]], net.classifier.weight.detach(), labels_all, confusion)
+            confusion_run += confusion
+        pred_all = scored["pred"].cpu().numpy().astype(np.int64)
         trace = torch.cat(head.traces, 0).numpy()
         epoch = head.epochs + 1
-        torch.cuda.synchronize()
         tm['train_s'] += time.perf_counter() - t_train0
         tm['steps'] += head.epochs
         # the reference's every-10th-epoch log lines, formatted in one go (fp32 percentages like `percent`)
@@ -307,23 +338,20 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         done = next(iter(net.block_counters().values())) - counters0
         net.advance_block_counters(n_calls - done)
 
-        # ---- scoring of the last epoch: validate (:321-326) + eval_base (:362-367) on cached features ----
-        t0 = time.perf_counter()
         test_acc, query_ys_pred, query_logits = [], [], []
-        confusion = torch.zeros((100, 100), dtype=torch.int64, device=dev)   # (gold id, predicted id) of this session
-        r0 = q_row0
-        for qx, qy in zip(novel_query_collection, novel_query_collection_id):
-            a1, a5, loss_q, pred, raw = _score(net, cache[r0:r0 + qx.shape[0]], qy, confusion)
-            test_acc.append(a1[0])
+        r0 = 0
+        for qx, qy_h in zip(novel_query_collection, query_ids_host):
+            nq = qx.shape[0]
+            pred = pred_all[r0:r0 + nq]
+            test_acc.append(percent(int((pred == qy_h).sum()), nq)[0])
             query_ys_pred.append(pred)
-            query_logits.append(raw["logits"])
-            r0 += qx.shape[0]
-        a1, _, _, base_pred, _ = _score(net, cache[b_row0:b_row0 + base_x.shape[0]], base_y, confusion)
-        acc_base_ = np.mean([a1[0].item()])
-        record['confusion'] = confusion
-        tm['score_s'] += time.perf_counter() - t0
-        ph['score'] += time.perf_counter() - t0
-        tm['images_scored'] += b_row0 - q_row0 + base_x.shape[0]
+            query_logits.append(scored["logits"][r0:r0 + nq])
+            r0 += nq
+        base_pred = pred_all[r0:r0 + base_x.shape[0]]
+        acc_base_ = np.mean([percent(int((base_pred == base_y_host).sum()), base_x.shape[0])[0].item()])
+        record['confusion_last'] = confusion
+        record['confusion'] = confusion_run
+        tm['images_scored'] += n_query + base_x.shape[0]
 
         if opt.memory_replay:
             inds = np.random.choice(opt.n_shots, opt.memory_replay)
@@ -361,6 +389,10 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
                             if 'running_' in k or 'num_batches_tracked' in k})
         record['sessions'].append(sess)
 
+    torch.cuda.current_stream().synchronize()
+    for name, e0, e1 in phase_events:
+        ph[name] += e0.elapsed_time(e1) * 1e-3
+    tm['score_s'] = ph['score']
     record.update(weighted=weighted_avg_l, novel=acc_novel_list, base=acc_base_list, acc_novel_avg=acc_novel.avg,
                   acc_base_avg=acc_base.avg, counters=net.block_counters())
     print("Overall continual accuracies: ", weighted_avg_l)

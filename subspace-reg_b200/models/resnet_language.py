@@ -182,13 +182,19 @@ class ResNet(nn.Module):
             for bi, m in enumerate(layer):
                 out.append(dict(prefix='layer%d.%d' % (li + 1, bi), mod=m, cin=m.conv1.weight.shape[1],
                                 cout=m.conv1.weight.shape[0], pool=m.stride, downsample=m.downsample is not None,
-                                drop_block=bool(m.drop_block), block_size=m.block_size))
+                                drop_block=bool(m.drop_block), block_size=m.block_size, drop_rate=float(m.drop_rate)))
         return out
 
     def engine(self):
         if self._engine is None:
-            self._engine = BackboneEngine(self._blocks())
+            self._engine = BackboneEngine(self._blocks(), precision=getattr(self, '_conv_precision', None))
         return self._engine
+
+    def set_conv_precision(self, precision):
+        """'bf16' (one tensor-core pass, the throughput tier) or 'bf16x3' (error-compensated operand pairs, three passes
+        into one fp32 accumulator: the parity tier against the reference's fp32 convolutions)."""
+        self._conv_precision = precision
+        self.engine().set_precision(precision)
 
     def __deepcopy__(self, memo):
         import copy
@@ -236,7 +242,7 @@ class ResNet(nn.Module):
         if is_feat:
             if self.training:
                 raise NotImplementedError("is_feat=True is only available in eval mode")
-            maps = [t.permute(0, 3, 1, 2).float() for t in taps]
+            maps = [(t[0].float() + t[1].float() if t.dim() == 5 else t.float()).permute(0, 3, 1, 2) for t in taps]
             return maps + [feat], out
         return out
 

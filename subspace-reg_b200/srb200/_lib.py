@@ -23,15 +23,16 @@ EXPORTS = [
 
 
 class ConvPanel(C.Structure):
-    _fields_ = [("act", C.c_void_p), ("wgt", C.c_void_p), ("cin_pad", C.c_int32), ("taps", C.c_int32)]
+    _fields_ = [("act", C.c_void_p), ("wgt", C.c_void_p), ("cin_pad", C.c_int32), ("taps", C.c_int32),
+                ("act_lo", C.c_void_p), ("wgt_lo", C.c_void_p)]
 
 
 class ConvArgs(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("cout", C.c_int32),
         ("n_panels", C.c_int32), ("panel", ConvPanel * 2),
-        ("shift", C.c_void_p), ("residual", C.c_void_p), ("slope", C.c_float), ("epilogue", C.c_int32),
-        ("out", C.c_void_p), ("stats", C.c_void_p),
+        ("shift", C.c_void_p), ("residual", C.c_void_p), ("residual_lo", C.c_void_p), ("slope", C.c_float),
+        ("epilogue", C.c_int32), ("out", C.c_void_p), ("out_lo", C.c_void_p), ("stats", C.c_void_p),
     ]
 
 
@@ -40,8 +41,9 @@ class BnApplyArgs(C.Structure):
         ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("channels", C.c_int32),
         ("raw", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
         ("res_raw", C.c_void_p), ("res_mean", C.c_void_p), ("res_invstd", C.c_void_p), ("res_gamma", C.c_void_p),
-        ("res_beta", C.c_void_p), ("res_act", C.c_void_p), ("lrelu", C.c_int32), ("slope", C.c_float),
-        ("pool", C.c_int32), ("keep", C.c_void_p), ("keep_scale", C.c_float), ("out", C.c_void_p),
+        ("res_beta", C.c_void_p), ("res_act", C.c_void_p), ("res_act_lo", C.c_void_p), ("lrelu", C.c_int32),
+        ("slope", C.c_float), ("pool", C.c_int32), ("keep", C.c_void_p), ("keep_scale", C.c_float), ("out", C.c_void_p),
+        ("out_lo", C.c_void_p),
     ]
 
 
@@ -58,7 +60,7 @@ class HeadArgs(C.Structure):
         ("max_epochs", C.c_int32), ("epoch0", C.c_int32), ("stable", C.c_int32), ("stable_epochs", C.c_int32),
         ("stable_count0", C.c_int32), ("min_novel_epochs", C.c_int32), ("max_novel_epochs", C.c_int32),
         ("convergence_epsilon", C.c_double), ("target_train_loss", C.c_double), ("prev_loss", C.c_float),
-        ("loss_trace", C.c_void_p), ("status", C.c_void_p), ("logits_support", C.c_void_p),
+        ("loss_trace", C.c_void_p), ("status", C.c_void_p), ("resume_status", C.c_void_p), ("logits_support", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
@@ -92,11 +94,11 @@ def load():
     lib.sr_check_device.restype = i32
     lib.sr_check_device.argtypes = [i32]
     lib.sr_pack_input.restype = i32
-    lib.sr_pack_input.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.sr_pack_input.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.sr_bn_fold.restype = i32
     lib.sr_bn_fold.argtypes = [vp, vp, vp, vp, f32, vp, vp, i32, vp]
     lib.sr_pack_weight.restype = i32
-    lib.sr_pack_weight.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.sr_pack_weight.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.sr_conv.restype = i32
     lib.sr_conv.argtypes = [C.POINTER(ConvArgs), vp]
     lib.sr_bn_finalize.restype = i32
@@ -118,11 +120,11 @@ def load():
     lib.sr_sgd_update.restype = i32
     lib.sr_sgd_update.argtypes = [vp, vp, i64, f32, f32, vp]
     lib.sr_global_avg.restype = i32
-    lib.sr_global_avg.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.sr_global_avg.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     lib.sr_host_bernoulli.restype = i64
     lib.sr_host_bernoulli.argtypes = [vp, i64, i32, C.c_double, i64, vp]
     lib.sr_pack_input_u8.restype = i32
-    lib.sr_pack_input_u8.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), i32, vp, vp, i32, vp]
+    lib.sr_pack_input_u8.argtypes = [vp, vp, vp, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), i32, vp, vp, i32, vp]
     lib.sr_conv_plan.restype = i32
     lib.sr_conv_plan.argtypes = [C.POINTER(ConvArgs), C.POINTER(C.c_int32)]
     lib.sr_host_dropblock.restype = i64

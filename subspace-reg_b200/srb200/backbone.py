@@ -4,6 +4,7 @@ The arithmetic is in libsrb200.so (sr_pack_input / sr_pack_weight / sr_bn_fold /
 sr_bn_apply); this module only owns buffers and launch order.  Reference semantics: BasicBlock.forward
 (models/resnet_language.py:268-301), ResNet.forward (:170-181), nn.BatchNorm2d eval/train.
 """
+import os
 import threading
 
 import torch
@@ -16,7 +17,6 @@ from . import ops
 SLOPE = 0.1
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
-DROP_RATE = 0.1
 
 
 _PINNED_POOL = {}
@@ -33,9 +33,14 @@ class BackboneEngine(object):
     `blocks` is the module's list of block descriptors: dict(prefix, mod, cin, cout, pool, downsample, drop_block,
     block_size) where `mod` carries conv1..3 / bn1..3 / downsample as parameter containers."""
 
-    def __init__(self, blocks, chunk=1024):
+    def __init__(self, blocks, chunk=1024, precision=None):
         self.blocks = blocks
         self.chunk = chunk
+        # 'bf16': one tcgen05 pass on bf16 operands (throughput tier, features ~3e-3 from fp32);
+        # 'bf16x3': error-compensated operand pairs, three passes into the same fp32 accumulator (parity tier, ~1e-5)
+        self.precision = precision or os.environ.get("SRB_CONV_PRECISION", "bf16")
+        if self.precision not in ("bf16", "bf16x3"):
+            raise ValueError("srb200: conv precision must be 'bf16' or 'bf16x3', got %r" % (self.precision,))
         self._folded = None      # per block: dict(w1, s1, w2, s2, w3, s3[, wd])
         self._raw = None         # per block: unscaled packed weights (train-mode pass)
         self._fold_key = None
@@ -63,6 +68,17 @@ class BackboneEngine(object):
     def invalidate(self):
         self._fold_key = None
 
+    @property
+    def split(self):
+        return self.precision == "bf16x3"
+
+    def set_precision(self, precision):
+        if precision not in ("bf16", "bf16x3"):
+            raise ValueError("srb200: conv precision must be 'bf16' or 'bf16x3', got %r" % (precision,))
+        if precision != self.precision:
+            self.precision = precision
+            self._folded = self._raw = self._fold_key = None
+
     def _ensure_folded(self):
         key = self._bn_key()
         if self._folded is not None and key == self._fold_key:
@@ -73,12 +89,12 @@ class BackboneEngine(object):
             d = {}
             for i, (cv, bn) in enumerate(((m.conv1, m.bn1), (m.conv2, m.bn2), (m.conv3, m.bn3))):
                 scale, shift = ops.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, BN_EPS)
-                d['w%d' % (i + 1)] = ops.pack_weight(cv.weight.detach(), scale, _pad16(cv.weight.shape[1]))
+                d['w%d' % (i + 1)] = ops.pack_weight(cv.weight.detach(), scale, _pad16(cv.weight.shape[1]), split=self.split)
                 d['s%d' % (i + 1)] = shift
             if b['downsample']:
                 cv, bn = m.downsample[0], m.downsample[1]
                 scale, shift = ops.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, BN_EPS)
-                d['wd'] = ops.pack_weight(cv.weight.detach(), scale, _pad16(cv.weight.shape[1]))
+                d['wd'] = ops.pack_weight(cv.weight.detach(), scale, _pad16(cv.weight.shape[1]), split=self.split)
                 d['s3'] = d['s3'] + shift      # both branches land in one accumulator: shifts add
             folded.append(d)
         self._folded = folded
@@ -92,10 +108,11 @@ class BackboneEngine(object):
         raw = []
         for b in self.blocks:
             m = b['mod']
-            d = {('w%d' % (i + 1)): ops.pack_weight(cv.weight.detach(), None, _pad16(cv.weight.shape[1]))
+            d = {('w%d' % (i + 1)): ops.pack_weight(cv.weight.detach(), None, _pad16(cv.weight.shape[1]), split=self.split)
                  for i, cv in enumerate((m.conv1, m.conv2, m.conv3))}
             if b['downsample']:
-                d['wd'] = ops.pack_weight(m.downsample[0].weight.detach(), None, _pad16(m.downsample[0].weight.shape[1]))
+                d['wd'] = ops.pack_weight(m.downsample[0].weight.detach(), None, _pad16(m.downsample[0].weight.shape[1]),
+                                          split=self.split)
             raw.append(d)
         self._raw = (key, raw)
 
@@ -112,14 +129,13 @@ class BackboneEngine(object):
             outs.append(self._eval_chunk(x[i0:i0 + step].contiguous(), taps))
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
-    @staticmethod
-    def pack(x):
+    def pack(self, x):
         """fp32 NCHW (already normalised, the reference's loader output) or uint8 NHWC (the raw image store: ToTensor +
         Normalize are fused into the packing kernel) -> NHWC bf16, 16 channels."""
         if x.dtype == torch.uint8:
             from dataset import transform_cfg
-            return ops.pack_input_u8(x.contiguous(), transform_cfg.mean, transform_cfg.std, 16)
-        return ops.pack_input(x.contiguous(), 16)
+            return ops.pack_input_u8(x.contiguous(), transform_cfg.mean, transform_cfg.std, 16, split=self.split)
+        return ops.pack_input(x.contiguous(), 16, split=self.split)
 
     def _eval_chunk(self, x, taps):
         h = self.pack(x)
@@ -161,19 +177,21 @@ class BackboneEngine(object):
             size = 84
             for bi, b in enumerate(self.blocks):
                 size = size // b['pool']
+                if not b.get('drop_rate', 0.1) > 0:      # BasicBlock.forward: `if self.drop_rate > 0` (resnet_language.py:292)
+                    continue
                 if b['drop_block']:
                     bs = b['block_size']
                     steps.append(('hold', (f, bi), batch * b['cout'] * (size - (bs - 1)) ** 2))
                 else:
                     shape = (batch, b['cout'], size, size)
                     ent = self._pinned(('pf', f, bi), shape)      # waits for the last H2D out of this buffer
-                    steps.append(('draw', (f, bi), ent[0], 1 - DROP_RATE))
+                    steps.append(('draw', (f, bi), ent[0], 1 - b.get('drop_rate', 0.1)))
         self._prefetch = host_rng.MaskPrefetch(steps)
         self._pf_fwd = 0
 
     @staticmethod
-    def _dropblock_gamma(nbt, bs, size):
-        keep_rate = max(1.0 - DROP_RATE / (20 * 2000) * nbt, 1.0 - DROP_RATE)
+    def _dropblock_gamma(nbt, bs, size, drop_rate=0.1):
+        keep_rate = max(1.0 - drop_rate / (20 * 2000) * nbt, 1.0 - drop_rate)
         return (1 - keep_rate) / bs ** 2 * size ** 2 / (size - bs + 1) ** 2
 
     def start_dropblock_ahead(self, forwards):
@@ -200,13 +218,13 @@ class BackboneEngine(object):
                     size = 84
                     for bi, b in enumerate(self.blocks):
                         size = size // b['pool']
-                        if not b['drop_block']:
+                        if not b['drop_block'] or not b.get('drop_rate', 0.1) > 0:
                             continue
                         st = pf.hold_state((f, bi))
                         if st is None:
                             return
                         bs = b['block_size']
-                        gamma = self._dropblock_gamma(nbt, bs, size)
+                        gamma = self._dropblock_gamma(nbt, bs, size, b.get('drop_rate', 0.1))
                         shape = (batch, b['cout'], size, size)
                         seed_shape = (batch, b['cout'], size - (bs - 1), size - (bs - 1))
                         seeds = self._scratch(('seed_ahead', f & 1, bi), seed_shape)
@@ -278,18 +296,21 @@ class BackboneEngine(object):
         resnet_language.py:292-299, 311-325).  -> (keep uint8 NCHW on `device`, scale)."""
         b = self.blocks[bi]
         shape = (batch, b['cout'], size, size)
+        drop_rate = b.get('drop_rate', 0.1)
+        if not drop_rate > 0:                                                  # `if self.drop_rate > 0` (:292): no draw at all
+            return None, 1.0
         if not b['drop_block']:
-            scale = float(torch.ones(1).div_(1 - DROP_RATE))                   # noise.div_(1 - p)
+            scale = float(torch.ones(1).div_(1 - drop_rate))                   # noise.div_(1 - p)
             got = self._prefetch.take((self._cur_fwd, bi), shape) if self._prefetch is not None else None
             if got is not None:                                                # drawn ahead of time on the host thread
                 ent = self._pinned(('pf', self._cur_fwd, bi), shape, sync=False)
             else:
                 ent = self._pinned(('m', bi, self._cur_fwd & 1), shape)
-                host_rng.bernoulli_u8(shape, 1 - DROP_RATE, 0, out=ent[0])    # noise.bernoulli_(1 - p)
+                host_rng.bernoulli_u8(shape, 1 - drop_rate, 0, out=ent[0])    # noise.bernoulli_(1 - p)
         else:
             bs = b['block_size']
             nbt = counters[b['prefix']]
-            gamma = self._dropblock_gamma(nbt, bs, size)
+            gamma = self._dropblock_gamma(nbt, bs, size, drop_rate)
             ahead = self._dropblock_take((self._cur_fwd, bi), gamma, shape)
             if ahead is not None:                                              # drawn on the second host thread
                 ent, kept = ahead
@@ -340,9 +361,9 @@ class BackboneEngine(object):
             m, cout = b['mod'], b['cout']
             last = bi == nb - 1
             r1, mu1, is1 = conv_bn(h, w['w1'], m.bn1, cout)
-            h1 = ops.bn_apply(r1, mu1, is1, m.bn1.weight.detach(), m.bn1.bias.detach(), lrelu=True, slope=SLOPE)
+            h1 = ops.bn_apply(r1, mu1, is1, m.bn1.weight.detach(), m.bn1.bias.detach(), lrelu=True, slope=SLOPE, split=self.split)
             r2, mu2, is2 = conv_bn(h1, w['w2'], m.bn2, cout)
-            h2 = ops.bn_apply(r2, mu2, is2, m.bn2.weight.detach(), m.bn2.bias.detach(), lrelu=True, slope=SLOPE)
+            h2 = ops.bn_apply(r2, mu2, is2, m.bn2.weight.detach(), m.bn2.bias.detach(), lrelu=True, slope=SLOPE, split=self.split)
             r3, mu3, is3 = conv_bn(h2, w['w3'], m.bn3, cout)
             if b['downsample']:
                 bnd = m.downsample[1]
@@ -354,12 +375,12 @@ class BackboneEngine(object):
             if b['downsample']:
                 h = ops.bn_apply(r3, mu3, is3, m.bn3.weight.detach(), m.bn3.bias.detach(), res_raw=rd,
                                  res_bn=(mud, isd, bnd.weight.detach(), bnd.bias.detach()), lrelu=True, slope=SLOPE,
-                                 pool=pool, keep=keep, keep_scale=scale)
+                                 pool=pool, keep=keep, keep_scale=scale, split=self.split)
             else:
                 h = ops.bn_apply(r3, mu3, is3, m.bn3.weight.detach(), m.bn3.bias.detach(), res_act=h, lrelu=True,
-                                 slope=SLOPE, pool=pool, keep=keep, keep_scale=scale)
+                                 slope=SLOPE, pool=pool, keep=keep, keep_scale=scale, split=self.split)
         torch._foreach_add_(bumped, 1)   # BatchNorm2d.num_batches_tracked of every BN that ran
         self.invalidate()   # running statistics moved: the folded weights are stale
-        if h.dim() == 4:    # resnet12: the last block is pooled 2x2, the global average follows
+        if h.dim() >= 4:    # resnet12: the last block is pooled 2x2, the global average follows
             h = ops.global_avg(h)
         return h

@@ -41,11 +41,22 @@ def _ptr(t, dtype=None, name="tensor"):
     return C.c_void_p(t.data_ptr())
 
 
-def pack_input(x_nchw, cpad=16):
-    """NCHW fp32 -> NHWC bf16 with channels zero-padded to cpad."""
+def _lo(t):
+    """Low plane of an error-compensated pair tensor [2, ...] (None for a plain tensor)."""
+    return None if t is None or t.dim() not in (5,) else t[1]
+
+
+def _planes(shape, split, device, dtype=torch.bfloat16):
+    """Output buffer: plain [shape] or an error-compensated pair [2, *shape] (plane 0 = hi, plane 1 = lo)."""
+    return torch.empty(((2,) + tuple(shape)) if split else tuple(shape), dtype=dtype, device=device)
+
+
+def pack_input(x_nchw, cpad=16, split=False):
+    """NCHW fp32 -> NHWC bf16 with channels zero-padded to cpad.  split: error-compensated pair [2,B,H,W,cpad]."""
     B, Cc, H, W = x_nchw.shape
-    y = torch.empty((B, H, W, cpad), dtype=torch.bfloat16, device=x_nchw.device)
-    rc = L.load().sr_pack_input(_ptr(x_nchw, torch.float32, "x"), _ptr(y), B, Cc, H, W, cpad, _stream())
+    y = _planes((B, H, W, cpad), split, x_nchw.device)
+    rc = L.load().sr_pack_input(_ptr(x_nchw, torch.float32, "x"), _ptr(y[0] if split else y), _ptr(y[1]) if split else None,
+                                B, Cc, H, W, cpad, _stream())
     L.check(rc, "sr_pack_input")
     LAUNCHES[0] += 1
     return y
@@ -62,41 +73,53 @@ def bn_fold(gamma, beta, running_mean, running_var, eps=1e-5):
     return scale, shift
 
 
-def pack_input_u8(x_nhwc_u8, mean, std, cpad=16, crop_ij=None, flip=None, pad=0):
+def pack_input_u8(x_nhwc_u8, mean, std, cpad=16, crop_ij=None, flip=None, pad=0, split=False):
     """uint8 NHWC images -> [RandomCrop(padding=pad) at crop_ij, horizontal flip where flip] -> ToTensor +
     Normalize(mean, std) -> NHWC bf16 with channels zero-padded to cpad (one kernel).  crop_ij: CUDA int32 [B,2],
     flip: CUDA uint8 [B] (see dataset.transform_cfg.draw_crop_flip), or None."""
     B, H, W, Cc = x_nhwc_u8.shape
-    y = torch.empty((B, H, W, cpad), dtype=torch.bfloat16, device=x_nhwc_u8.device)
+    y = _planes((B, H, W, cpad), split, x_nhwc_u8.device)
     m = (C.c_float * Cc)(*[float(v) for v in mean])
     s = (C.c_float * Cc)(*[float(v) for v in std])
     if crop_ij is not None and tuple(crop_ij.shape) != (B, 2):
         raise RuntimeError("srb200: crop_ij must be [batch, 2]")
     if flip is not None and flip.numel() != B:
         raise RuntimeError("srb200: flip must be [batch]")
-    rc = L.load().sr_pack_input_u8(_ptr(x_nhwc_u8, torch.uint8, "x"), _ptr(y), B, Cc, H, W, m, s, cpad,
+    rc = L.load().sr_pack_input_u8(_ptr(x_nhwc_u8, torch.uint8, "x"), _ptr(y[0] if split else y),
+                                   _ptr(y[1]) if split else None, B, Cc, H, W, m, s, cpad,
                                    _ptr(crop_ij, torch.int32, "crop_ij"), _ptr(flip, torch.uint8, "flip"), int(pad), _stream())
     L.check(rc, "sr_pack_input_u8")
     LAUNCHES[0] += 1
     return y
 
 
-def pack_weight(w_oihw, scale=None, cin_pad=None, out=None):
-    """OIHW fp32 -> bf16 [cout, kh*kw, cin_pad] (optionally scaled per output channel)."""
+def pack_weight(w_oihw, scale=None, cin_pad=None, out=None, split=False):
+    """OIHW fp32 -> bf16 [cout, kh*kw, cin_pad] (optionally scaled per output channel); split: pair [2, cout, taps, cin_pad]."""
     co, ci, kh, kw = w_oihw.shape
     if cin_pad is None:
         cin_pad = (ci + 15) // 16 * 16
     if out is None:
-        out = torch.empty((co, kh * kw, cin_pad), dtype=torch.bfloat16, device=w_oihw.device)
-    rc = L.load().sr_pack_weight(_ptr(w_oihw, torch.float32, "w"), _ptr(scale, torch.float32, "scale"), _ptr(out), co, ci,
-                                 kh, kw, cin_pad, _stream())
+        out = _planes((co, kh * kw, cin_pad), split, w_oihw.device)
+    split = out.dim() == 4
+    rc = L.load().sr_pack_weight(_ptr(w_oihw, torch.float32, "w"), _ptr(scale, torch.float32, "scale"),
+                                 _ptr(out[0] if split else out), _ptr(out[1]) if split else None, co, ci, kh, kw, cin_pad,
+                                 _stream())
     L.check(rc, "sr_pack_weight")
     LAUNCHES[0] += 1
     return out
 
 
 def conv(panels, cout, shift=None, residual=None, slope=0.1, epilogue=L.SR_EPI_ACT, stats=None, out=None):
-    """panels: list of (act NHWC bf16 [B,H,W,cin_pad], packed weight bf16 [cout,taps,cin_pad])."""
+    """panels: list of (act NHWC bf16 [B,H,W,cin_pad], packed weight bf16 [cout,taps,cin_pad]); or, error-compensated
+    mode, of pair tensors (act [2,B,H,W,cin_pad], weight [2,cout,taps,cin_pad]) - then residual / bf16 outputs are pairs too."""
+    split = panels[0][0].dim() == 5
+    if split:
+        if any(act.dim() != 5 or wgt.dim() != 4 for act, wgt in panels) or (residual is not None and residual.dim() != 5):
+            raise RuntimeError("srb200: error-compensated conv needs pair tensors for every operand")
+        lo_panels = [(act[1], wgt[1]) for act, wgt in panels]
+        panels = [(act[0], wgt[0]) for act, wgt in panels]
+        residual_lo = None if residual is None else residual[1]
+        residual = None if residual is None else residual[0]
     act0 = panels[0][0]
     B, H, W, _ = act0.shape
     a = L.ConvArgs()
@@ -112,8 +135,13 @@ def conv(panels, cout, shift=None, residual=None, slope=0.1, epilogue=L.SR_EPI_A
         a.panel[i].wgt = _ptr(wgt, torch.bfloat16, "wgt")
         a.panel[i].cin_pad = act.shape[3]
         a.panel[i].taps = wgt.shape[1]
+        if split:
+            a.panel[i].act_lo = _ptr(lo_panels[i][0], torch.bfloat16, "act_lo")
+            a.panel[i].wgt_lo = _ptr(lo_panels[i][1], torch.bfloat16, "wgt_lo")
     a.shift = _ptr(shift, torch.float32, "shift")
     a.residual = _ptr(residual, torch.bfloat16, "residual")
+    if split and residual is not None:
+        a.residual_lo = _ptr(residual_lo, torch.bfloat16, "residual_lo")
     if residual is not None and tuple(residual.shape) != (B, H, W, cout):
         raise RuntimeError("srb200: residual shape mismatch")
     a.slope = slope
@@ -121,14 +149,17 @@ def conv(panels, cout, shift=None, residual=None, slope=0.1, epilogue=L.SR_EPI_A
     dev = act0.device
     if out is None:
         if epilogue == L.SR_EPI_ACT:
-            out = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=dev)
+            out = _planes((B, H, W, cout), split, dev)
         elif epilogue == L.SR_EPI_ACT_POOL2:
-            out = torch.empty((B, H // 2, W // 2, cout), dtype=torch.bfloat16, device=dev)
+            out = _planes((B, H // 2, W // 2, cout), split, dev)
         elif epilogue == L.SR_EPI_ACT_AVG:
             out = torch.empty((B, cout), dtype=torch.float32, device=dev)
         else:
             out = torch.empty((B, H, W, cout), dtype=torch.float32, device=dev)
-    a.out = _ptr(out)
+    if split and out.dim() == 5:
+        a.out, a.out_lo = _ptr(out[0]), _ptr(out[1])
+    else:
+        a.out = _ptr(out)
     a.stats = _ptr(stats, torch.float64, "stats")
     L.check(L.load().sr_conv(C.byref(a), _stream()), "sr_conv")
     LAUNCHES[0] += 1
@@ -148,7 +179,8 @@ def bn_finalize(stats, count, running_mean, running_var, eps=1e-5, momentum=0.1)
 
 
 def bn_apply(raw, mean, invstd, gamma, beta, res_raw=None, res_bn=None, res_act=None, lrelu=True, slope=0.1, pool=0,
-             keep=None, keep_scale=1.0):
+             keep=None, keep_scale=1.0, split=False):
+    """split: bf16 outputs (and res_act) are error-compensated pairs [2, ...]."""
     B, H, W, Cc = raw.shape
     a = L.BnApplyArgs()
     a.batch, a.height, a.width, a.channels = B, H, W, Cc
@@ -160,7 +192,10 @@ def bn_apply(raw, mean, invstd, gamma, beta, res_raw=None, res_bn=None, res_act=
         rm, ri, rg, rb = res_bn
         a.res_mean, a.res_invstd = _ptr(rm, torch.float32), _ptr(ri, torch.float32)
         a.res_gamma, a.res_beta = _ptr(rg, torch.float32), _ptr(rb, torch.float32)
-    a.res_act = _ptr(res_act, torch.bfloat16, "res_act")
+    if res_act is not None and res_act.dim() == 5:
+        a.res_act, a.res_act_lo = _ptr(res_act[0], torch.bfloat16, "res_act"), _ptr(res_act[1], torch.bfloat16, "res_act_lo")
+    else:
+        a.res_act = _ptr(res_act, torch.bfloat16, "res_act")
     a.lrelu = 1 if lrelu else 0
     a.slope = slope
     a.pool = pool
@@ -169,10 +204,13 @@ def bn_apply(raw, mean, invstd, gamma, beta, res_raw=None, res_bn=None, res_act=
     if pool == -1:
         out = torch.empty((B, Cc), dtype=torch.float32, device=raw.device)
     elif pool == 2:
-        out = torch.empty((B, H // 2, W // 2, Cc), dtype=torch.bfloat16, device=raw.device)
+        out = _planes((B, H // 2, W // 2, Cc), split, raw.device)
     else:
-        out = torch.empty((B, H, W, Cc), dtype=torch.bfloat16, device=raw.device)
-    a.out = _ptr(out)
+        out = _planes((B, H, W, Cc), split, raw.device)
+    if split and out.dim() == 5:
+        a.out, a.out_lo = _ptr(out[0]), _ptr(out[1])
+    else:
+        a.out = _ptr(out)
     L.check(L.load().sr_bn_apply(C.byref(a), _stream()), "sr_bn_apply")
     LAUNCHES[0] += 1
     return out
@@ -213,7 +251,7 @@ class HeadSession(object):
         self.base_weight, self.reserve_weight, self.pull = base_weight, reserve_weight, pull
         Cn, d = weight.shape
         self.opt_state = torch.zeros((2 if adam else 1, Cn, d), dtype=torch.float32, device=dev)
-        self.status = torch.zeros(4, dtype=torch.int32, device=dev)
+        self._pending = []       # [(status, trace)] of launches whose results have not been read back yet
         self.logits = torch.empty((n_support, Cn), dtype=torch.float32, device=dev) if want_logits else None
         a = L.HeadArgs()
         a.feat, a.dim = _ptr(feat, torch.float32, "feat"), d
@@ -234,7 +272,6 @@ class HeadSession(object):
         a.stable, a.stable_epochs = (1 if stable else 0), stable_epochs
         a.min_novel_epochs, a.max_novel_epochs = min_novel_epochs, max_novel_epochs
         a.convergence_epsilon, a.target_train_loss = convergence_epsilon, target_train_loss
-        a.status = _ptr(self.status)
         a.logits_support = _ptr(self.logits)
         ws_bytes = int(L.load().sr_head_workspace_bytes(C.byref(a)))
         self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -246,11 +283,15 @@ class HeadSession(object):
         self.stopped = False
         self.traces = []
 
-    def run(self, max_epochs, feat=None, support_row0=None, memory_row0=None):
+    def run(self, max_epochs, feat=None, support_row0=None, memory_row0=None, defer=False):
         """Run up to max_epochs more epochs on the device; returns the [epochs, SR_TRACE_COLS] trace (host).
 
         `feat` / row offsets may change between calls (epoch 1 uses the train-mode features, later epochs the
-        eval-mode cache); labels, weight and optimiser state carry over."""
+        eval-mode cache); labels, weight and optimiser state carry over.
+
+        defer=True enqueues the launch and returns None WITHOUT reading anything back: the next run() is chained to it on
+        the device (sr_head_args.resume_status), and collect() reads every pending status / trace in one go.  A whole
+        session (epoch 1, cache build, remaining epochs, scoring) is then queued without a host synchronisation."""
         a = self.args
         if feat is not None:
             self.feat = feat
@@ -261,24 +302,41 @@ class HeadSession(object):
             a.support_row0 = support_row0
         if memory_row0 is not None:
             a.memory_row0 = memory_row0
-        trace = torch.zeros((max_epochs, L.SR_TRACE_COLS), dtype=torch.float32, device=self.feat.device)
+        dev = self.feat.device
+        trace = torch.zeros((max_epochs, L.SR_TRACE_COLS), dtype=torch.float32, device=dev)
+        status = torch.zeros(8, dtype=torch.int32, device=dev)
         a.loss_trace = _ptr(trace)
+        a.status = _ptr(status)
+        a.resume_status = _ptr(self._pending[-1][0]) if self._pending else None
         a.max_epochs, a.epoch0, a.step0 = max_epochs, self.epochs, self.epochs
         a.stable_count0, a.prev_loss = self.stable_count, self.prev_loss
         L.check(L.load().sr_head_run(C.byref(a), _stream()), "sr_head_run")
         LAUNCHES[0] += 1
-        st = self.status.cpu().tolist()  # the one host sync per call
-        if st[3] != 0:
-            raise RuntimeError("srb200: head kernel reported a grid-barrier timeout")
-        n = st[0]
-        tr = trace[:n].cpu()
-        self.epochs += n
-        self.stopped = bool(st[1])
-        self.stable_count = st[2]
-        if n > 0:
-            self.prev_loss = float(tr[-1, 0])
-        self.traces.append(tr)
-        return tr
+        self._pending.append((status, trace))
+        if defer:
+            return None
+        return self.collect()
+
+    def collect(self):
+        """Read back every pending launch (the one host sync): -> concatenated trace of the epochs they ran."""
+        if not self._pending:
+            return torch.zeros((0, L.SR_TRACE_COLS), dtype=torch.float32)
+        sts = torch.stack([st for st, _ in self._pending]).cpu().tolist()
+        out = []
+        for st, (_, trace) in zip(sts, self._pending):
+            if st[3] != 0:
+                raise RuntimeError("srb200: head kernel reported a grid-barrier timeout")
+            n = st[0]
+            self.epochs += n
+            self.stopped = bool(st[1])
+            self.stable_count = st[2]
+            if n > 0:
+                tr = trace[:n].cpu()
+                self.prev_loss = float(tr[-1, 0])
+                self.traces.append(tr)
+                out.append(tr)
+        self._pending = []
+        return torch.cat(out, 0) if out else torch.zeros((0, L.SR_TRACE_COLS), dtype=torch.float32)
 
     def run_to_convergence(self, chunk=1 << 20):
         while not self.stopped:
@@ -391,10 +449,13 @@ def score_logits(logits, labels, confusion=None):
 
 
 def global_avg(x_nhwc):
-    """bf16 NHWC [B,H,W,C] -> fp32 [B,C] (AdaptiveAvgPool2d(1))."""
+    """bf16 NHWC [B,H,W,C] (or an error-compensated pair [2,B,H,W,C]) -> fp32 [B,C] (AdaptiveAvgPool2d(1))."""
+    lo = _lo(x_nhwc)
+    if lo is not None:
+        x_nhwc = x_nhwc[0]
     B, H, W, Cc = x_nhwc.shape
     y = torch.empty((B, Cc), dtype=torch.float32, device=x_nhwc.device)
-    rc = L.load().sr_global_avg(_ptr(x_nhwc, torch.bfloat16, "x"), _ptr(y), B, H, W, Cc, _stream())
+    rc = L.load().sr_global_avg(_ptr(x_nhwc, torch.bfloat16, "x"), _ptr(lo, torch.bfloat16, "x_lo"), _ptr(y), B, H, W, Cc, _stream())
     L.check(rc, "sr_global_avg")
     LAUNCHES[0] += 1
     return y

@@ -69,7 +69,7 @@ def test_argument_validation_without_gpu(lib):
     assert b"n_panels" in lib.sr_last_error()
     h = _lib.HeadArgs()
     assert lib.sr_head_run(ctypes.byref(h), None) == -1
-    assert lib.sr_pack_input(None, None, 1, 3, 84, 84, 16, None) == -1
+    assert lib.sr_pack_input(None, None, None, 1, 3, 84, 84, 16, None) == -1
 
 
 def test_no_cpu_fallback():

@@ -20,7 +20,8 @@ def _close(a, b, tol=1e-5):
 
 
 @pytest.mark.parametrize("case,schedule", [("subspace_s2e3", "cached"), ("semantic_s2e2", "cached"),
-                                           ("mapping_s2e2", "literal")])
+                                           ("mapping_s2e2", "literal"), ("dropblock_s2e3", "cached"),
+                                           ("adam_s2e3", "cached")])
 def test_oracle_matches_reference_golden(case, schedule, golden_dir, word_embed_dir):
     from oracle import init as oinit, session
     g = torch.load(os.path.join(golden_dir, case + ".pt"), weights_only=False)

@@ -12,7 +12,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "subspace-reg_b200"))
 
-GROUPS = ["conv_basic", "conv_k", "conv_epi", "conv_train", "head", "factor"]
+GROUPS = ["conv_basic", "conv_k", "conv_epi", "conv_train", "conv_x3", "head", "factor"]
 
 
 def _ref_conv(act_nhwc, w_packed, taps):
@@ -91,6 +91,81 @@ def conv_case(B, H, cin, cout, taps, epi, residual=False, second=None, seed=0):
         return _report(name, out.permute(0, 3, 1, 2), F.max_pool2d(y, 2), 6e-3)
     return _report(name, out, y.mean((2, 3)), 1e-5)
 
+
+
+def _split(x):
+    """fp32 -> error-compensated bf16 pair [2, ...] (hi = rn(x), lo = rn(x - hi))."""
+    import torch
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo], 0).contiguous()
+
+
+def conv_case_x3(B, H, cin, cout, taps, epi, residual=False, second=None, seed=0, tol=2e-5):
+    """Error-compensated (bf16x3) mode against an fp64 convolution of the fp32 operands."""
+    import torch
+    import torch.nn.functional as F
+    from srb200 import ops, _lib as L
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    dev = "cuda"
+
+    def operand(cin_, taps_):
+        cp = (cin_ + 15) // 16 * 16
+        a = torch.zeros(B, H, H, cp, device=dev)
+        a[..., :cin_] = torch.randn(B, H, H, cin_, device=dev, generator=g)
+        w = torch.zeros(cout, taps_, cp, device=dev)
+        w[..., :cin_] = torch.randn(cout, taps_, cin_, device=dev, generator=g) / (taps_ * cin_) ** 0.5
+        k = 3 if taps_ == 9 else 1
+        ref = F.conv2d(a.double().permute(0, 3, 1, 2), w.double().reshape(cout, k, k, cp).permute(0, 3, 1, 2), padding=k // 2)
+        return _split(a), _split(w), ref
+    a1, w1, ref = operand(cin, taps)
+    panels = [(a1, w1)]
+    if second is not None:
+        a2, w2, r2 = operand(second, 1)
+        panels.append((a2, w2))
+        ref = ref + r2
+    shift = torch.randn(cout, device=dev, generator=g) * 0.1
+    res = res_pair = None
+    if residual:
+        res = torch.randn(B, H, H, cout, device=dev, generator=g)
+        res_pair = _split(res)
+    name = "conv x3 B%d %dx%d cin%d cout%d taps%d epi%d%s%s" % (B, H, H, cin, cout, taps, epi, " +res" if residual else "",
+                                                               " +ds%d" % second if second else "")
+    if epi == L.SR_EPI_RAW_STATS:
+        stats = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
+        out = ops.conv(panels, cout, epilogue=epi, stats=stats)
+        torch.cuda.synchronize()
+        ok = _report(name + " raw", out.permute(0, 3, 1, 2), ref, tol)
+        ok &= _report(name + " sumsq", stats[cout:], (ref ** 2).sum((0, 2, 3)), tol)
+        return ok
+    y = ref + shift.double().view(1, -1, 1, 1)
+    if residual:
+        y = y + (res_pair[0].double() + res_pair[1].double()).permute(0, 3, 1, 2)
+    y = F.leaky_relu(y, 0.1)
+    out = ops.conv(panels, cout, shift=shift, residual=res_pair, epilogue=epi)
+    torch.cuda.synchronize()
+    if epi == L.SR_EPI_ACT_AVG:
+        return _report(name, out, y.mean((2, 3)), tol)
+    got = (out[0].double() + out[1].double()).permute(0, 3, 1, 2)
+    want = y if epi == L.SR_EPI_ACT else F.max_pool2d(y, 2)
+    # the pair itself must be well formed: hi is the bf16 rounding of the value
+    ok = bool((out[0] == (out[0].float() + out[1].float()).to(torch.bfloat16)).all().item())
+    if not ok:
+        print(name + ": hi plane is not rn(hi + lo)  FAIL", flush=True)
+    return _report(name, got, want, tol) and ok
+
+
+def group_conv_x3():
+    from srb200 import _lib as L
+    ok = True
+    ok &= conv_case_x3(2, 84, 3, 64, 9, L.SR_EPI_ACT)                       # first layer (32-byte rows, tap reuse)
+    ok &= conv_case_x3(2, 84, 64, 64, 9, L.SR_EPI_ACT_POOL2, second=3)      # layer1 conv3 + downsample: 6 internal panels
+    ok &= conv_case_x3(2, 42, 160, 160, 9, L.SR_EPI_ACT)                    # ragged channel blocks
+    ok &= conv_case_x3(7, 21, 320, 320, 9, L.SR_EPI_ACT_POOL2, second=160)  # floor pool 21 -> 10, N split
+    ok &= conv_case_x3(13, 10, 320, 320, 9, L.SR_EPI_ACT, residual=True)    # identity residual pair
+    ok &= conv_case_x3(23, 5, 640, 640, 9, L.SR_EPI_ACT_AVG, residual=True) # fused global average
+    ok &= conv_case_x3(3, 42, 64, 160, 9, L.SR_EPI_RAW_STATS)               # train-mode raw output + statistics
+    return ok
 
 def group_conv_basic():
     from srb200 import _lib as L
