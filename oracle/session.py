@@ -35,6 +35,7 @@ class Timers(object):
     def __init__(self):
         self.train_s = 0.0       # epoch-loop body up to and including the convergence bookkeeping
         self.score_s = 0.0       # validate + eval_base
+        self.loop_s = 0.0        # the whole `while stop_condition` body (language_eval.py:242-350): train step + validate
         self.steps = 0
         self.images_scored = 0
         self.images_backbone = 0
@@ -152,7 +153,7 @@ def run_sessions(sd, world, n_sessions=None, schedule='literal', ckpt=None, mode
         sup_f = None
         go = True
         while go:
-            t0 = time.perf_counter()
+            t0 = t_loop0 = time.perf_counter()
             train_mode = epoch == 1        # net.train() at :211, validate() leaves the net in eval mode from epoch 2 on
             if schedule == 'literal' or train_mode:
                 f_s = fwd(support_xs, train_mode)
@@ -226,6 +227,7 @@ def run_sessions(sd, world, n_sessions=None, schedule='literal', ckpt=None, mode
                 for k in counters:
                     counters[k] += len(query_x_list)
             T.score_s += time.perf_counter() - t0
+            T.loop_s += time.perf_counter() - t_loop0
             epoch += 1
 
         if opt.memory_replay:                                          # :353-359

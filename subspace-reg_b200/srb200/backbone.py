@@ -138,7 +138,12 @@ class BackboneEngine(object):
         return ops.pack_input(x.contiguous(), 16, split=self.split)
 
     def _eval_chunk(self, x, taps):
-        h = self.pack(x)
+        return self.eval_packed(self.pack(x), taps)
+
+    def eval_packed(self, h, taps=None):
+        """The convolution launches of one eval-mode pass on an already packed NHWC bf16 input (18 for resnet18):
+        what bench.py's roofline probe times."""
+        self._ensure_folded()
         nb = len(self.blocks)
         for bi, (b, w) in enumerate(zip(self.blocks, self._folded)):
             cout = b['cout']

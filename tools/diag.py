@@ -148,10 +148,10 @@ def conv_case_x3(B, H, cin, cout, taps, epi, residual=False, second=None, seed=0
         return _report(name, out, y.mean((2, 3)), tol)
     got = (out[0].double() + out[1].double()).permute(0, 3, 1, 2)
     want = y if epi == L.SR_EPI_ACT else F.max_pool2d(y, 2)
-    # the pair itself must be well formed: hi is the bf16 rounding of the value
-    ok = bool((out[0] == (out[0].float() + out[1].float()).to(torch.bfloat16)).all().item())
+    # the pair itself must be well formed: lo is at most half a bf16 ulp of hi
+    ok = bool((out[1].float().abs() <= out[0].float().abs() * 2.0 ** -8 + 1e-30).all().item())
     if not ok:
-        print(name + ": hi plane is not rn(hi + lo)  FAIL", flush=True)
+        print(name + ": lo plane exceeds half an ulp of hi  FAIL", flush=True)
     return _report(name, got, want, tol) and ok
 
 
