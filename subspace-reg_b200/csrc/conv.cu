@@ -190,8 +190,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     __shared__ uint64_t tmem_full_bar[4];
     __shared__ uint64_t tmem_empty_bar[4];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(16) float s_sum[256];   // per-channel sums of this tile (RAW_STATS)
-    __shared__ float s_sq[256];
+    // RAW_STATS: per-channel (sum, sum of squares) of this tile, one slot per epilogue warp in the staging region:
+    // [2][kEpiWarps][n_cta] floats.  Every slot is written by exactly one warp and the eight are added in a fixed order,
+    // so a tile's contribution is a deterministic fp32 value and the fp64 atomics that collect the tiles are exact
+    // (fp32-valued addends, < 2^29 of them): the batch statistics do not depend on the execution order.
+    float* const s_part = reinterpret_cast<float*>(staging);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -399,13 +402,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t, it.next(p)) {
             const TileCoord tc = it.coord(p);
-            if (p.epi == SR_EPI_RAW_STATS) {
-                for (int i = et; i < p.n_cta; i += kEpiThreads) {
-                    s_sum[i] = 0.f;
-                    s_sq[i] = 0.f;
-                }
-                named_bar_sync(1, kEpiThreads);
-            }
             // this thread's own output pixel, and (SR_EPI_ACT) the four pixels whose pieces it writes out
             const bool valid = (m < p.rows_sub) && (tc.n0 + nl + sub_n < p.B) && (tc.h0 + hl + sub_h < p.H);
             const size_t origin = ((size_t)tc.n0 * p.H + tc.h0) * p.W + tc.w0;   // pixel index of the tile origin
@@ -440,8 +436,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                     const float tsum = warp_transpose_sum16(v, lane);
                     const float tsq = warp_transpose_sum16(sq, lane);
                     if (lane < 16) {
-                        atomicAdd(&s_sum[c16 + lane], tsum);
-                        atomicAdd(&s_sq[c16 + lane], tsq);
+                        s_part[(warp - kEpiWarp0) * p.n_cta + c16 + lane] = tsum;
+                        s_part[(kEpiWarps + warp - kEpiWarp0) * p.n_cta + c16 + lane] = tsq;
                     }
                     return;
                 }
@@ -641,8 +637,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             if (p.epi == SR_EPI_RAW_STATS) {
                 named_bar_sync(1, kEpiThreads);
                 for (int i = et; i < p.n_cta; i += kEpiThreads) {
-                    atomicAdd(&p.stats[tc.co0 + i], (double)s_sum[i]);
-                    atomicAdd(&p.stats[p.Cout + tc.co0 + i], (double)s_sq[i]);
+                    float a = 0.f, b = 0.f;
+#pragma unroll
+                    for (int w = 0; w < kEpiWarps; ++w) {
+                        a += s_part[w * p.n_cta + i];
+                        b += s_part[(kEpiWarps + w) * p.n_cta + i];
+                    }
+                    atomicAdd(&p.stats[tc.co0 + i], (double)a);
+                    atomicAdd(&p.stats[p.Cout + tc.co0 + i], (double)b);
                 }
                 named_bar_sync(1, kEpiThreads);
             }
@@ -843,6 +845,7 @@ int32_t plan_conv(const sr_conv_args* a, int max_dyn, ConvPlan* plan) {
     int staging = 0;   // the producer prefetches the next tile during the epilogue: staging cannot alias the pipeline
     if (a->epilogue == SR_EPI_ACT_POOL2 || a->epilogue == SR_EPI_ACT) staging = (precise ? 2 : 1) * kLoStaging;
     if (a->epilogue == SR_EPI_ACT_AVG) staging = 2 * kSubRows * kStagePitchF32 * 4;
+    if (a->epilogue == SR_EPI_RAW_STATS) staging = 2 * kEpiWarps * (a->cout / ns) * 4;
     p.staging_bytes = staging;
     const int shift_bytes = a->epilogue == SR_EPI_RAW_STATS ? 0 : (int)align_up((int64_t)a->cout * 4, 16);
     const int budget = max_dyn - 1024 - staging - shift_bytes;
@@ -904,7 +907,7 @@ int32_t plan_conv(const sr_conv_args* a, int max_dyn, ConvPlan* plan) {
     return SR_OK;
 }
 
-constexpr int kStaticSmemEstimate = 3072;   // conv_umma_kernel's static shared memory (ptxas -v); used when no device is present
+constexpr int kStaticSmemEstimate = 1024;   // conv_umma_kernel's static shared memory (ptxas -v); used when no device is present
 
 // Per-device launch state (function attributes are per context; the SM count is per device): no process-wide assumption
 // that every GPU is the one first seen.

@@ -11,8 +11,10 @@ support tiling :279-350) - and the deterministic tail of its transforms (ToTenso
 Two ways to get the pixels:
   * default: normalised fp32 NCHW tensors, like the reference's loaders (computed batch-wise with torch ops that round
     exactly like ToTensor + Normalize);
-  * `raw=True`: the uint8 NHWC images themselves - feed them to `ResNet.features` / `BackboneEngine`, whose first kernel
-    (`sr_pack_input_u8`) normalises and packs them on the GPU.
+  * `raw=True` (or SRB_RAW_U8=1 in the environment, for callers that cannot pass the flag): the uint8 NHWC images
+    themselves - feed them to `ResNet.features` / `BackboneEngine`, whose first kernel (`sr_pack_input_u8`) normalises
+    and packs them on the GPU; the support branch's random crop / flip is applied to the uint8 pixels with torchvision's
+    own draws.
 Callables passed as `transform` / `train_transform` / `test_transform` are applied per image exactly like the reference
 does (that is where its PIL augmentations would go; they are not part of this package).
 
@@ -25,6 +27,7 @@ import pickle
 import numpy as np
 import torch
 
+from . import transform_cfg
 from .transform_cfg import mean as _MEAN, std as _STD
 
 
@@ -37,9 +40,20 @@ def _normalise(batch_u8_nhwc):
 
 
 def _apply(transform, batch_u8_nhwc, raw):
+    """transform: None / kind 'plain' = ToTensor + Normalize; a callable = applied per image like the reference does.
+    raw: return uint8 NHWC (normalisation happens in sr_pack_input_u8); a 'crop_flip' transform is then applied HERE on the
+    uint8 pixels with the draws torchvision would make (same generator consumption, same pixels), anything else that is
+    not plain (ColorJitter, user callables) cannot be expressed on uint8 and raises instead of being dropped."""
+    kind = getattr(transform, 'srb_kind', None) if transform is not None else 'plain'
     if raw:
-        return torch.from_numpy(np.ascontiguousarray(batch_u8_nhwc))
-    if transform is None:
+        if kind == 'plain':
+            return torch.from_numpy(np.ascontiguousarray(batch_u8_nhwc))
+        if kind == 'crop_flip':
+            ij, flip = transform_cfg.draw_crop_flip(len(batch_u8_nhwc), size=batch_u8_nhwc.shape[1])
+            return torch.from_numpy(transform_cfg.apply_crop_flip_u8(batch_u8_nhwc, ij.numpy(), flip.numpy()))
+        raise NotImplementedError("srb200: raw=True supports the plain and the crop+flip transforms (transforms_test_options"
+                                  "['A']); %r would be silently dropped" % (kind or transform,))
+    if kind == 'plain':
         return _normalise(batch_u8_nhwc)
     return torch.stack([transform(img) for img in batch_u8_nhwc])
 
@@ -47,9 +61,11 @@ def _apply(transform, batch_u8_nhwc, raw):
 class ImageNet(object):
     """Flat view of one split: `self[i] -> (image, label - min(labels), i)`."""
 
-    def __init__(self, args, split='train', phase=None, is_sample=False, k=4096, transform=None, raw=False):
+    def __init__(self, args, split='train', phase=None, is_sample=False, k=4096, transform=None, raw=None):
         if is_sample:
             raise NotImplementedError("contrastive sampling is outside the incremental-session path")
+        if raw is None:      # callers that cannot pass the flag (the unmodified eval_incremental.py) select it by environment
+            raw = os.environ.get("SRB_RAW_U8", "0") == "1"
         self.split, self.phase, self.raw = split, phase, raw
         self.data_aug = getattr(args, 'data_aug', False)
         self.mean, self.std = list(_MEAN), list(_STD)
@@ -116,7 +132,7 @@ class MetaImageNet(ImageNet):
     """Episodes: `self[i] -> (support_xs, support_ys, query_xs, query_ys)`."""
 
     def __init__(self, args, split, phase=None, train_transform=None, test_transform=None, fix_seed=True,
-                 use_episodes=False, disjoint_classes=False, raw=False):
+                 use_episodes=False, disjoint_classes=False, raw=None):
         if use_episodes:
             raise NotImplementedError("XtarNet episode files are outside the incremental-session path")
         super(MetaImageNet, self).__init__(args, split, phase, raw=raw)
@@ -128,7 +144,10 @@ class MetaImageNet(ImageNet):
         self.n_aug_support_samples = args.n_aug_support_samples
         self.n_base_aug_support_samples = args.n_base_aug_support_samples
         self.n_base_support_samples = args.n_base_support_samples
-        self.train_transform, self.test_transform = train_transform, test_transform
+        # like the reference (:242-262): no train_transform = RandomCrop + ColorJitter + RandomHorizontalFlip, no
+        # test_transform = ToTensor + Normalize
+        self.train_transform = transform_cfg.transforms_options['A'][0] if train_transform is None else train_transform
+        self.test_transform = test_transform
         # images of a class, in store order; classes in order of first appearance, then shuffled with the run's seed
         lab = np.asarray(self.labels)
         self._members = {}

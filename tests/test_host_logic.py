@@ -146,7 +146,9 @@ def test_episode_front_end_matches_the_reference_sampler(tmp_path):
     import numpy as np
     import torch
     from dataset.mini_imagenet import ImageNet, MetaImageNet
+    from dataset.transform_cfg import transforms_test_options
     from srb200 import synthetic
+    plain = transforms_test_options['A'][1]      # ToTensor + Normalize (what the golden run passed on both branches)
     gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "episodes.pt"), weights_only=False)
     root = synthetic.write_image_store(str(tmp_path / "store"))
     for seed, g in gold.items():
@@ -164,7 +166,8 @@ def test_episode_front_end_matches_the_reference_sampler(tmp_path):
         assert all(base[i][1] == base.labels[i] - min(base.labels) and base[i][2] == i for i in probe[:5])
 
         for raw in (False, True):
-            sup = MetaImageNet(args=a, split='train', phase='train', fix_seed=True, use_episodes=False, raw=raw)
+            sup = MetaImageNet(args=a, split='train', phase='train', train_transform=plain, test_transform=plain,
+                               fix_seed=True, use_episodes=False, raw=raw)
             assert len(sup) == g['exemplar_len']
             for item, want in zip((0, 3), g['exemplars']):
                 sx, sy, qx, qy = sup[item]
@@ -173,7 +176,8 @@ def test_episode_front_end_matches_the_reference_sampler(tmp_path):
                     assert sx.dtype == torch.uint8 and np.array_equal(synthetic.image_ids(sx.numpy()), want['ids'])
                 else:
                     assert sx.dtype == torch.float32 and tuple(sx.shape[1:]) == (3, 4, 4)
-            val = MetaImageNet(args=a, split='val', fix_seed=True, use_episodes=False, disjoint_classes=True, raw=raw)
+            val = MetaImageNet(args=a, split='val', train_transform=plain, test_transform=plain, fix_seed=True,
+                               use_episodes=False, disjoint_classes=True, raw=raw)
             assert len(val) == g['val_len'] and list(val.label2human) == g['val_label2human']
             for item, want in enumerate(g['sessions']):
                 sx, sy, qx, qy = val[item]
@@ -222,3 +226,72 @@ def test_rng_thread_share_between_local_ranks(monkeypatch):
     monkeypatch.setenv("SRB_RNG_THREADS", "3")
     sdist.init()
     assert os.environ["SRB_RNG_THREADS"] == "3"          # an explicit setting wins
+
+
+def test_support_augmentation_is_never_dropped(tmp_path):
+    """The reference's support transform (RandomCrop(84, padding 8) + RandomHorizontalFlip, transform_cfg.py:32-40) on the
+    uint8 front end: MetaImageNet(raw=True) with transforms_test_options['A'] returns the SAME pixels torchvision produces
+    (before ToTensor / Normalize) and leaves torch's generator in the same state; a transform it cannot express on uint8
+    (ColorJitter, the reference's default when train_transform is None) raises instead of being skipped."""
+    import argparse
+    import numpy as np
+    import pytest
+    import torch
+    from dataset.mini_imagenet import MetaImageNet
+    from dataset.transform_cfg import transforms_test_options, mean, std
+    from srb200 import synthetic
+    root = synthetic.write_image_store(str(tmp_path / "store"), side=84, per_class=30, n_classes=100, light=True)
+    a = argparse.Namespace(data_root=root, data_aug=False, set_seed=3, continual=True, n_ways=5, n_shots=5, n_queries=15,
+                           n_test_runs=8, eval_mode="few-shot-incremental-fine-tune", n_aug_support_samples=5,
+                           n_base_aug_support_samples=1, n_base_support_samples=1)
+    sup_t, qry_t = transforms_test_options['A']
+    ref = MetaImageNet(args=a, split='val', train_transform=sup_t, test_transform=qry_t, fix_seed=True, disjoint_classes=True)
+    raw = MetaImageNet(args=a, split='val', train_transform=sup_t, test_transform=qry_t, fix_seed=True, disjoint_classes=True,
+                       raw=True)
+    torch.manual_seed(7)
+    sx, sy, qx, qy = ref[0]
+    state_ref = torch.get_rng_state()
+    torch.manual_seed(7)
+    rx, ry, rqx, rqy = raw[0]
+    assert torch.equal(torch.get_rng_state(), state_ref)
+    assert rx.dtype == torch.uint8 and tuple(rx.shape) == (125, 84, 84, 3)
+    m = torch.tensor(mean).view(1, 3, 1, 1)
+    sd = torch.tensor(std).view(1, 3, 1, 1)
+    want = rx.permute(0, 3, 1, 2).float().div(255).sub(m).div(sd)
+    assert torch.equal(want, sx)                       # same crop, same flip, same pixels
+    assert not torch.equal(rx[:25], rx[25:50])         # the tiled copies really are augmented differently
+    assert torch.equal(rqx.permute(0, 3, 1, 2).float().div(255).sub(m).div(sd), qx)
+    with pytest.raises(NotImplementedError):
+        MetaImageNet(args=a, split='val', fix_seed=True, disjoint_classes=True, raw=True)[0]
+
+
+def test_reference_format_checkpoint_round_trip(tmp_path):
+    """a checkpoint in the layout train_supervised.py:194-202 writes (argparse.Namespace opt, numpy-keyed
+    training_classes) is readable by the callers' PLAIN torch.load(path) once the shadow `models` package is imported
+    (torch >= 2.6 defaults to weights_only=True and would reject it), and its state dict loads into the shadow model."""
+    import argparse
+    import numpy as np
+    import torch
+    import models                                      # registers the safe globals
+    from models.util import create_model
+    from srb200 import synthetic
+    from srb200.checkpoint import load_backbone, load_reference_checkpoint, save_reference_checkpoint
+    opt = synthetic.default_opt(1)
+    net = synthetic.init_model(create_model, opt, 1)
+    path = str(tmp_path / "resnet18_last.pth")
+    mapping = {'map.weight': torch.randn(640, 300), 'map.bias': torch.randn(640)}
+    save_reference_checkpoint(path, net, {np.int64(7 + i): np.int64(i) for i in range(60)}, synthetic.LABELS,
+                              opt=argparse.Namespace(model='resnet18', continual=True), mapping=mapping)
+    ckpt = torch.load(path)                            # exactly what eval_incremental.py:86 does
+    assert set(ckpt) == {'opt', 'model', 'training_classes', 'label2human', 'mapping_linear_label2image'}
+    assert all(isinstance(k, np.int64) for k in ckpt['training_classes']) and ckpt['training_classes'][np.int64(7)] == 0
+    assert ckpt['opt'].model == 'resnet18' and ckpt['label2human'] == synthetic.LABELS
+    assert 'classifier.bias' not in ckpt['model'] and len(ckpt['model']) == 67 + 66     # SURVEY 8b key set
+    other = synthetic.init_model(create_model, opt, 2)
+    load_backbone(other, load_reference_checkpoint(path))
+    for (k, a), (_, b) in zip(net.state_dict().items(), other.state_dict().items()):
+        assert torch.equal(a, b), k
+    opt_b = synthetic.default_opt(1, linear_bias=True)
+    import pytest
+    with pytest.raises(ValueError):
+        load_backbone(synthetic.init_model(create_model, opt_b, 1), ckpt)
