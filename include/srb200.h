@@ -109,7 +109,12 @@ typedef struct sr_conv_args {
     int32_t epilogue;        /* SR_EPI_*                                                                 */
     void* out;               /* see SR_EPI_*                                                             */
     void* out_lo;            /* error-compensated mode, bf16 outputs: low plane (same shape as out)      */
-    double* stats;           /* SR_EPI_RAW_STATS only                                                    */
+    double* stats;           /* SR_EPI_RAW_STATS: per-channel sums; NULL = raw fp32 output only           */
+    /* The two fields below serve the tensor-core classifier head (csrc/head_tc.cu), which runs its two GEMMs
+     * (logits = X W^T, dW = dZ^T X; resnet_language.py:187 and its autograd) on this kernel as 1x1 convolutions. */
+    int32_t weights_per_image;      /* image n uses weight rows [n*cout, (n+1)*cout): a batch of independent GEMMs  */
+                                    /*   (split-K partial products); needs height*width >= 1024                     */
+    const int32_t* skip_if_nonzero; /* optional DEVICE flag read at kernel start: non-zero = the launch does nothing */
 } sr_conv_args;
 
 int32_t sr_conv(const sr_conv_args* a, void* stream);

@@ -83,6 +83,8 @@ struct ConvParams {
     void* out;
     void* out_lo;
     double* stats;
+    const int* skip;    // optional device flag: a non-zero value turns the launch into a no-op (chained head epochs)
+    int w_per_img;      // weights differ per image: image n uses rows [n*Cout, (n+1)*Cout) of the weight tensor (split-K GEMMs)
     long long* trace;   // SRB_CONV_DBG & 16: clock64 stamps of CTA 0, [tile][8 events]
 };
 
@@ -196,6 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     // (fp32-valued addends, < 2^29 of them): the batch statistics do not depend on the execution order.
     float* const s_part = reinterpret_cast<float*>(staging);
 
+    if (p.skip != nullptr && *p.skip != 0) return;   // uniform over the grid; nothing has been allocated yet
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int sub_dh = p.stack_h ? p.TH : 0;
@@ -264,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                         dw = o - (dh + 1) * 3 - 1;
                     }
                     const int w = tc.w0 + dw, h = tc.h0 + dh;
+                    const int co_row = tc.co0 + (p.w_per_img ? tc.n0 * p.Cout : 0);
                     int krow = o * cin_pad;
                     for (int cb = 0; cb < ncb; ++cb, krow += kc) {
                         mbar_wait_a(a_empty + 8u * s, ph ^ 1u);
@@ -275,12 +279,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
                             mbar_expect_tx_a(fb, tx);
                             tma_load_4d_a(slot, &pn.tmA, fb, cb * kc, w, h, tc.n0);
                             if (reuse) {
-                                tma_load_2d_a(slot + (uint32_t)p.b_off, &pn.tmB, fb, krow, tc.co0);
-                                tma_load_2d_a(slot + (uint32_t)p.b_off + b_tile, &pn.tmB, fb, krow + 3 * cin_pad, tc.co0);
-                                tma_load_2d_a(slot + (uint32_t)p.b_off + 2u * b_tile, &pn.tmB, fb, krow + 6 * cin_pad, tc.co0);
+                                tma_load_2d_a(slot + (uint32_t)p.b_off, &pn.tmB, fb, krow, co_row);
+                                tma_load_2d_a(slot + (uint32_t)p.b_off + b_tile, &pn.tmB, fb, krow + 3 * cin_pad, co_row);
+                                tma_load_2d_a(slot + (uint32_t)p.b_off + 2u * b_tile, &pn.tmB, fb, krow + 6 * cin_pad, co_row);
                             } else {
                                 tma_load_4d_a(slot + (uint32_t)p.sub_stride, &pn.tmA, fb, cb * kc, w, h + sub_dh, tc.n0 + sub_dn);
-                                tma_load_2d_a(slot + (uint32_t)p.b_off, &pn.tmB, fb, krow, tc.co0);
+                                tma_load_2d_a(slot + (uint32_t)p.b_off, &pn.tmB, fb, krow, co_row);
                             }
                         }
                         __syncwarp();
@@ -430,6 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = 0.f;
                     }
+                    if (p.stats == nullptr) return;   // plain fp32 GEMM output (the tensor-core head): no statistics
                     float sq[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
@@ -634,7 +639,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             if (warp == kEpiWarp0) SRB_TRACE(7);
             if (++as == p.acc_stages) { as = 0; aph ^= 1u; }
 
-            if (p.epi == SR_EPI_RAW_STATS) {
+            if (p.epi == SR_EPI_RAW_STATS && p.stats != nullptr) {
                 named_bar_sync(1, kEpiThreads);
                 for (int i = et; i < p.n_cta; i += kEpiThreads) {
                     float a = 0.f, b = 0.f;
@@ -836,6 +841,10 @@ int32_t plan_conv(const sr_conv_args* a, int max_dyn, ConvPlan* plan) {
     p.out = a->out;
     p.out_lo = a->out_lo;
     p.stats = a->stats;
+    p.skip = a->skip_if_nonzero;
+    p.w_per_img = a->weights_per_image ? 1 : 0;
+    if (p.w_per_img && !(tile.stack_h && tile.TN == 1))
+        return fail(SR_E_ARG, "sr_conv: weights_per_image needs a feature map whose tiles hold one image (H*W >= 1024)");
     if (2 * p.n_cta > 512) return fail(SR_E_ARG, "sr_conv: accumulators need %d TMEM columns", 2 * p.n_cta);
     p.acc_stages = std::min(4, 512 / (2 * p.n_cta));   // as many accumulator stages as TMEM holds
     p.tmem_cols = 512;                                 // one persistent CTA per SM owns all of TMEM
@@ -963,7 +972,6 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
         const int32_t rc = check_conv_args(a);
         if (rc != SR_OK) return rc;
     }
-    if (a->epilogue == SR_EPI_RAW_STATS && !a->stats) return fail(SR_E_ARG, "sr_conv: RAW_STATS needs stats");
     if (!a->out) return fail(SR_E_ARG, "sr_conv: null out");
     const bool precise = a->panel[0].act_lo != nullptr;
     if (precise && (a->epilogue == SR_EPI_ACT || a->epilogue == SR_EPI_ACT_POOL2) && !a->out_lo)
@@ -1007,7 +1015,8 @@ extern "C" int32_t sr_conv(const sr_conv_args* a, void* stream_v) {
             if (r != CUDA_SUCCESS) return fail(SR_E_CUDA, "sr_conv: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
         }
         {
-            cuuint64_t gdim[2] = {(cuuint64_t)sp.taps * sp.cin_pad, (cuuint64_t)a->cout};
+            cuuint64_t gdim[2] = {(cuuint64_t)sp.taps * sp.cin_pad,
+                                  (cuuint64_t)a->cout * (cuuint64_t)(a->weights_per_image ? a->batch : 1)};
             cuuint64_t gstr[1] = {(cuuint64_t)sp.taps * sp.cin_pad * 2};
             cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)p.n_cta};
             cuuint32_t est[2] = {1, 1};

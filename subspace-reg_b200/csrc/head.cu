@@ -603,6 +603,7 @@ extern "C" int64_t sr_head_workspace_bytes(const sr_head_args* a) {
     if (!a) return 0;
     int64_t n = head_layout(a).total;
     if (a->dim >= 64 && a->dim % 64 == 0) n = std::max<int64_t>(n, srb::head_small_workspace_bytes(a));
+    if (srb::head_tc_applicable(a)) n = std::max<int64_t>(n, srb::head_tc_workspace_bytes(a));
     return n;
 }
 
@@ -626,6 +627,8 @@ extern "C" int32_t sr_head_run(const sr_head_args* a, void* stream_v) {
         return fail(SR_E_ARG, "sr_head_run: resume_status must be a different block than status");
     // Paper-sized problems: everything constant over the session stays in shared memory (head_small.cu).
     if (srb::head_small_applicable(a)) return srb::head_small_run(a, stream);
+    // Large problems: the two GEMMs on tcgen05 (head_tc.cu).  SRB_HEAD_SIMT=1 keeps the fp32 SIMT kernel below (A/B checks).
+    if (srb::head_tc_applicable(a) && !getenv("SRB_HEAD_SIMT")) return srb::head_tc_run(a, stream);
     const HeadLayout L = head_layout(a);
     if (a->workspace_bytes < L.total) return fail(SR_E_SMALLWS, "sr_head_run: workspace %lld < %lld",
                                                   (long long)a->workspace_bytes, (long long)L.total);

@@ -35,6 +35,52 @@ def test_head_stress_config5():
     assert diag.head_case("config5 nb256", 10000, 0, 256, 0, 100, 512, L.SR_PULL_PROJECT, epochs=3)
 
 
+@pytest.mark.parametrize("adam", [False, True])
+def test_head_tensor_core_path_matches_simt_and_honours_the_stopping_rule(adam):
+    """The tcgen05 head (csrc/head_tc.cu: both GEMMs as error-compensated 1x1 convolutions) against the fp32 SIMT
+    head_kernel on the same large problem - memory rows, previous-novel anchors, fixed pullers, SGD and Adam - including
+    the device-side stopping rule: max_novel_epochs = 4 inside a 10-epoch call stops after exactly 4 updates, and a
+    chained second call does nothing.  Loss terms and (SGD) weights at 1e-5; under Adam a weight whose gradient is ~0 moves
+    by +-lr on the sign of rounding noise (measured 3.7e-3 of max |W| after 4 steps), so only the losses are held tight."""
+    import os
+    from srb200 import ops, _lib as L
+    dev = "cuda"
+    res = {}
+    for mode in ("tc", "simt"):
+        if mode == "simt":
+            os.environ["SRB_HEAD_SIMT"] = "1"
+        else:
+            os.environ.pop("SRB_HEAD_SIMT", None)
+        try:
+            g = torch.Generator(device=dev).manual_seed(5)
+            Ns, Nm, nb, npv, nn_, d = 9000, 1000, 1000, 50, 50, 512
+            Cn = nb + npv + nn_
+            feat = (torch.randn(Ns + Nm, d, device=dev, generator=g) * 0.45 + 0.53).clamp_min(-0.11)
+            ys = torch.randint(0, Cn, (Ns,), device=dev, generator=g)
+            ym = torch.randint(0, Cn, (Nm,), device=dev, generator=g)
+            W = (torch.rand(Cn, d, device=dev, generator=g) * 2 - 1) / d ** 0.5
+            base = W[:nb].clone() + 0.01 * torch.randn(nb, d, device=dev, generator=g)
+            reserve = W[nb:nb + npv].clone() + 0.01 * torch.randn(npv, d, device=dev, generator=g)
+            pull = torch.randn(nn_, d, device=dev, generator=g) / d ** 0.5
+            hs = ops.HeadSession(feat, Ns, 0, ys, W, nb, nn_, n_memory=Nm, memory_row0=Ns, labels_memory=ym, base_weight=base,
+                                 reserve_weight=reserve, pull_mode=L.SR_PULL_FIXED, pull=pull, lmbd_base=0.2, lmbd_novel=0.1,
+                                 gamma=1.0, adam=adam, lr=0.002, stable=False, target_train_loss=-1.0, min_novel_epochs=0,
+                                 max_novel_epochs=4)
+            hs.run(10, defer=True)
+            hs.run(10, defer=True)            # chained on the device: must find the rule already fired
+            tr = hs.collect()
+            res[mode] = (hs.epochs, hs.stopped, tr.clone(), W.clone())
+        finally:
+            os.environ.pop("SRB_HEAD_SIMT", None)
+    (e1, s1, t1, w1), (e2, s2, t2, w2) = res["tc"], res["simt"]
+    assert e1 == e2 == 4 and s1 and s2
+    rel_t = ((t1[:, :6] - t2[:, :6]).abs().max() / t2[:, :6].abs().max()).item()
+    rel_w = ((w1 - w2).abs().max() / w2.abs().max()).item()
+    print("tensor-core head vs SIMT head: loss terms rel %.2e, W rel %.2e, hits equal %s" %
+          (rel_t, rel_w, bool((t1[:, 6:] == t2[:, 6:]).all())))
+    assert rel_t < 1e-5 and rel_w < (1e-2 if adam else 1e-5)
+
+
 def test_eval_logits_properties():
     """Scoring: predictions equal torch.argmax, hit counts / CE equal the reference's accuracy() + CrossEntropyLoss, the
     confusion matrix sums to n and its trace equals the top-1 hits."""
