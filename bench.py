@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--base-batch", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-epochs", type=int, default=2, help="epochs per session in the bounded CPU sample")
+    ap.add_argument("--concurrency", type=int, default=0,
+                    help="sweeps (seeds) in flight per GPU, each on its own host thread + CUDA stream; 0 = auto")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"], help="convolution tier of the b200 arm")
     return ap.parse_args()
 
 
@@ -147,21 +150,30 @@ def run_sweep(prepared):
     import torch
     from eval.language_eval import few_shot_finetune_incremental_test
     world, net, ckpt = prepared
+    few_shot_finetune_incremental_test(net, ckpt, torch.nn.CrossEntropyLoss(), world.meta_valloader,
+                                       world.base_val_loader, world.opt, base_support_loader=world.base_support_loader)
+    return net._last_record
+
+
+def run_sweeps(worlds, pool):
+    """All `worlds`, at most pool.workers in flight (one host thread + CUDA stream each); the reference's prints go nowhere."""
     with contextlib.redirect_stdout(io.StringIO()):
-        few_shot_finetune_incremental_test(net, ckpt, torch.nn.CrossEntropyLoss(), world.meta_valloader,
-                                           world.base_val_loader, world.opt, base_support_loader=world.base_support_loader)
-    return few_shot_finetune_incremental_test.last_record
+        if pool is None:
+            return [run_sweep(w) for w in worlds]
+        return pool.map(run_sweep, worlds)
 
 
-def timed_sweeps(worlds, device):
-    """CUDA-event time (ms) of running all `worlds` back to back on the current stream + records."""
+def timed_sweeps(worlds, device, pool):
+    """CUDA-event time (ms) from before the first to after the last of `worlds` (device-wide: the closing event is
+    recorded after every stream has been synchronised) + records."""
     import torch
     from srb200 import dist as sdist
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sdist.barrier()
     torch.cuda.synchronize()
     e0.record()
-    recs = [run_sweep(w) for w in worlds]
+    recs = run_sweeps(worlds, pool)
+    torch.cuda.synchronize()
     e1.record()
     torch.cuda.synchronize()
     sdist.barrier()
@@ -277,7 +289,24 @@ def main():
     wdir = word_embed_dir()
 
     def mk(seed):
-        return synthetic.make_world(seed, n_sessions=args.sessions, n_base_batch=args.base_batch, word_embed_path=wdir)
+        return synthetic.make_world(seed, n_sessions=args.sessions, n_base_batch=args.base_batch, word_embed_path=wdir,
+                                    conv_precision=args.precision)
+
+    # sweeps in flight per GPU: each needs a host thread for its launches plus the mask threads, so the number follows the
+    # host cores this rank can use (SRB_RNG_THREADS is set by dist.init from the node's core count)
+    conc = args.concurrency
+    if conc <= 0:
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        cores = max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world_size))))
+        conc = 3 if cores >= 12 else (2 if cores >= 6 else 1)
+    conc = max(1, min(conc, args.steps))
+    from srb200.concurrent import SeedPool
+    pool = SeedPool(conc, device) if conc > 1 else None
+    config["sweeps_in_flight_per_gpu"] = conc
+    config["conv_precision"] = args.precision
 
     # seeds: rank r owns seed index r, r + world, ... (warm-up uses its own seeds)
     warm = [mk(1000 + rank + world_size * k) for k in range(args.warmup)]
@@ -290,8 +319,7 @@ def main():
     # warm-up is then at least the timed region's, whatever --steps / --warmup are)
     worlds = [prepare(place_world(mk(s), 'gpu')) for s in timed_seeds]
     warm = [prepare(place_world(w, 'gpu')) for w in warm]
-    for w in warm:
-        run_sweep(w)
+    run_sweeps(warm, pool)
     del warm
 
     # ---- value: inputs already resident in HBM ----
@@ -299,7 +327,7 @@ def main():
     torch.cuda.synchronize()
     l0 = ops.LAUNCHES[0]
     sampler.start()
-    ms, recs = timed_sweeps(worlds, device)
+    ms, recs = timed_sweeps(worlds, device, pool)
     clocks = sampler.stop()
     launches = ops.LAUNCHES[0] - l0
     del worlds
@@ -314,7 +342,7 @@ def main():
     # ---- e2e: same sweeps through the public API with PINNED HOST inputs (H2D + result D2H inside the region) ----
     worlds = [prepare(place_world(mk(s), 'pinned')) for s in timed_seeds]
     h2d = sum(world_bytes(w[0]) for w in worlds) / max(len(worlds), 1)
-    ms_e2e, recs_e2e = timed_sweeps(worlds, device)
+    ms_e2e, recs_e2e = timed_sweeps(worlds, device, pool)
     del worlds
     epochs_e2e = sum(sum(s['epochs'] for s in r['sessions']) for r in recs_e2e)
     ms_e2e_max = sdist.max_over_ranks(ms_e2e, device)

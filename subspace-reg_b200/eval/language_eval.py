@@ -27,6 +27,7 @@ from dataset.memory import Memory
 from models.resnet_language import LangPuller
 from srb200 import _lib as L
 from srb200 import ops
+from srb200 import rng
 from .util import AverageMeter, drop_a_dim, freeze_backbone_weights, get_vocabs, log_episode, percent
 
 
@@ -102,8 +103,7 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
     if getattr(opt, 'conv_precision', None):     # 'bf16' | 'bf16x3' (not a reference flag: the B200 precision tier)
         net.set_conv_precision(opt.conv_precision)
 
-    torch.manual_seed(opt.set_seed)
-    np.random.seed(opt.set_seed)
+    rng.manual_seed(opt.set_seed)          # torch.manual_seed + np.random.seed (of this thread's run, srb200/rng.py)
 
     basenet = copy.deepcopy(net).cuda()
     base_weight, base_bias = basenet._get_base_weights()
@@ -354,7 +354,7 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         tm['images_scored'] += n_query + base_x.shape[0]
 
         if opt.memory_replay:
-            inds = np.random.choice(opt.n_shots, opt.memory_replay)
+            inds = rng.np_random().choice(opt.n_shots, opt.memory_replay)
             margin = 5 * np.arange(5)
             offset = np.arange(0, 125, 25)
             inds = np.tile(margin + inds, (5, 1)) + (np.tile(offset, (5, 1))).T

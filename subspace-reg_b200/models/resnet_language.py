@@ -9,6 +9,7 @@ import torch.nn as nn
 
 from srb200 import autograd as sra
 from srb200 import ops
+from srb200 import rng
 from srb200.backbone import BackboneEngine
 from .util import get_embeds
 
@@ -62,7 +63,15 @@ class LangPuller(nn.Module):
         self.novel_embeds = self._load(vocab_novel)
 
     def create_pulling_mapping(self, state_dict, base_weight_size=640):
-        self.mapping_model = LinearMap(self.novel_embeds.size(1), base_weight_size)
+        if rng.private():
+            # (a run on a private generator: consume the draws LinearMap's nn.Linear init makes, then build the module
+            # without touching the process-global generator's stream semantics)
+            rng.linear_init(base_weight_size, self.novel_embeds.size(1), True)
+            saved = torch.get_rng_state()
+            self.mapping_model = LinearMap(self.novel_embeds.size(1), base_weight_size)
+            torch.set_rng_state(saved)
+        else:
+            self.mapping_model = LinearMap(self.novel_embeds.size(1), base_weight_size)
         self.mapping_model.load_state_dict(state_dict)
         self.mapping_model = self.mapping_model.cuda()
 
@@ -258,10 +267,9 @@ class ResNet(nn.Module):
         base_weight = self.classifier.weight.detach()
         base_bias = self.classifier.bias.detach() if self.classifier.bias is not None else None
         if novel_weight is None:
-            novel_classifier = nn.Linear(base_weight.size(1), n, bias=(base_bias is not None))
-            novel_weight = novel_classifier.weight.detach()
+            novel_weight, drawn_bias = rng.linear_init(n, base_weight.size(1), base_bias is not None)
             if base_bias is not None and novel_bias is None:
-                novel_bias = novel_classifier.bias.detach()
+                novel_bias = drawn_bias
         augmented = torch.cat([base_weight, novel_weight.to(base_weight.device)], 0)
         self.classifier.weight = nn.Parameter(augmented, requires_grad=True)
         if base_bias is not None:

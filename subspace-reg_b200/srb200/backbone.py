@@ -12,6 +12,7 @@ import torch.nn.functional as F
 
 from . import _lib as L
 from . import host_rng
+from . import rng
 from . import ops
 
 SLOPE = 0.1
@@ -50,6 +51,7 @@ class BackboneEngine(object):
         self._db_done = True
         self._db_cv = threading.Condition()
         self._pf_fwd = 0          # index of the next train-mode forward relative to the prefetch plan
+        self._pool_owner = threading.get_ident()   # staging buffers are pooled per run thread (helper threads use the owner's)
 
     # ---------------------------------------------------------------- weight packing
     def _bn_key(self):
@@ -260,9 +262,9 @@ class BackboneEngine(object):
         if got is None:
             return None
         before, after, ent, kept, g, shp = got
-        if g != gamma or tuple(shp) != tuple(shape) or not torch.equal(torch.get_rng_state(), before):
+        if g != gamma or tuple(shp) != tuple(shape) or not torch.equal(rng.get_state(), before):
             return None
-        torch.set_rng_state(after)
+        rng.set_state(after)
         return ent, kept
 
     def mask_prefetch_alive(self):
@@ -273,6 +275,7 @@ class BackboneEngine(object):
         n = 1
         for d in shape:
             n *= int(d)
+        key = (self._pool_owner,) + tuple(key)     # one pool per run thread: concurrent runs never share a buffer
         flat = _SCRATCH_POOL.get(key)
         if flat is None or flat.numel() < n:
             flat = torch.empty(1 << max(int(n - 1).bit_length(), 12), dtype=torch.uint8)
@@ -284,6 +287,7 @@ class BackboneEngine(object):
         n = 1
         for d in shape:
             n *= int(d)
+        key = (self._pool_owner,) + tuple(key)     # one pool per run thread: concurrent runs never share a buffer
         ent = _PINNED_POOL.get(key)     # process-wide: cudaHostAlloc is far too slow to repeat per model instance
         if ent is None or ent[2].numel() < n:
             cap = 1 << max(int(n - 1).bit_length(), 12)          # power-of-two capacity: batches grow session by session

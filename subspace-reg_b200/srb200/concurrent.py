@@ -1,0 +1,68 @@
+"""Several independent runs (seeds) in flight on ONE GPU: a host thread + CUDA stream + private CPU generators per run.
+
+A sweep alternates phases that cannot fill a B200 on their own - the persistent head kernel is latency-bound on ~85 SMs,
+a train-mode pass pushes a few hundred images through ~65 small launches, the host draws masks in between - so the device
+is shared by K runs whose phases interleave: while one run's head loop spins on its grid barriers another run's
+convolutions take the idle SMs.  Runs share nothing (the reference runs one process per seed: scripts/continual/
+slurm_subspace_reg.sh:7-8,25), so there is no data-path synchronisation between the threads; ctypes and PyTorch release
+the GIL while they enqueue, and the numbers of a run do not depend on K (srb200.rng binds private generators).
+"""
+import queue
+import threading
+
+import torch
+
+from . import host_rng
+from . import rng
+
+
+class SeedPool(object):
+    """K persistent worker threads, each with its own CUDA stream.  map(fn, items) runs fn(item) for every item, at most K
+    at a time, and returns the results in order; exceptions are re-raised in the caller."""
+
+    def __init__(self, workers, device=None):
+        self.workers = max(1, int(workers))
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        host_rng.replay_available()              # the generator self-check touches the global generator: do it here, once
+        self._q = queue.Queue()
+        self._threads = [threading.Thread(target=self._work, daemon=True) for _ in range(self.workers)]
+        for t in self._threads:
+            t.start()
+
+    def _work(self):
+        torch.cuda.set_device(self.device)
+        stream = torch.cuda.Stream(device=self.device)
+        while True:
+            job = self._q.get()
+            if job is None:
+                return
+            fn, item, out, idx, done = job
+            try:
+                with torch.cuda.stream(stream), rng.scope():
+                    out[idx] = (True, fn(item))
+                    stream.synchronize()
+            except BaseException as e:            # noqa: BLE001 - handed to the caller
+                out[idx] = (False, e)
+            done.release()
+
+    def map(self, fn, items):
+        items = list(items)
+        out = [None] * len(items)
+        done = threading.Semaphore(0)
+        torch.cuda.current_stream().synchronize()     # inputs prepared on the caller's stream are complete
+        for i, it in enumerate(items):
+            self._q.put((fn, it, out, i, done))
+        for _ in items:
+            done.acquire()
+        res = []
+        for ok, v in out:
+            if not ok:
+                raise v
+            res.append(v)
+        return res
+
+    def close(self):
+        for _ in self._threads:
+            self._q.put(None)
+        for t in self._threads:
+            t.join()

@@ -12,29 +12,31 @@ import threading
 import torch
 
 from . import _lib as L
+from . import rng
 
 _replay_ok = None
 
 
 def _torch_draw(shape, p, kind):
+    g = rng.generator()
     if kind == 0:
-        return torch.empty(shape, dtype=torch.uint8).bernoulli_(p)
+        return torch.empty(shape, dtype=torch.uint8).bernoulli_(p, generator=g)
     probs = torch.tensor(p)                       # float32, like torch.distributions.Bernoulli(gamma).probs
-    return torch.bernoulli(probs.expand(shape)).to(torch.uint8)
+    return torch.bernoulli(probs.expand(shape), generator=g).to(torch.uint8)
 
 
 def _replay_draw(shape, p, kind, out=None):
     n = 1
     for s in shape:
         n *= int(s)
-    state = torch.get_rng_state()
+    state = rng.get_state()
     if out is None:
         out = torch.empty(shape, dtype=torch.uint8)
     ones = L.load().sr_host_bernoulli(C.c_void_p(state.data_ptr()), state.numel(), kind, float(p), n,
                                       C.c_void_p(out.data_ptr()))
     if ones < 0:
         raise RuntimeError("srb200: unexpected torch CPU generator state layout")
-    torch.set_rng_state(state)
+    rng.set_state(state)
     return out, int(ones)
 
 
@@ -129,7 +131,7 @@ class MaskPrefetch(object):
         if not self.ok:
             self.dead = True
             return
-        self._state = torch.get_rng_state().clone()
+        self._state = rng.get_state().clone()
         self._steps = steps
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
@@ -192,9 +194,9 @@ class MaskPrefetch(object):
             return None
         self._pending -= 1
         before, after, buf, ones = ent
-        if tuple(buf.shape) != tuple(shape) or not torch.equal(torch.get_rng_state(), before):
+        if tuple(buf.shape) != tuple(shape) or not torch.equal(rng.get_state(), before):
             self.dead = True           # the stream went somewhere else: everything drawn after this point is void too
             self.results = {}
             return None
-        torch.set_rng_state(after)
+        rng.set_state(after)
         return buf, ones

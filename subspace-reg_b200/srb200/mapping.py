@@ -38,5 +38,5 @@ def fit_linear_map(label_embeds, targets, epochs=1000, lr=1.0, weight_decay=5e-4
         dW, db = ops.linear_bwd(dy, X, True)
         L.check(lib.sr_sgd_update(ops._ptr(W), ops._ptr(dW), W.numel(), lr, weight_decay, st), "sr_sgd_update")
         L.check(lib.sr_sgd_update(ops._ptr(b), ops._ptr(db), b.numel(), lr, weight_decay, st), "sr_sgd_update")
-        ops.LAUNCHES[0] += 3
+        ops.LAUNCHES.add(3)
     return {'map.weight': W, 'map.bias': b}, losses.cpu().tolist()

@@ -5,13 +5,29 @@ dtype), passes raw pointers + the current stream to libsrb200.so and returns tor
 No function in this module has a CPU or PyTorch-op fallback.
 """
 import ctypes as C
+import threading
 
 import torch
 
 from . import _lib as L
 
 _checked_devices = set()
-LAUNCHES = [0]   # number of srb200 kernels enqueued through this module (bench.py's gpu_launches)
+class _LaunchCounter(object):
+    """Number of srb200 kernels enqueued through this module (bench.py's gpu_launches): one slot per host thread, so
+    concurrent runs never lose an update; LAUNCHES[0] reads the total, LAUNCHES.add(n) adds to the caller's slot."""
+
+    def __init__(self):
+        self._slots = {}
+
+    def __getitem__(self, i):
+        return sum(self._slots.values())
+
+    def add(self, n=1):
+        k = threading.get_ident()
+        self._slots[k] = self._slots.get(k, 0) + n
+
+
+LAUNCHES = _LaunchCounter()
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
@@ -58,7 +74,7 @@ def pack_input(x_nchw, cpad=16, split=False):
     rc = L.load().sr_pack_input(_ptr(x_nchw, torch.float32, "x"), _ptr(y[0] if split else y), _ptr(y[1]) if split else None,
                                 B, Cc, H, W, cpad, _stream())
     L.check(rc, "sr_pack_input")
-    LAUNCHES[0] += 1
+    LAUNCHES.add(1)
     return y
 
 
@@ -69,7 +85,7 @@ def bn_fold(gamma, beta, running_mean, running_var, eps=1e-5):
     rc = L.load().sr_bn_fold(_ptr(gamma, torch.float32), _ptr(beta, torch.float32), _ptr(running_mean, torch.float32),
                              _ptr(running_var, torch.float32), eps, _ptr(scale), _ptr(shift), Cc, _stream())
     L.check(rc, "sr_bn_fold")
-    LAUNCHES[0] += 1
+    LAUNCHES.add(1)
     return scale, shift
 
 
@@ -89,7 +105,7 @@ def pack_input_u8(x_nhwc_u8, mean, std, cpad=16, crop_ij=None, flip=None, pad=0,
                                    _ptr(y[1]) if split else None, B, Cc, H, W, m, s, cpad,
                                    _ptr(crop_ij, torch.int32, "crop_ij"), _ptr(flip, torch.uint8, "flip"), int(pad), _stream())
     L.check(rc, "sr_pack_input_u8")
-    LAUNCHES[0] += 1
+    LAUNCHES.add(1)
     return y
 
 
@@ -105,7 +121,7 @@ def pack_weight(w_oihw, scale=None, cin_pad=None, out=None, split=False):
                                  _ptr(out[0] if split else out), _ptr(out[1]) if split else None, co, ci, kh, kw, cin_pad,
                                  _stream())
     L.check(rc, "sr_pack_weight")
-    LAUNCHES[0] += 1
+    LAUNCHES.add(1)
     return out
 
 
@@ -162,7 +178,7 @@ def conv(panels, cout, shift=None, residual=None, slope=0.1, epilogue=L.SR_EPI_A
         a.out = _ptr(out)
     a.stats = _ptr(stats, torch.float64, "stats")
     L.check(L.load().sr_conv(C.byref(a), _stream()), "sr_conv")
-    LAUNCHES[0] += 1
+    LAUNCHES.add(1)
     return out
 
 
@@ -174,7 +190,7 @@ def bn_finalize(stats, count, running_mean, running_var, eps=1e-5, momentum=0.1)
                                  _ptr(running_mean, torch.float32), _ptr(running_var, torch.float32), _ptr(mean),
                                  _ptr(invstd), Cc, _stream())
     L.check(rc, "sr_bn_finalize")
-    LAUNCHES[0] += 1
+    LAUNCHES.add(1)
     return mean, invstd
 
 
@@ -212,7 +228,7 @@ def bn_apply(raw, mean, invstd, gamma, beta, res_raw=None, res_bn=None, res_act=
     else:
         a.out = _ptr(out)
     L.check(L.load().sr_bn_apply(C.byref(a), _stream()), "sr_bn_apply")
-    LAUNCHES[0] += 1
+    LAUNCHES.add(1)
     return out
 
 
@@ -230,7 +246,7 @@ def subspace_factor(base_weight):
     rc = lib.sr_subspace_factor(_ptr(base_weight, torch.float32, "base_weight"), n, d, _ptr(qt), _ptr(info), _ptr(ws),
                                 ws.numel(), _stream())
     L.check(rc, "sr_subspace_factor")
-    LAUNCHES[0] += 4
+    LAUNCHES.add(4)
     info_h = info.cpu().tolist()
     if info_h[2] != 0:
         raise RuntimeError("srb200: base weights are rank deficient (Cholesky pivot %d <= 0)" % (info_h[2] - 1))
@@ -311,7 +327,7 @@ class HeadSession(object):
         a.max_epochs, a.epoch0, a.step0 = max_epochs, self.epochs, self.epochs
         a.stable_count0, a.prev_loss = self.stable_count, self.prev_loss
         L.check(L.load().sr_head_run(C.byref(a), _stream()), "sr_head_run")
-        LAUNCHES[0] += 1
+        LAUNCHES.add(1)
         self._pending.append((status, trace))
         if defer:
             return None
@@ -361,7 +377,7 @@ def eval_logits(feat, weight, labels, confusion=None):
     a.confusion = _ptr(confusion, torch.int64, "confusion")
     a.conf_dim = 0 if confusion is None else confusion.shape[0]
     L.check(L.load().sr_eval_logits(C.byref(a), _stream()), "sr_eval_logits")
-    LAUNCHES[0] += 2
+    LAUNCHES.add(2)
     return {"logits": logits, "pred": pred, "counts": counts, "loss_sum": loss_sum}
 
 
@@ -378,7 +394,7 @@ def semantic_pullers(novel_embeds, base_embeds, base_weight, temperature, mask=F
                                       _ptr(base_weight, torch.float32, "base_weight"), n, b, e, d, temperature, 1 if mask else 0,
                                       _ptr(out), _stream())
     L.check(rc, "sr_semantic_pullers")
-    LAUNCHES[0] += 1
+    LAUNCHES.add(1)
     return out
 
 
@@ -389,7 +405,7 @@ def linear_fwd(x, w, bias=None):
     rc = L.load().sr_linear_fwd(_ptr(x, torch.float32, "x"), _ptr(w, torch.float32, "w"), _ptr(bias, torch.float32, "bias"), n, k, m,
                                 _ptr(y), _stream())
     L.check(rc, "sr_linear_fwd")
-    LAUNCHES[0] += 1
+    LAUNCHES.add(1)
     return y
 
 
@@ -400,7 +416,7 @@ def linear_bwd(dy, x, want_bias):
     db = torch.empty(m, dtype=torch.float32, device=x.device) if want_bias else None
     rc = L.load().sr_linear_bwd(_ptr(dy, torch.float32, "dy"), _ptr(x, torch.float32, "x"), n, k, m, _ptr(dw), _ptr(db), _stream())
     L.check(rc, "sr_linear_bwd")
-    LAUNCHES[0] += 1
+    LAUNCHES.add(1)
     return dw, db
 
 
@@ -408,7 +424,7 @@ def sqdist(a, b):
     out = torch.empty(1, dtype=torch.float32, device=a.device)
     rc = L.load().sr_sqdist(_ptr(a, torch.float32, "a"), _ptr(b, torch.float32, "b"), a.numel(), _ptr(out), _stream())
     L.check(rc, "sr_sqdist")
-    LAUNCHES[0] += 1
+    LAUNCHES.add(1)
     return out
 
 
@@ -417,7 +433,7 @@ def diff_scale(a, b, scale, gout=None, sq=None):
     rc = L.load().sr_diff_scale(_ptr(a, torch.float32, "a"), _ptr(b, torch.float32, "b"), a.numel(), scale,
                                 _ptr(gout, torch.float32, "gout"), _ptr(sq, torch.float32, "sq"), _ptr(out), _stream())
     L.check(rc, "sr_diff_scale")
-    LAUNCHES[0] += 1
+    LAUNCHES.add(1)
     return out
 
 
@@ -426,7 +442,7 @@ def project_rows(x, qt, q_rows):
     out = torch.empty_like(x)
     rc = L.load().sr_project_rows(_ptr(x, torch.float32, "x"), _ptr(qt, torch.float32, "qt"), n, q_rows, d, _ptr(out), _stream())
     L.check(rc, "sr_project_rows")
-    LAUNCHES[0] += 1
+    LAUNCHES.add(1)
     return out
 
 
@@ -444,7 +460,7 @@ def score_logits(logits, labels, confusion=None):
     a.confusion = _ptr(confusion, torch.int64, "confusion")
     a.conf_dim = 0 if confusion is None else confusion.shape[0]
     L.check(L.load().sr_score_logits(C.byref(a), _stream()), "sr_score_logits")
-    LAUNCHES[0] += 1
+    LAUNCHES.add(1)
     return {"pred": pred, "counts": counts, "loss_sum": loss_sum}
 
 
@@ -457,5 +473,5 @@ def global_avg(x_nhwc):
     y = torch.empty((B, Cc), dtype=torch.float32, device=x_nhwc.device)
     rc = L.load().sr_global_avg(_ptr(x_nhwc, torch.bfloat16, "x"), _ptr(lo, torch.bfloat16, "x_lo"), _ptr(y), B, H, W, Cc, _stream())
     L.check(rc, "sr_global_avg")
-    LAUNCHES[0] += 1
+    LAUNCHES.add(1)
     return y

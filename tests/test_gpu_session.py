@@ -61,7 +61,7 @@ def test_session_vs_reference_golden(case, precision, golden_dir, word_embed_dir
     if case.startswith("adam"):
         # Adam divides by sqrt(v): where a gradient component is ~0 its sign - hence a step of +-lr - is decided by noise,
         # so classifier weights separate faster than under SGD (measured 7.8e-4 / 5e-3 after 3 epochs)
-        tol.update(W=tol['W'] * 100 if precision == "bf16x3" else 2e-2, loss=tol['loss'] * 5)
+        tol.update(W=tol['W'] * 100 if precision == "bf16x3" else 2e-2, loss=tol['loss'] * 5, reg=tol['reg'] * 50)
     world = _world(g, word_embed_dir, conv_precision=precision)
     rec, net = _run_b200(world, g['n_sessions'], g.get('ckpt_extra'))
     ref = g['reference']
@@ -132,3 +132,45 @@ def test_session_vs_oracle_converged(golden_dir, word_embed_dir):
             assert agree >= 0.99
             assert abs(rec['novel'][0] - orec['novel'][0]) <= 1.0
             assert abs(rec['base'][0] - orec['base'][0]) <= 1.6
+
+
+def test_concurrent_seeds_reproduce_sequential_runs(word_embed_dir):
+    """srb200.concurrent.SeedPool: three seeds in flight on one GPU (a host thread + CUDA stream + private CPU generators
+    each) give bit-identical records to the same seeds run one after another on the main thread with the process-global
+    generators - epochs, loss traces, final weights, BN buffers, predictions."""
+    import contextlib
+    import io
+    from eval.language_eval import few_shot_finetune_incremental_test
+    from models.util import create_model
+    from srb200 import synthetic
+    from srb200.concurrent import SeedPool
+
+    def prepare(seed):
+        world = synthetic.make_world(seed, n_sessions=3, n_base_batch=200, word_embed_path=word_embed_dir, max_novel_epochs=60)
+        world.opt.n_sessions_override = 3
+        net = synthetic.init_model(create_model, world.opt, seed)
+        ckpt = synthetic.make_ckpt(net, world)
+        return world, net.cuda(), ckpt
+
+    def run(prepared):
+        world, net, ckpt = prepared
+        few_shot_finetune_incremental_test(net, ckpt, torch.nn.CrossEntropyLoss(), world.meta_valloader, world.base_val_loader,
+                                           world.opt, base_support_loader=world.base_support_loader)
+        return net._last_record
+
+    seeds = [11, 12, 13]
+    with contextlib.redirect_stdout(io.StringIO()):
+        seq = [run(prepare(s)) for s in seeds]
+        pool = SeedPool(3)
+        try:
+            par = pool.map(run, [prepare(s) for s in seeds])
+        finally:
+            pool.close()
+    for s, a, b in zip(seeds, seq, par):
+        assert a['weighted'] == b['weighted'] and a['counters'] == b['counters'], s
+        for x, y in zip(a['sessions'], b['sessions']):
+            assert x['epochs'] == y['epochs']
+            assert np.array_equal(x['terms'], y['terms'])
+            assert torch.equal(x['W'], y['W'])
+            assert all(torch.equal(p, q) for p, q in zip(x['query_pred'], y['query_pred'])) and torch.equal(x['base_pred'], y['base_pred'])
+            assert all(torch.equal(x['bn'][k], y['bn'][k]) for k in x['bn'])

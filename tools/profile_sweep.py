@@ -54,7 +54,7 @@ def sweep_timing():
         prep = bench.prepare(bench.place_world(world, 'gpu'))
         torch.cuda.synchronize()
         t2 = time.perf_counter()
-        rec = bench.run_sweep(prep)
+        rec = bench.run_sweeps([prep], None)[0]
         torch.cuda.synchronize()
         t3 = time.perf_counter()
         print("sweep %d: make_world %.2fs prepare %.2fs sweep %.2fs; phases %s" % (it, t1 - t0, t2 - t1, t3 - t2, rec.get('phases')), flush=True)
