@@ -150,8 +150,10 @@ def run_sweep(prepared):
     import torch
     from eval.language_eval import few_shot_finetune_incremental_test
     world, net, ckpt = prepared
+    t0 = time.perf_counter()
     few_shot_finetune_incremental_test(net, ckpt, torch.nn.CrossEntropyLoss(), world.meta_valloader,
                                        world.base_val_loader, world.opt, base_support_loader=world.base_support_loader)
+    net._last_record['wall_ms'] = 1e3 * (time.perf_counter() - t0)   # host wall time of this sweep (it ends synchronised)
     return net._last_record
 
 
@@ -393,8 +395,11 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops (burst: the kernel is timed alone)" if peaks else "fallback 1.59 PF (burst)"
     # the same kernel INSIDE the timed sweeps: device time of the cache-build phases (pack + concatenation + convs, CUDA
     # events on the sweep's stream) over the images they encoded, against the sustained peak
-    cache_s = sum(r['phases']['cache'] for r in recs)
-    cache_imgs = sum(sum(185 + 25 * i + 125 * (i + 1) + args.base_batch for i in range(len(r['sessions']))) for r in recs)
+    # (with several sweeps in flight the events of one stream also span the other streams' kernels, so the phases are
+    # taken from one extra sweep run alone after the timed region)
+    solo = run_sweeps([prepare(place_world(mk(2000 + rank), 'gpu'))], None)
+    cache_s = sum(r['phases']['cache'] for r in solo)
+    cache_imgs = sum(sum(185 + 25 * i + 125 * (i + 1) + args.base_batch for i in range(len(r['sessions']))) for r in solo)
     in_sweep = GFLOP_PER_IMAGE * cache_imgs / max(cache_s, 1e-9) / 1e3
     peak_sus = peaks.get("bf16_tflops_sustained", 1400.0)
     roofline = {"bound": "tensor", "kernel": "conv_umma_kernel (18 convs + 4 fused 1x1 panels per image, eval-mode backbone pass)",
@@ -410,9 +415,9 @@ def main():
 
     # ---- second roofline entry: the fused head / regulariser kernel at the PAPER sizes (inside the timed sweeps) ----
     # algorithmic bytes per fine-tune step: features + labels + W/momentum read+write + W0 + reserve + factor
-    head_s = sum(r['phases']['head'] for r in recs)
+    head_s = sum(r['phases']['head'] for r in solo)
     head_bytes = 0.0
-    for r in recs:
+    for r in solo:
         for i, sess in enumerate(r['sessions']):
             n_rows, n_cls = 185 + 25 * i, 65 + 5 * i
             per_step = 4 * n_rows * 640 + 8 * n_rows + 4 * n_cls * 640 * 4 + 4 * 60 * 640 + 4 * 5 * i * 640 + 4 * 60 * 640
@@ -421,7 +426,7 @@ def main():
     head_gbs = head_bytes / max(head_s, 1e-9) / 1e9
     roofline_head = {"bound": "hbm", "kernel": "head_small_kernel (persistent fused head: logits, CE, regularisers, SGD; paper sizes)",
                      "achieved": head_gbs, "peak": hbm, "unit": "GB/s", "frac": head_gbs / hbm, "traffic": None,
-                     "us_per_step": 1e6 * head_s / max(epochs - sum(len(r['sessions']) for r in recs), 1),
+                     "us_per_step": 1e6 * head_s / max(sum(max(s_['epochs'] - 1, 0) for r in solo for s_ in r['sessions']), 1),
                      "note": "1.45-2.6 MB and 32-90 MFLOP per step: 0.2-0.4 us at HBM speed, i.e. latency-bound (two grid "
                              "barriers per step); the HBM fraction is reported for completeness (SURVEY 8d)"}
 
@@ -435,7 +440,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_max / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16 convs (fp32 accumulate) + f32 head", "data": "synthetic", "config": config,
             "epochs_per_step": epochs / max(args.steps, 1),
-            "phases_ms_per_step": {k: 1e3 * sum(r['phases'][k] for r in recs) / max(len(recs), 1) for k in recs[0]['phases']},
+            "sweep_wall_ms": [round(r['wall_ms'], 1) for r in recs], "sweep_wall_ms_e2e": [round(r['wall_ms'], 1) for r in recs_e2e],
+            "phases_ms_per_step": {k: 1e3 * sum(r['phases'][k] for r in solo) / max(len(solo), 1) for k in solo[0]['phases']},
             "query_img_per_s": (scored / score_s) if score_s > 0 else None,
             "backbone_img_per_step": bb_imgs / max(args.steps, 1),
             "e2e": {"value": epochs_e2e_all / (ms_e2e_max * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": int(h2d),

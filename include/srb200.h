@@ -115,6 +115,8 @@ typedef struct sr_conv_args {
     int32_t weights_per_image;      /* image n uses weight rows [n*cout, (n+1)*cout): a batch of independent GEMMs  */
                                     /*   (split-K partial products); needs height*width >= 1024                     */
     const int32_t* skip_if_nonzero; /* optional DEVICE flag read at kernel start: non-zero = the launch does nothing */
+    int32_t max_cout_per_cta;       /* 0 = 256; smaller N tiles (>= 32) trade MMA width for more tiles and a second   */
+                                    /*   TMEM accumulator stage (epilogue overlaps the next tile's main loop)          */
 } sr_conv_args;
 
 int32_t sr_conv(const sr_conv_args* a, void* stream);

@@ -46,6 +46,7 @@ constexpr int kStagePitchBf16 = 80; // bytes per staged row (32 bf16 + pad, conf
 constexpr int kStagePitchF32 = 33;  // floats per staged row (32 fp32 + 1)
 constexpr int kMaxPanels = 6;       // 2 for plain bf16; 2 x 3 in the error-compensated mode (hi*hi + hi*lo + lo*hi)
 constexpr int kLoStaging = 2 * kSubRows * kStagePitchBf16;   // byte offset of the "lo" half rows in the staging tile
+constexpr int kStagePitchRaw = 80;  // bytes per staged fp32 half row of the raw epilogue (16 fp32 + 16 pad)
 
 struct PanelDev {
     CUtensorMap tmA;  // rank 4: (C, W, H, N); box (KC, TW, TH, TN), or the tall box (KC, TW, 2*TH+2, 1) when `reuse`
@@ -376,6 +377,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         // SR_EPI_ACT writes go through a warp-private transposition in shared memory so that one store instruction covers
         // 8 pixels x 64 contiguous bytes (a thread's own 64 bytes sit Cout*2 bytes apart from its neighbour's: 32 partial
         // lines per instruction).  This lane then stores 16-byte piece (lane & 3) of rows (lane >> 2) + 8 i, i = 0..3.
+        // The raw fp32 epilogue (train-mode BN input, GEMM outputs) does the same per 16-channel half (64 bytes of fp32):
+        // the staging tile then costs no more shared memory than the bf16 one, which keeps the three-stage tall-box ring
+        // of the 84x84 layers.
+        const bool raw_mode = p.epi == SR_EPI_RAW_STATS;
         const int piece = lane & 3;
         // element offsets relative to the tile origin (sub-tile included); tile-independent
         const int sub_n = sub * sub_dn, sub_h = sub * sub_dh;
@@ -389,12 +394,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             const int rh = rr / p.TW;
             t_nl[i] = (r < p.rows_sub ? rn : (1 << 20)) + sub_n;   // rows past the box are never valid
             t_hl[i] = rh + sub_h;
-            t_rel[i] = (((rn + sub_n) * p.H + rh + sub_h) * p.W + (rr - rh * p.TW)) * p.Cout + piece * 8;
+            t_rel[i] = (((rn + sub_n) * p.H + rh + sub_h) * p.W + (rr - rh * p.TW)) * p.Cout + (raw_mode ? piece * 4 : piece * 8);
         }
         const uint32_t stg_s = smem_u32(staging);
         const uint32_t shift_s = smem_u32(s_shift);
         const uint32_t my_row = stg_s + (uint32_t)((sub * kSubRows + m) * kStagePitchBf16);
         const uint32_t t_rows = stg_s + (uint32_t)((sub * kSubRows + q * 32 + (lane >> 2)) * kStagePitchBf16 + piece * 16);
+        // raw epilogue: the fp32 tile is staged behind the statistics slots
+        const uint32_t raw_s = stg_s + (uint32_t)(2 * kEpiWarps * p.n_cta * 4);
+        const uint32_t raw_my = raw_s + (uint32_t)((sub * kSubRows + m) * kStagePitchRaw);
+        const uint32_t raw_rows = raw_s + (uint32_t)((sub * kSubRows + q * 32 + (lane >> 2)) * kStagePitchRaw + piece * 16);
         if (p.epi != SR_EPI_RAW_STATS) {
             for (int i = et; i < p.Cout; i += kEpiThreads) s_shift[i] = p.shift ? __ldg(p.shift + i) : 0.f;
             named_bar_sync(1, kEpiThreads);
@@ -426,14 +435,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
             auto do_half = [&](float* v, int c16) {
                 const int cbase = tc.co0 + c16;
                 if (p.epi == SR_EPI_RAW_STATS) {
-                    if (valid) {
-                        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Cout + cbase);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    } else {
+                    if (!valid) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = 0.f;
                     }
+                    // fp32 half row (64 bytes) through the staging tile: one store instruction then covers 8 pixels x 64
+                    // contiguous bytes instead of 32 pixels x 16 bytes
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        sts128(raw_my + (uint32_t)(16 * j),
+                               make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                          __float_as_uint(v[4 * j + 3])));
+                    __syncwarp();
+                    {
+                        float* const o32 = reinterpret_cast<float*>(p.out) + origin * p.Cout + cbase;
+                        uint4 x[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) x[i] = lds128(raw_rows + (uint32_t)(8 * i * kStagePitchRaw));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (t_ok[i]) *reinterpret_cast<uint4*>(o32 + t_rel[i]) = x[i];
+                    }
+                    __syncwarp();   // the rows are rewritten by the next half
                     if (p.stats == nullptr) return;   // plain fp32 GEMM output (the tensor-core head): no statistics
                     float sq[16];
 #pragma unroll
@@ -803,10 +826,11 @@ int32_t plan_conv(const sr_conv_args* a, int max_dyn, ConvPlan* plan) {
     const int n_in = expand_panels(a, pin);
     // N split
     int ns = 0;
-    for (int c = 1; c <= 16; ++c) {
+    const int n_max = (a->max_cout_per_cta >= 32 && a->max_cout_per_cta < 256) ? a->max_cout_per_cta : 256;
+    for (int c = 1; c <= 64; ++c) {
         if (a->cout % c) continue;
         const int n = a->cout / c;
-        if (n % 32 == 0 && n <= 256) {
+        if (n % 32 == 0 && n <= n_max) {
             ns = c;
             break;
         }
@@ -854,7 +878,7 @@ int32_t plan_conv(const sr_conv_args* a, int max_dyn, ConvPlan* plan) {
     int staging = 0;   // the producer prefetches the next tile during the epilogue: staging cannot alias the pipeline
     if (a->epilogue == SR_EPI_ACT_POOL2 || a->epilogue == SR_EPI_ACT) staging = (precise ? 2 : 1) * kLoStaging;
     if (a->epilogue == SR_EPI_ACT_AVG) staging = 2 * kSubRows * kStagePitchF32 * 4;
-    if (a->epilogue == SR_EPI_RAW_STATS) staging = 2 * kEpiWarps * (a->cout / ns) * 4;
+    if (a->epilogue == SR_EPI_RAW_STATS) staging = 2 * kEpiWarps * (a->cout / ns) * 4 + 2 * kSubRows * kStagePitchRaw;
     p.staging_bytes = staging;
     const int shift_bytes = a->epilogue == SR_EPI_RAW_STATS ? 0 : (int)align_up((int64_t)a->cout * 4, 16);
     const int budget = max_dyn - 1024 - staging - shift_bytes;

@@ -15,6 +15,7 @@
 // Same arithmetic as head_kernel (head.cu) except that the projection gradient uses the closed form 2*gamma*(w - Pw)
 // (P is an orthogonal projector; the reference's autograd expression 2*gamma*(rP - r) differs by O(1e-8)).
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include "common.h"
 #include "head_common.cuh"
@@ -569,7 +570,13 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
 
 // Rows of X per row CTA: as few as keeps the grid within one wave (every row CTA streams all of W each epoch, so
 // fewer rows per CTA buy parallelism with L2 traffic).
-int pick_rows(int nt) { return nt <= 384 ? 4 : (nt <= 768 ? 8 : 16); }
+int pick_rows(int nt) {
+    if (const char* e = getenv("SRB_HEAD_ROWS")) {   // A/B timing only
+        const int v = atoi(e);
+        if (v == 4 || v == 8 || v == 16) return v;
+    }
+    return nt <= 384 ? 4 : (nt <= 768 ? 8 : 16);
+}
 
 struct SmallLayout {
     int64_t ctrl, DL, Wt, rowloss, rowhit, nb, nn, pull, u, total;

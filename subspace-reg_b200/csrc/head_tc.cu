@@ -21,6 +21,7 @@
 #include <cuda_bf16.h>
 #include "common.h"
 #include "head_common.cuh"
+#include "ptx.cuh"
 
 namespace {
 using namespace srb;
@@ -30,7 +31,7 @@ constexpr int kUpdElems = 1024;   // classifier elements per CTA of the update k
 constexpr int kMaxEpochsPerCall = 1024;
 
 struct TcGeom {
-    int N, d, C, Cp, S, slice, n_upd;
+    int N, d, C, Cp, Cz, S, slice, n_upd;   // Cp: class padding of the dW GEMM (256), Cz: of the logits GEMM / Z pitch (128)
     int n_rowctas;
     int64_t ctrl, start, Xp, XpT, Wp, Z, dZt, part, rowlse, rowpart, pull_sq, gpull, nbp, nnp, total;
 };
@@ -51,10 +52,11 @@ bool tc_geometry(const sr_head_args* a, TcGeom* g) {
     g->d = a->dim;
     g->C = a->n_classes;
     g->Cp = (int)align_up(a->n_classes, 256);
+    g->Cz = (int)align_up(a->n_classes, 128);
     // (the dW GEMM maps classes to a 2 x Cp/2 feature map whose tiles must hold one slice: Cp >= 1024)
     if (a->dim % 64 != 0 || a->dim > 2048 || g->Cp > 4096 || g->Cp < 1024) return false;
-    const int ns_c = split_for(g->Cp), ns_d = split_for(a->dim);
-    if (!ns_c || !ns_d) return false;
+    const int ns_d = split_for(a->dim);
+    if (!ns_d) return false;
     const int ctas_per_slice = (g->Cp / 256) * ns_d;
     g->S = std::max(1, std::min(148 / std::max(ctas_per_slice, 1), (g->N + 63) / 64));
     g->slice = (int)align_up((g->N + g->S - 1) / g->S, 64);
@@ -67,7 +69,7 @@ bool tc_geometry(const sr_head_args* a, TcGeom* g) {
     g->Xp = take(2ll * g->N * g->d * 2);
     g->XpT = take(2ll * g->S * g->d * g->slice * 2);
     g->Wp = take(2ll * g->Cp * g->d * 2);
-    g->Z = take((int64_t)g->N * g->Cp * 4);
+    g->Z = take((int64_t)g->N * g->Cz * 4);
     g->dZt = take(2ll * g->S * g->Cp * g->slice * 2);
     g->part = take((int64_t)g->S * g->Cp * g->d * 4);
     g->n_rowctas = (g->N + 7) / 8;
@@ -186,50 +188,50 @@ __global__ void __launch_bounds__(kT) tc_prep_w_kernel(const TcParams p) {
     if (threadIdx.x == 0 && (int)blockIdx.x < p.g.n_upd) { p.nbp[blockIdx.x] = nb; p.nnp[blockIdx.x] = nn; }
 }
 
-// Row statistics of Z: one warp per sample keeps its row in registers (one pass over memory): log-sum-exp, CE, top-1 /
-// top-5 rank of the label; per-CTA partial sums of the losses and hits for the loss kernel.
-constexpr int kRowRegs = 40;   // classes per lane held in registers: rows of up to 1280 classes; longer rows re-read memory
+// Row statistics of Z: one warp per sample; the row is brought into shared memory by ONE bulk asynchronous copy (few
+// registers, so six CTAs per SM keep ~200 KB of loads in flight), then log-sum-exp, CE and the top-1 / top-5 rank of the
+// label are computed from there; per-CTA partial sums of the losses and hits go to the loss kernel.
 constexpr int kRowsPerCta = kT / 32;
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 
 __global__ void __launch_bounds__(kT) tc_rowstats_kernel(const TcParams p) {
     if (p.ctrl->stop) return;
+    extern __shared__ __align__(128) float s_rows[];   // [kRowsPerCta][Cz]
+    __shared__ uint64_t s_bar[kRowsPerCta];
     __shared__ double s_part[kRowsPerCta][4];
     const sr_head_args& a = p.a;
-    const int C = p.g.C, Cp = p.g.Cp, N = p.g.N;
+    const int C = p.g.C, Cz = p.g.Cz, N = p.g.N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = blockIdx.x * kRowsPerCta + warp;
     double ls = 0.0, lm = 0.0, h1 = 0.0, h5 = 0.0;
     if (n < N) {
-        const float* z = p.Z + (int64_t)n * Cp;
+        const float* z = s_rows + warp * Cz;
+        const uint32_t bar = smem_u32(&s_bar[warp]);
+        if (lane == 0) {
+            mbar_init(&s_bar[warp], 1);
+            mbar_fence_init();
+            mbar_expect_tx_a(bar, (uint32_t)Cz * 4u);
+            bulk_load_1d(smem_u32(z), p.Z + (int64_t)n * Cz, (uint32_t)Cz * 4u, bar);
+        }
+        __syncwarp();
         const bool is_sup = n < a.n_support;
         const int y = (int)(is_sup ? a.labels_support[n] : a.labels_memory[n - a.n_support]);
-        float v[kRowRegs];
+        mbar_wait_a(bar, 0u);
         float mx = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < kRowRegs; ++i) {
-            const int c = lane + 32 * i;
-            v[i] = c < C ? __ldg(z + c) : -INFINITY;
-            mx = fmaxf(mx, v[i]);
-        }
-        for (int c = lane + 32 * kRowRegs; c < C; c += 32) mx = fmaxf(mx, z[c]);
+        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, z[c]);
         mx = warp_max(mx);
         float se = 0.f;
-#pragma unroll
-        for (int i = 0; i < kRowRegs; ++i) se += (lane + 32 * i < C) ? expf(v[i] - mx) : 0.f;
-        for (int c = lane + 32 * kRowRegs; c < C; c += 32) se += expf(z[c] - mx);
+        for (int c = lane; c < C; c += 32) se += expf(z[c] - mx);
         se = warp_sum(se);
         const float lse = mx + logf(se);
         const float zy = z[y];
         int greater = 0, tie_before = 0;
-#pragma unroll
-        for (int i = 0; i < kRowRegs; ++i) {
-            const int c = lane + 32 * i;
-            if (c < C) {
-                greater += v[i] > zy ? 1 : 0;
-                tie_before += (v[i] == zy && c < y) ? 1 : 0;
-            }
-        }
-        for (int c = lane + 32 * kRowRegs; c < C; c += 32) {
+        for (int c = lane; c < C; c += 32) {
             const float zc = z[c];
             greater += zc > zy ? 1 : 0;
             tie_before += (zc == zy && c < y) ? 1 : 0;
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(kT) tc_dz_kernel(const TcParams p) {
     __shared__ float s_lse[64], s_inv[64];
     __shared__ int s_y[64];
     const sr_head_args& a = p.a;
-    const int C = p.g.C, Cp = p.g.Cp, N = p.g.N;
+    const int C = p.g.C, Cp = p.g.Cp, Cz = p.g.Cz, N = p.g.N;
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
     const int col = tid & 63, rq = tid >> 6;
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(kT) tc_dz_kernel(const TcParams p) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int n = n0 + i * 4 + rq, c = c0 + col;
-        z[i] = (n < N && c < C) ? __ldg(p.Z + (int64_t)n * Cp + c) : 0.f;
+        z[i] = (n < N && c < C) ? __ldg(p.Z + (int64_t)n * Cz + c) : 0.f;
     }
     if (tid < 64) {
         const int n = n0 + tid;
@@ -370,7 +372,6 @@ __global__ void __launch_bounds__(kT) tc_pull_kernel(const TcParams p) {
 // Loss of epoch e (pre-update weights) + the reference's stopping rule (language_eval.py:298-318).  One CTA.
 __global__ void __launch_bounds__(kT) tc_loss_kernel(const TcParams p, int e) {
     if (p.ctrl->stop) return;
-    __shared__ double red[32];
     const sr_head_args& a = p.a;
     const int tid = threadIdx.x;
     const bool has_base = a.base_weight != nullptr;
@@ -385,8 +386,25 @@ __global__ void __launch_bounds__(kT) tc_loss_kernel(const TcParams p, int e) {
     }
     for (int i = tid; i < p.g.n_upd; i += kT) { nb += p.nbp[i]; nn += p.nnp[i]; }
     for (int i = tid; i < n_pull; i += kT) ps += p.pull_sq[i];
-    ls = block_sum(ls, red); lm = block_sum(lm, red); h1 = block_sum(h1, red); h5 = block_sum(h5, red);
-    nb = block_sum(nb, red); nn = block_sum(nn, red); ps = block_sum(ps, red);
+    {   // the seven sums in one pass: warp shuffles, then warp totals added in warp order (deterministic)
+        __shared__ double s7[kT / 32][7];
+        double v[7] = {ls, lm, h1, h5, nb, nn, ps};
+#pragma unroll
+        for (int k = 0; k < 7; ++k) v[k] = warp_sum(v[k]);
+        if ((tid & 31) == 0)
+#pragma unroll
+            for (int k = 0; k < 7; ++k) s7[tid >> 5][k] = v[k];
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                double t = 0.0;
+                for (int w = 0; w < kT / 32; ++w) t += s7[w][k];
+                v[k] = t;
+            }
+            ls = v[0]; lm = v[1]; h1 = v[2]; h5 = v[3]; nb = v[4]; nn = v[5]; ps = v[6];
+        }
+    }
     if (tid == 0) {
         p.ctrl->norm_base_sq = nb;
         p.ctrl->norm_prev_sq = nn;
@@ -572,10 +590,14 @@ int32_t head_tc_run(const sr_head_args* a, cudaStream_t stream) {
     tc_prep_w_kernel<<<(unsigned)(((int64_t)g.Cp * g.d + kUpdElems - 1) / kUpdElems), kT, 0, stream>>>(p);
     SR_CUDA_OK(cudaGetLastError());
 
+    const size_t row_smem = (size_t)kRowsPerCta * g.Cz * 4;
+    if (row_smem > 48 * 1024)
+        SR_CUDA_OK(cudaFuncSetAttribute(tc_rowstats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
     const int32_t* stop_flag = &p.ctrl->stop;
     sr_conv_args gz;   // logits
     memset(&gz, 0, sizeof(gz));
-    gz.batch = g.N; gz.height = 1; gz.width = 1; gz.cout = g.Cp; gz.n_panels = 1;
+    gz.batch = g.N; gz.height = 1; gz.width = 1; gz.cout = g.Cz; gz.n_panels = 1;
+    gz.max_cout_per_cta = 128;   // 2 accumulator stages: the fp32 epilogue of a tile overlaps the next tile's main loop
     gz.panel[0].act = p.Xp; gz.panel[0].act_lo = p.Xp + (int64_t)g.N * g.d;
     gz.panel[0].wgt = p.Wp; gz.panel[0].wgt_lo = p.Wp + (int64_t)g.Cp * g.d;
     gz.panel[0].cin_pad = g.d; gz.panel[0].taps = 1;
@@ -594,7 +616,7 @@ int32_t head_tc_run(const sr_head_args* a, cudaStream_t stream) {
     for (int e = 0; e < epochs; ++e) {
         int32_t rc = sr_conv(&gz, stream);
         if (rc != SR_OK) return rc;
-        tc_rowstats_kernel<<<g.n_rowctas, kT, 0, stream>>>(p);
+        tc_rowstats_kernel<<<g.n_rowctas, kT, row_smem, stream>>>(p);
         tc_dz_kernel<<<dim3((g.N + 63) / 64, (g.C + 63) / 64), kT, 0, stream>>>(p);
         if (n_pull) tc_pull_kernel<<<n_pull, kT, 3 * g.d * sizeof(float), stream>>>(p);
         rc = sr_conv(&gw, stream);

@@ -33,7 +33,7 @@ class ConvArgs(C.Structure):
         ("n_panels", C.c_int32), ("panel", ConvPanel * 2),
         ("shift", C.c_void_p), ("residual", C.c_void_p), ("residual_lo", C.c_void_p), ("slope", C.c_float),
         ("epilogue", C.c_int32), ("out", C.c_void_p), ("out_lo", C.c_void_p), ("stats", C.c_void_p),
-        ("weights_per_image", C.c_int32), ("skip_if_nonzero", C.c_void_p),
+        ("weights_per_image", C.c_int32), ("skip_if_nonzero", C.c_void_p), ("max_cout_per_cta", C.c_int32),
     ]
 
 

@@ -129,7 +129,7 @@ def test_conv_plan_for_every_backbone_layer(lib):
                 assert p['n_cta'] * p['n_splits'] == cout and p['n_cta'] % 32 == 0 and p['n_cta'] <= 256, tag
                 assert p['tmem_stages'] * 2 * p['n_cta'] <= 512, tag
                 assert p['TW'] * p['TH'] * p['TN'] >= 115 and p['TW'] * p['TH'] * p['TN'] <= 128, tag
-                assert p['ring'] >= 3 and p['dyn_smem'] <= 227 * 1024 - 3072, tag
+                assert p['ring'] >= 3 and p['dyn_smem'] <= 227 * 1024 - 1024, tag      # 1 KB of static shared memory
                 assert p['row_bytes'] == (128 if cin >= 64 else 32), tag
                 if mode == POOL:
                     assert p['stacked'] or p['TH'] % 2 == 0, tag
