@@ -235,10 +235,14 @@ def head_stress(device, hbm_gbs, steps=5):
         qr = min(n_base, d)
         bytes_step = 4 * N * d + 8 * N + 4 * Cn * d * 4 + 4 * n_base * d + 4 * qr * d
         flops_step = 4.0 * N * Cn * d + (4.0 * n_new * qr * d if n_base < d else 0.0)
+        tc = Cn >= 769   # csrc/head_tc.cu takes problems whose class count pads to >= 1024; the rest stays on the fp32 SIMT kernel
         out[name] = {"ms_per_step": ms, "steps_per_s": 1e3 / ms, "algorithmic_MB": bytes_step / 1e6,
                      "achieved_GBps": bytes_step / (ms * 1e-3) / 1e9, "hbm_frac": bytes_step / (ms * 1e-3) / 1e9 / hbm_gbs,
-                     "fp32_TFLOPs": flops_step / (ms * 1e-3) / 1e12,
-                     "binding": "compute (fp32 SIMT tiles; 22.5 GFLOP/step >> 5 us of HBM time)"}
+                     "TFLOPs": flops_step / (ms * 1e-3) / 1e12,
+                     "kernel": "head_tc (tcgen05 GEMMs, error-compensated bf16x3: 3x the FLOPs on the tensor pipe)" if tc
+                               else "head_kernel (fp32 SIMT tiles)",
+                     "binding": "tensor pipe (22.5 GFLOP/step x3 passes vs 5 us of algorithmic HBM time; SURVEY D6)" if tc
+                                else "compute (fp32 SIMT tiles)"}
     return out
 
 
@@ -303,7 +307,7 @@ def main():
         except AttributeError:
             cores = os.cpu_count() or 1
         cores = max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world_size))))
-        conc = 3 if cores >= 12 else (2 if cores >= 6 else 1)
+        conc = 2 if cores >= 8 else 1
     conc = max(1, min(conc, args.steps))
     from srb200.concurrent import SeedPool
     pool = SeedPool(conc, device) if conc > 1 else None
@@ -430,6 +434,19 @@ def main():
                      "note": "1.45-2.6 MB and 32-90 MFLOP per step: 0.2-0.4 us at HBM speed, i.e. latency-bound (two grid "
                              "barriers per step); the HBM fraction is reported for completeness (SURVEY 8d)"}
 
+    # ---- the parity tier next to the throughput tier: the same sweep with error-compensated (bf16x3) convolutions ----
+    parity_tier = None
+    if rank == 0 and args.precision == "bf16":
+        def mk_x3(seed):
+            return synthetic.make_world(seed, n_sessions=args.sessions, n_base_batch=args.base_batch, word_embed_path=wdir,
+                                        conv_precision="bf16x3")
+        run_sweeps([prepare(place_world(mk_x3(3000), 'gpu'))], None)                       # warm-up (packs the weight pairs)
+        r3 = run_sweeps([prepare(place_world(mk_x3(1), 'gpu'))], None)[0]
+        ep3 = sum(s_['epochs'] for s_ in r3['sessions'])
+        parity_tier = {"conv_precision": "bf16x3", "ms_per_step": r3['wall_ms'], "value": ep3 / (r3['wall_ms'] * 1e-3),
+                       "unit": "steps/s", "note": "one sweep (seed 1) run alone, host wall time; this is the tier whose class "
+                       "predictions are identical to the fp32 oracle's (tests/test_gpu_config2.py)"}
+
     # ---- BASELINE config 5: head / regulariser stress shapes (1000 base + 100 novel classes, 100-shot, 512-d) ----
     stress = None
     if rank == 0:
@@ -448,7 +465,7 @@ def main():
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e_max / max(args.steps, 1)},
             "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline, "roofline_head": roofline_head,
             "accuracy": {"weighted_mean_last": float(weighted[:, -1].mean()), "confusion_total": int(conf.sum())},
-            "stress_head": stress}
+            "stress_head": stress, "parity_tier": parity_tier}
 
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         r = cpu_reference_sample(1, 1, 64, args.cpu_epochs, wdir)

@@ -254,8 +254,13 @@ typedef struct sr_eval_args {
     float* loss_sum;        /* [1]: += sum over rows of (logsumexp - z_y)                                */
     int64_t* confusion;     /* optional [conf_dim, conf_dim] += 1 at (label, pred)                       */
     int32_t conf_dim;
+    void* workspace;        /* optional: sr_eval_workspace_bytes(n, dim, n_classes) bytes let large problems run  */
+    int64_t workspace_bytes;/*   their logits GEMM on tcgen05 (error-compensated bf16x3); NULL = fp32 SIMT tiles */
 } sr_eval_args;
 
+/* Bytes of workspace with which sr_eval_logits takes the tensor-core path for this shape; 0 = the shape stays on the
+ * SIMT kernel (small problems are launch-bound anyway). */
+int64_t sr_eval_workspace_bytes(int32_t n, int32_t dim, int32_t n_classes);
 int32_t sr_eval_logits(const sr_eval_args* a, void* stream);
 /* Same scoring on logits the caller already has (feat / weight / dim ignored): eval/util.py accuracy :26-40. */
 int32_t sr_score_logits(const sr_eval_args* a, void* stream);

@@ -454,7 +454,8 @@ __global__ void __launch_bounds__(kHeadThreads) logits_kernel(const float* X, co
         }
 }
 
-__global__ void __launch_bounds__(256) score_rows_kernel(const sr_eval_args a) {
+// `src` / `pitch`: logits computed elsewhere with a padded row pitch (the tensor-core path); they are copied to a.logits.
+__global__ void __launch_bounds__(256) score_rows_kernel(const sr_eval_args a, const float* src, int pitch) {
     __shared__ int s_cnt[2];
     __shared__ float s_loss;
     if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_loss = 0.f; }
@@ -462,13 +463,14 @@ __global__ void __launch_bounds__(256) score_rows_kernel(const sr_eval_args a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = blockIdx.x * 8 + warp;
     if (r < a.n) {
-        const float* z = a.logits + (int64_t)r * a.n_classes;
         const int C = a.n_classes;
+        const float* z = src != nullptr ? src + (int64_t)r * pitch : a.logits + (int64_t)r * C;
         const int y = (int)a.labels[r];
         float mx = -INFINITY;
         int arg = 0x7fffffff;
         for (int c = lane; c < C; c += 32) {
             const float v = z[c];
+            if (src != nullptr) a.logits[(int64_t)r * C + c] = v;
             if (v > mx) { mx = v; arg = c; }  // strided ascending: first maximum per lane
         }
 #pragma unroll
@@ -669,6 +671,18 @@ extern "C" int32_t sr_eval_logits(const sr_eval_args* a, void* stream_v) {
     if (!a || !a->feat || !a->weight || !a->labels || !a->logits || !a->pred || !a->counts || !a->loss_sum)
         return fail(SR_E_ARG, "sr_eval_logits: null pointer");
     if (a->n < 1 || a->n_classes < 1 || a->dim < 4 || a->dim % 4) return fail(SR_E_ARG, "sr_eval_logits: bad sizes");
+    if (a->workspace != nullptr && !getenv("SRB_HEAD_SIMT")) {
+        const int64_t need = srb::eval_tc_workspace_bytes(a->n, a->dim, a->n_classes);
+        if (need > 0 && a->workspace_bytes >= need) {
+            const float* z = nullptr;
+            int pitch = 0;
+            const int32_t rc = srb::eval_tc_logits(a, stream, &z, &pitch);
+            if (rc != SR_OK) return rc;
+            score_rows_kernel<<<(a->n + 7) / 8, 256, 0, stream>>>(*a, z, pitch);
+            SR_CUDA_OK(cudaGetLastError());
+            return SR_OK;
+        }
+    }
     const int64_t t64 = ((int64_t)(a->n + 63) / 64) * ((a->n_classes + 63) / 64);
     if (t64 >= 2 * (int64_t)num_sms()) {
         logits_kernel<64><<<(unsigned)t64, kHeadThreads, 0, stream>>>(a->feat, a->weight, a->logits, a->n, a->n_classes, a->dim);
@@ -677,9 +691,13 @@ extern "C" int32_t sr_eval_logits(const sr_eval_args* a, void* stream_v) {
         logits_kernel<32><<<(unsigned)t32, kHeadThreads, 0, stream>>>(a->feat, a->weight, a->logits, a->n, a->n_classes, a->dim);
     }
     SR_CUDA_OK(cudaGetLastError());
-    score_rows_kernel<<<(a->n + 7) / 8, 256, 0, stream>>>(*a);
+    score_rows_kernel<<<(a->n + 7) / 8, 256, 0, stream>>>(*a, nullptr, 0);
     SR_CUDA_OK(cudaGetLastError());
     return SR_OK;
+}
+
+extern "C" int64_t sr_eval_workspace_bytes(int32_t n, int32_t dim, int32_t n_classes) {
+    return srb::eval_tc_workspace_bytes(n, dim, n_classes);
 }
 
 extern "C" int32_t sr_score_logits(const sr_eval_args* a, void* stream_v) {
@@ -687,7 +705,7 @@ extern "C" int32_t sr_score_logits(const sr_eval_args* a, void* stream_v) {
     if (!a || !a->labels || !a->logits || !a->pred || !a->counts || !a->loss_sum)
         return fail(SR_E_ARG, "sr_score_logits: null pointer");
     if (a->n < 1 || a->n_classes < 1) return fail(SR_E_ARG, "sr_score_logits: bad sizes");
-    score_rows_kernel<<<(a->n + 7) / 8, 256, 0, stream>>>(*a);
+    score_rows_kernel<<<(a->n + 7) / 8, 256, 0, stream>>>(*a, nullptr, 0);
     SR_CUDA_OK(cudaGetLastError());
     return SR_OK;
 }

@@ -134,4 +134,6 @@ int32_t head_small_run(const sr_head_args* a, cudaStream_t stream);
 bool head_tc_applicable(const sr_head_args* a);
 int64_t head_tc_workspace_bytes(const sr_head_args* a);
 int32_t head_tc_run(const sr_head_args* a, cudaStream_t stream);
+int64_t eval_tc_workspace_bytes(int n, int dim, int n_classes);
+int32_t eval_tc_logits(const sr_eval_args* a, cudaStream_t stream, const float** z, int* pitch);
 }  // namespace srb

@@ -540,9 +540,61 @@ __global__ void tc_finish_kernel(const TcParams p) {
     head_write_status(p.a, st, p.ctrl->epochs_done, p.ctrl->stop, p.ctrl->stable_count, p.ctrl->prev_loss, p.ctrl->error);
 }
 
+// ---- scoring (sr_eval_logits): fp32 rows -> hi / lo planes, optionally zero-padded to `rows_out` rows ----
+__global__ void __launch_bounds__(kT) tc_split_rows_kernel(const float* __restrict__ src, int rows, int rows_out, int d,
+                                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const int64_t i = ((int64_t)blockIdx.x * kT + threadIdx.x) * 4;
+    if (i >= (int64_t)rows_out * d) return;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (i < (int64_t)rows * d) {
+        const float4 v = *reinterpret_cast<const float4*>(src + i);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    }
+    __align__(8) __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_bf16(x[j], h[j], l[j]);
+    *reinterpret_cast<uint2*>(hi + i) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<const uint2*>(l);
+}
+
 }  // namespace
 
 namespace srb {
+
+// Query / base scoring of large problems (BASELINE config 5: 16 384 x 1100 x 512): the logits GEMM on tcgen05, same
+// error-compensated 1x1 convolution as the head's.  Workspace: X planes | W planes (rows padded to 128) | Z [n][Cz].
+int64_t eval_tc_workspace_bytes(int n, int dim, int n_classes) {
+    if ((int64_t)n * n_classes < (1ll << 20) || dim % 64 != 0 || dim > 2048 || n_classes > 4096) return 0;
+    const int64_t Cz = align_up(n_classes, 128);
+    return align_up(2ll * n * dim * 2, 256) + align_up(2ll * Cz * dim * 2, 256) + align_up((int64_t)n * Cz * 4, 256);
+}
+
+int32_t eval_tc_logits(const sr_eval_args* a, cudaStream_t stream, const float** z_out, int* pitch) {
+    const int n = a->n, d = a->dim, C = a->n_classes;
+    const int Cz = (int)align_up(C, 128);
+    uint8_t* ws = static_cast<uint8_t*>(a->workspace);
+    if (reinterpret_cast<uintptr_t>(ws) & 255) return fail(SR_E_ARG, "sr_eval_logits: workspace must be 256-byte aligned");
+    __nv_bfloat16* Xp = reinterpret_cast<__nv_bfloat16*>(ws);
+    __nv_bfloat16* Wp = reinterpret_cast<__nv_bfloat16*>(ws + align_up(2ll * n * d * 2, 256));
+    float* Z = reinterpret_cast<float*>(ws + align_up(2ll * n * d * 2, 256) + align_up(2ll * Cz * d * 2, 256));
+    tc_split_rows_kernel<<<(unsigned)(((int64_t)n * d / 4 + kT - 1) / kT), kT, 0, stream>>>(a->feat, n, n, d, Xp, Xp + (int64_t)n * d);
+    tc_split_rows_kernel<<<(unsigned)(((int64_t)Cz * d / 4 + kT - 1) / kT), kT, 0, stream>>>(a->weight, C, Cz, d, Wp,
+                                                                                             Wp + (int64_t)Cz * d);
+    SR_CUDA_OK(cudaGetLastError());
+    sr_conv_args g;
+    memset(&g, 0, sizeof(g));
+    g.batch = n; g.height = 1; g.width = 1; g.cout = Cz; g.n_panels = 1;
+    g.max_cout_per_cta = 128;
+    g.panel[0].act = Xp; g.panel[0].act_lo = Xp + (int64_t)n * d;
+    g.panel[0].wgt = Wp; g.panel[0].wgt_lo = Wp + (int64_t)Cz * d;
+    g.panel[0].cin_pad = d; g.panel[0].taps = 1;
+    g.epilogue = SR_EPI_RAW_STATS; g.out = Z; g.stats = nullptr;
+    const int32_t rc = sr_conv(&g, stream);
+    if (rc != SR_OK) return rc;
+    *z_out = Z;
+    *pitch = Cz;
+    return SR_OK;
+}
 
 // Large problems whose shapes fit the two GEMM mappings; everything else stays on the SIMT head_kernel.
 bool head_tc_applicable(const sr_head_args* a) {

@@ -18,7 +18,7 @@ EXPORTS = [
     "sr_last_error", "sr_version", "sr_check_device", "sr_pack_input", "sr_bn_fold", "sr_pack_weight", "sr_conv",
     "sr_bn_finalize", "sr_bn_apply", "sr_subspace_factor_workspace_bytes", "sr_subspace_factor",
     "sr_head_workspace_bytes", "sr_head_run", "sr_eval_logits", "sr_semantic_pullers", "sr_linear_fwd",
-    "sr_linear_bwd", "sr_sqdist", "sr_diff_scale", "sr_project_rows", "sr_score_logits", "sr_host_bernoulli", "sr_host_dropblock", "sr_conv_plan", "sr_pack_input_u8", "sr_global_avg", "sr_mse_grad", "sr_sgd_update",
+    "sr_linear_bwd", "sr_sqdist", "sr_diff_scale", "sr_project_rows", "sr_score_logits", "sr_host_bernoulli", "sr_host_dropblock", "sr_conv_plan", "sr_pack_input_u8", "sr_global_avg", "sr_mse_grad", "sr_sgd_update", "sr_eval_workspace_bytes",
 ]
 
 
@@ -71,7 +71,7 @@ class EvalArgs(C.Structure):
         ("feat", C.c_void_p), ("weight", C.c_void_p), ("labels", C.c_void_p),
         ("n", C.c_int32), ("dim", C.c_int32), ("n_classes", C.c_int32),
         ("logits", C.c_void_p), ("pred", C.c_void_p), ("counts", C.c_void_p), ("loss_sum", C.c_void_p),
-        ("confusion", C.c_void_p), ("conf_dim", C.c_int32),
+        ("confusion", C.c_void_p), ("conf_dim", C.c_int32), ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -114,6 +114,8 @@ def load():
     lib.sr_head_workspace_bytes.argtypes = [C.POINTER(HeadArgs)]
     lib.sr_head_run.restype = i32
     lib.sr_head_run.argtypes = [C.POINTER(HeadArgs), vp]
+    lib.sr_eval_workspace_bytes.restype = i64
+    lib.sr_eval_workspace_bytes.argtypes = [i32, i32, i32]
     lib.sr_eval_logits.restype = i32
     lib.sr_eval_logits.argtypes = [C.POINTER(EvalArgs), vp]
     lib.sr_mse_grad.restype = i32

@@ -376,8 +376,11 @@ def eval_logits(feat, weight, labels, confusion=None):
     a.logits, a.pred, a.counts, a.loss_sum = _ptr(logits), _ptr(pred), _ptr(counts), _ptr(loss_sum)
     a.confusion = _ptr(confusion, torch.int64, "confusion")
     a.conf_dim = 0 if confusion is None else confusion.shape[0]
+    ws_bytes = int(L.load().sr_eval_workspace_bytes(n, d, Cn))     # > 0: large problem, logits GEMM on tcgen05
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes > 0 else None
+    a.workspace, a.workspace_bytes = _ptr(ws), ws_bytes
     L.check(L.load().sr_eval_logits(C.byref(a), _stream()), "sr_eval_logits")
-    LAUNCHES.add(2)
+    LAUNCHES.add(2 if ws is None else 4)
     return {"logits": logits, "pred": pred, "counts": counts, "loss_sum": loss_sum}
 
 

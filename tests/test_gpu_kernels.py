@@ -102,6 +102,26 @@ def test_eval_logits_properties():
     ce = torch.nn.functional.cross_entropy(Zf.double(), y, reduction="sum").item()
     assert abs(r["loss_sum"].item() - ce) < 1e-4 * ce
     assert int(conf.sum()) == n and int(conf.diag().sum()) == int(r["counts"][0])
+    # the same call on the fp32 SIMT tiles (SRB_HEAD_SIMT=1): the tensor-core logits (error-compensated bf16x3) agree to 1e-5
+    import os
+    os.environ["SRB_HEAD_SIMT"] = "1"
+    try:
+        r2 = ops.eval_logits(X, W, y)
+    finally:
+        os.environ.pop("SRB_HEAD_SIMT", None)
+    rel = ((r["logits"] - r2["logits"]).abs().max() / r2["logits"].abs().max()).item()
+    print("eval logits, tensor-core vs SIMT: rel %.2e; predictions equal: %s" % (rel, bool((r["pred"] == r2["pred"]).all())))
+    assert rel < 1e-5
+    for fn, name in ((lambda: ops.eval_logits(X, W, y), "tensor-core"),):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        print("query scoring 16384 x 1100 x 512 (%s): %.1f us per call" % (name, e0.elapsed_time(e1) * 1e3 / 5))
 
 
 def test_backbone_linearity_in_last_residual():
