@@ -605,6 +605,7 @@ extern "C" int64_t sr_head_workspace_bytes(const sr_head_args* a) {
     if (!a) return 0;
     int64_t n = head_layout(a).total;
     if (a->dim >= 64 && a->dim % 64 == 0) n = std::max<int64_t>(n, srb::head_small_workspace_bytes(a));
+    if (a->dim >= 64 && a->dim % 64 == 0 && a->n_classes <= 128) n = std::max<int64_t>(n, srb::head_cluster_workspace_bytes(a));
     if (srb::head_tc_applicable(a)) n = std::max<int64_t>(n, srb::head_tc_workspace_bytes(a));
     return n;
 }
@@ -628,6 +629,8 @@ extern "C" int32_t sr_head_run(const sr_head_args* a, void* stream_v) {
     if (a->resume_status && a->resume_status == a->status)
         return fail(SR_E_ARG, "sr_head_run: resume_status must be a different block than status");
     // Paper-sized problems: everything constant over the session stays in shared memory (head_small.cu).
+    // ... or, opt-in (SRB_HEAD_CLUSTER=1), the variant that splits both reductions over thread-block clusters (head_cluster.cu)
+    if (srb::head_small_applicable(a) && srb::head_cluster_applicable(a)) return srb::head_cluster_run(a, stream);
     if (srb::head_small_applicable(a)) return srb::head_small_run(a, stream);
     // Large problems: the two GEMMs on tcgen05 (head_tc.cu).  SRB_HEAD_SIMT=1 keeps the fp32 SIMT kernel below (A/B checks).
     if (srb::head_tc_applicable(a) && !getenv("SRB_HEAD_SIMT")) return srb::head_tc_run(a, stream);

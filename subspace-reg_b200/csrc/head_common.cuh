@@ -131,6 +131,9 @@ namespace srb {
 bool head_small_applicable(const sr_head_args* a);
 int64_t head_small_workspace_bytes(const sr_head_args* a);
 int32_t head_small_run(const sr_head_args* a, cudaStream_t stream);
+bool head_cluster_applicable(const sr_head_args* a);
+int64_t head_cluster_workspace_bytes(const sr_head_args* a);
+int32_t head_cluster_run(const sr_head_args* a, cudaStream_t stream);
 bool head_tc_applicable(const sr_head_args* a);
 int64_t head_tc_workspace_bytes(const sr_head_args* a);
 int32_t head_tc_run(const sr_head_args* a, cudaStream_t stream);

@@ -25,6 +25,15 @@ def test_kernel_group(group):
     assert getattr(diag, "group_" + group)()
 
 
+def test_head_cluster_variant(monkeypatch):
+    """The paper-size head has a second implementation that splits both reductions of an epoch over 8-CTA thread-block
+    clusters with a DSMEM reduction (head_cluster.cu, opt-in with SRB_HEAD_CLUSTER=1: on par with head_small.cu, not faster).
+    Same cases as the `head` group, same 1e-5 bar against fp64 autograd."""
+    import diag
+    monkeypatch.setenv("SRB_HEAD_CLUSTER", "1")
+    assert diag.group_head()
+
+
 def test_head_stress_config5():
     """BASELINE config 5 shapes: 1000 base + 100 novel classes, 100-shot, 512-d.  With 1000 base rows in 512-d the span
     is everything: the projector is the identity and the regulariser vanishes; n_base = 256 is the

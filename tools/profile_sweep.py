@@ -43,6 +43,7 @@ def head_timing():
               (s, Ns + Nm, Cn, e0.elapsed_time(e1) * 1e3 / 2000, t[0] / 2000, t[1] / 2000, t[2] / 2000, t[3] / 2000, t[4] / 2000, t[5] / 2000), flush=True)
         print("    phase 1: W stream %.0f  logits->smem %.0f  softmax+dlogits %.0f | phase 2: prologue %.0f  DLt stream %.0f  update %.0f (ns/epoch)" %
               tuple(x / 2000 for x in t[6:12]), flush=True)
+        print("    raw t_ns/epoch:", [round(x / 2000) for x in t], flush=True)
 
 
 def sweep_timing():
