@@ -41,12 +41,6 @@ struct TcStart {
     float prev_loss;
 };
 
-int split_for(int n) {   // same rule as plan_conv: the smallest split whose share is a multiple of 32 and <= 256
-    for (int c = 1; c <= 16; ++c)
-        if (n % c == 0 && (n / c) % 32 == 0 && n / c <= 256) return c;
-    return 0;
-}
-
 bool tc_geometry(const sr_head_args* a, TcGeom* g) {
     g->N = a->n_support + a->n_memory;
     g->d = a->dim;
@@ -55,8 +49,9 @@ bool tc_geometry(const sr_head_args* a, TcGeom* g) {
     g->Cz = (int)align_up(a->n_classes, 128);
     // (the dW GEMM maps classes to a 2 x Cp/2 feature map whose tiles must hold one slice: Cp >= 1024)
     if (a->dim % 64 != 0 || a->dim > 2048 || g->Cp > 4096 || g->Cp < 1024) return false;
-    const int ns_d = split_for(a->dim);
-    if (!ns_d) return false;
+    // dW tiles are 256 classes x 128 features: half the fp32 epilogue per CTA and half as many split-K partials as 256 x 256
+    if (a->dim % 128 != 0) return false;
+    const int ns_d = a->dim / 128;
     const int ctas_per_slice = (g->Cp / 256) * ns_d;
     g->S = std::max(1, std::min(148 / std::max(ctas_per_slice, 1), (g->N + 63) / 64));
     g->slice = (int)align_up((g->N + g->S - 1) / g->S, 64);
@@ -662,6 +657,7 @@ int32_t head_tc_run(const sr_head_args* a, cudaStream_t stream) {
     gw.panel[0].cin_pad = g.slice; gw.panel[0].taps = 1;
     gw.epilogue = SR_EPI_RAW_STATS; gw.out = p.part; gw.stats = nullptr; gw.skip_if_nonzero = stop_flag;
     gw.weights_per_image = 1;
+    gw.max_cout_per_cta = 128;
 
     const int n_pull = a->pull_mode == SR_PULL_NONE ? 0 : a->n_new;
     const int epochs = std::min(a->max_epochs, kMaxEpochsPerCall);
