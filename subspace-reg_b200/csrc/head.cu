@@ -581,15 +581,7 @@ __global__ void trisolve_kernel(const double* __restrict__ L, const float* __res
 
 __global__ void set_info_kernel(int* info, int a, int b, int c) { info[0] = a; info[1] = b; info[2] = c; info[3] = 0; }
 
-int g_num_sms = 0;
-int num_sms() {
-    if (!g_num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return g_num_sms;
-}
+int num_sms() { return current_device_sms(); }
 
 template <int BT>
 int32_t launch_head(const HeadParams& p, int grid, size_t dyn, cudaStream_t stream) {
@@ -660,8 +652,8 @@ extern "C" int32_t sr_head_run(const sr_head_args* a, void* stream_v) {
     const int64_t tasksC = ((int64_t)(a->n_classes + bt - 1) / bt) * ((a->dim + bt - 1) / bt);
     int grid = (int)std::min<int64_t>(sms, std::max<int64_t>(std::max(tasksA, tasksC), 1));
     {
-        static std::once_flag once;
-        std::call_once(once, [] {
+        static PerDeviceOnce once;
+        once_per_device(once, [] {
             cudaFuncSetAttribute(head_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
             cudaFuncSetAttribute(head_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         });
@@ -741,8 +733,8 @@ extern "C" int32_t sr_subspace_factor(const float* base, int32_t n_base, int32_t
     const size_t gbytes = (size_t)n * n * 8;
     const int use_smem = gbytes <= 200 * 1024 ? 1 : 0;
     if (use_smem) {
-        static std::once_flag once;
-        std::call_once(once, [] { cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+        static PerDeviceOnce once;
+        once_per_device(once, [] { cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
     }
     chol_kernel<<<1, 1024, use_smem ? gbytes : 0, stream>>>(G, n, use_smem, info);
     SR_CUDA_OK(cudaGetLastError());

@@ -632,7 +632,6 @@ ClLayout cl_layout(const sr_head_args* a, const ClParams& p) {
     return L;
 }
 
-constexpr int kMaxDevices = 64;
 int g_max_clusters[kMaxDevices][2];     // per device, per template instance: 0 = not queried yet, -1 = unusable
 constexpr int kClSmemMax = 200 * 1024;
 

@@ -68,14 +68,6 @@ __device__ __forceinline__ float ldg_early_f32(const float* p) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
 __device__ __forceinline__ int64_t feat_row(const sr_head_args& a, int r) {
     return r < a.n_support ? (int64_t)a.support_row0 + r : (int64_t)a.memory_row0 + (r - a.n_support);
 }
@@ -603,8 +595,8 @@ SmallLayout small_layout(const sr_head_args* a, int GC) {
 
 template <int R, int CP>
 int32_t launch_small(const SmallParams& p, size_t dyn, cudaStream_t stream) {
-    static std::once_flag once;
-    std::call_once(once, [] {
+    static PerDeviceOnce once;
+    once_per_device(once, [] {
         cudaFuncSetAttribute(head_small_kernel<R, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     });
     void* args[] = {const_cast<SmallParams*>(&p)};

@@ -53,7 +53,7 @@ bool tc_geometry(const sr_head_args* a, TcGeom* g) {
     if (a->dim % 128 != 0) return false;
     const int ns_d = a->dim / 128;
     const int ctas_per_slice = (g->Cp / 256) * ns_d;
-    g->S = std::max(1, std::min(148 / std::max(ctas_per_slice, 1), (g->N + 63) / 64));
+    g->S = std::max(1, std::min(current_device_sms() / std::max(ctas_per_slice, 1), (g->N + 63) / 64));
     g->slice = (int)align_up((g->N + g->S - 1) / g->S, 64);
     g->S = (g->N + g->slice - 1) / g->slice;          // no empty slices
     g->n_upd = (int)(((int64_t)g->C * g->d + kUpdElems - 1) / kUpdElems);
