@@ -15,6 +15,7 @@ from . import _lib as L
 from . import rng
 
 _replay_ok = None
+WAIT_S = [0.0, 0.0, 0]   # diagnostics: seconds the consumer waited for pre-drawn masks / spent drawing inline, inline draws
 
 
 def _torch_draw(shape, p, kind):
@@ -78,7 +79,12 @@ def bernoulli_u8(shape, p, kind, out=None):
     """uint8 CPU tensor of draws (1 with probability p) + number of ones, consuming torch's CPU generator exactly like
     kind 0: tensor.bernoulli_(p)   kind 1: torch.bernoulli(torch.tensor(p).expand(shape))."""
     if replay_available():
-        return _replay_draw(shape, p, kind, out)
+        import time
+        t0 = time.perf_counter()
+        r = _replay_draw(shape, p, kind, out)
+        WAIT_S[1] += time.perf_counter() - t0
+        WAIT_S[2] += 1
+        return r
     t = _torch_draw(shape, p, kind)
     if out is not None:
         out.copy_(t)
@@ -186,10 +192,13 @@ class MaskPrefetch(object):
         """-> (uint8 buffer, ones) or None.  Advances torch's live generator exactly as the draw would have."""
         if self.thread is None or self.dead:
             return None
+        import time
+        t0 = time.perf_counter()
         with self._cv:
             while key not in self.results and not self.finished and not self.dead:
                 self._cv.wait()
             ent = self.results.pop(key, None)
+        WAIT_S[0] += time.perf_counter() - t0
         if ent is None:
             return None
         self._pending -= 1

@@ -17,5 +17,13 @@ for it in range(int(os.environ.get("SWEEPS", "1"))):
     prep = bench.prepare(bench.place_world(world, 'gpu'))
     rec = bench.run_sweeps([prep], None)[0]
     torch.cuda.synchronize()
-    print("sweep %d: phases %s epochs %s" % (it, {k: round(v * 1e3, 1) for k, v in rec['phases'].items()},
-                                              [s['epochs'] for s in rec['sessions']]), flush=True)
+    from srb200 import host_rng
+    print("sweep %d: wall %.1f ms phases %s epochs %s | mask wait %.1f ms, inline draws %d (%.1f ms)" % (
+        it, rec['wall_ms'], {k: round(v * 1e3, 1) for k, v in rec['phases'].items()}, [s['epochs'] for s in rec['sessions']],
+        host_rng.WAIT_S[0] * 1e3, host_rng.WAIT_S[2], host_rng.WAIT_S[1] * 1e3), flush=True)
+    host_rng.WAIT_S[:] = [0.0, 0.0, 0]
+    ms = torch.cuda.memory_stats()
+    import gc
+    print("    allocator: cudaMalloc calls %d, cudaFree calls %d, retries %d, reserved %.1f GB; gc counts %s" % (
+        ms.get('num_device_alloc', 0), ms.get('num_device_free', 0), ms.get('num_alloc_retries', 0),
+        ms.get('reserved_bytes.all.current', 0) / 1e9, gc.get_count()), flush=True)
