@@ -301,6 +301,10 @@ def main():
     from srb200 import _lib, ops, synthetic
     _lib.load()
     wdir = word_embed_dir()
+    from srb200.concurrent import prewarm_allocator
+    # one large cached segment for the caching allocator to split (see prewarm_allocator: fewer cudaMalloc stalls)
+    prewarm_allocator(16 + 0.8 * (args.steps + args.warmup), device)
+    config["allocator_prewarm_gb"] = 16 + 0.8 * (args.steps + args.warmup)
 
     def mk(seed):
         return synthetic.make_world(seed, n_sessions=args.sessions, n_base_batch=args.base_batch, word_embed_path=wdir,

@@ -156,6 +156,31 @@ typedef struct sr_bn_apply_args {
 
 int32_t sr_bn_apply(const sr_bn_apply_args* a, void* stream);
 
+/* One BasicBlock of the train-mode pass up to its last BatchNorm (resnet_language.py:273-286), sequenced by the library:
+ *   conv1 -> batch statistics -> BN + LeakyReLU -> conv2 -> ... -> conv3 [, 1x1 downsample conv of the block input] with
+ *   every BatchNorm's running statistics updated in place - 9 (11) launches behind one call.
+ * The caller finishes the block with ONE sr_bn_apply (bn3 [+ downsample BN | identity residual], LeakyReLU, pooling,
+ * dropout / DropBlock keep-mask) on raw[2] / raw[3] and the mean / invstd rows this call leaves in `mean_invstd`; that
+ * split lets the host draw the block's keep-mask while these launches run.  All buffers are caller-owned. */
+typedef struct sr_train_block_args {
+    int32_t batch, height, width, cin_pad, cout;
+    int32_t downsample;          /* 1: the block has the 1x1 conv + BN residual branch                              */
+    const void *x, *x_lo;        /* block input NHWC bf16 [B,H,W,cin_pad] (+ low plane in the error-compensated tier) */
+    const void* w[4];            /* packed raw weights (sr_pack_weight, no BN scale): conv1, conv2, conv3, downsample */
+    const void* w_lo[4];         /* their low planes, or NULL                                                        */
+    const float* gamma[2];       /* BN affine of bn1, bn2 (bn3 / downsample BN are applied by the caller)            */
+    const float* beta[2];
+    float* running_mean[4];      /* running statistics of bn1, bn2, bn3, downsample BN: EMA-updated in place         */
+    float* running_var[4];
+    float eps, momentum, slope;
+    double* stats;               /* [(3|4)][2*cout] fp64, zeroed by the caller                                       */
+    float* mean_invstd;          /* out [(3|4)][2][cout]: batch mean, then 1/sqrt(biased var + eps), per conv         */
+    float* raw[4];               /* fp32 NHWC [B,H,W,cout] conv outputs; raw[0] / raw[1] are scratch and may alias    */
+    void *h1, *h1_lo, *h2, *h2_lo; /* scratch activations bf16 NHWC [B,H,W,cout] (low planes in the x3 tier)         */
+} sr_train_block_args;
+
+int32_t sr_train_block(const sr_train_block_args* a, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Subspace regulariser: orthonormal factor of span(base weights)
  * Replaces torch.qr(base_weight^T, some=True) in LangPuller.get_projected_weight

@@ -369,6 +369,52 @@ extern "C" int32_t sr_bn_finalize(const double* stats, int64_t count, float eps,
     return SR_OK;
 }
 
+extern "C" int32_t sr_bn_apply(const sr_bn_apply_args* a, void* stream_v);
+
+extern "C" int32_t sr_train_block(const sr_train_block_args* a, void* stream_v) {
+    if (!a || !a->x || !a->stats || !a->mean_invstd || !a->h1 || !a->h2) return fail(SR_E_ARG, "sr_train_block: null pointer");
+    const int n_convs = a->downsample ? 4 : 3;
+    const bool precise = a->x_lo != nullptr;
+    for (int i = 0; i < n_convs; ++i)
+        if (!a->w[i] || !a->raw[i] || !a->running_mean[i] || !a->running_var[i] || (precise && !a->w_lo[i]))
+            return fail(SR_E_ARG, "sr_train_block: null pointer for conv %d", i);
+    if (precise && (!a->h1_lo || !a->h2_lo)) return fail(SR_E_ARG, "sr_train_block: the x3 tier needs h1_lo / h2_lo");
+    const int64_t count = (int64_t)a->batch * a->height * a->width;
+    const void* in[4] = {a->x, a->h1, a->h2, a->x};
+    const void* in_lo[4] = {a->x_lo, a->h1_lo, a->h2_lo, a->x_lo};
+    void* act[2] = {a->h1, a->h2};
+    void* act_lo[2] = {a->h1_lo, a->h2_lo};
+    for (int i = 0; i < n_convs; ++i) {
+        sr_conv_args c;
+        memset(&c, 0, sizeof(c));
+        c.batch = a->batch; c.height = a->height; c.width = a->width; c.cout = a->cout; c.n_panels = 1;
+        c.panel[0].act = in[i]; c.panel[0].act_lo = precise ? in_lo[i] : nullptr;
+        c.panel[0].wgt = a->w[i]; c.panel[0].wgt_lo = precise ? a->w_lo[i] : nullptr;
+        c.panel[0].cin_pad = (i == 0 || i == 3) ? a->cin_pad : a->cout;
+        c.panel[0].taps = i == 3 ? 1 : 9;
+        c.epilogue = SR_EPI_RAW_STATS;
+        c.out = a->raw[i];
+        c.stats = a->stats + (int64_t)i * 2 * a->cout;
+        int32_t rc = sr_conv(&c, stream_v);
+        if (rc != SR_OK) return rc;
+        float* mean = a->mean_invstd + (int64_t)i * 2 * a->cout;
+        rc = sr_bn_finalize(c.stats, count, a->eps, a->momentum, a->running_mean[i], a->running_var[i], mean, mean + a->cout,
+                            a->cout, stream_v);
+        if (rc != SR_OK) return rc;
+        if (i < 2) {   // bn1 / bn2 + LeakyReLU -> the next conv's input
+            sr_bn_apply_args b;
+            memset(&b, 0, sizeof(b));
+            b.batch = a->batch; b.height = a->height; b.width = a->width; b.channels = a->cout;
+            b.raw = a->raw[i]; b.mean = mean; b.invstd = mean + a->cout; b.gamma = a->gamma[i]; b.beta = a->beta[i];
+            b.lrelu = 1; b.slope = a->slope; b.pool = 0; b.keep_scale = 1.f;
+            b.out = act[i]; b.out_lo = precise ? act_lo[i] : nullptr;
+            rc = sr_bn_apply(&b, stream_v);
+            if (rc != SR_OK) return rc;
+        }
+    }
+    return SR_OK;
+}
+
 extern "C" int32_t sr_bn_apply(const sr_bn_apply_args* a, void* stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     if (!a || !a->raw || !a->mean || !a->invstd || !a->gamma || !a->beta || !a->out)

@@ -18,7 +18,7 @@ EXPORTS = [
     "sr_last_error", "sr_version", "sr_check_device", "sr_pack_input", "sr_bn_fold", "sr_pack_weight", "sr_conv",
     "sr_bn_finalize", "sr_bn_apply", "sr_subspace_factor_workspace_bytes", "sr_subspace_factor",
     "sr_head_workspace_bytes", "sr_head_run", "sr_eval_logits", "sr_semantic_pullers", "sr_linear_fwd",
-    "sr_linear_bwd", "sr_sqdist", "sr_diff_scale", "sr_project_rows", "sr_score_logits", "sr_host_bernoulli", "sr_host_dropblock", "sr_conv_plan", "sr_pack_input_u8", "sr_global_avg", "sr_mse_grad", "sr_sgd_update", "sr_eval_workspace_bytes",
+    "sr_linear_bwd", "sr_sqdist", "sr_diff_scale", "sr_project_rows", "sr_score_logits", "sr_host_bernoulli", "sr_host_dropblock", "sr_conv_plan", "sr_pack_input_u8", "sr_global_avg", "sr_mse_grad", "sr_sgd_update", "sr_eval_workspace_bytes", "sr_train_block",
 ]
 
 
@@ -45,6 +45,16 @@ class BnApplyArgs(C.Structure):
         ("res_beta", C.c_void_p), ("res_act", C.c_void_p), ("res_act_lo", C.c_void_p), ("lrelu", C.c_int32),
         ("slope", C.c_float), ("pool", C.c_int32), ("keep", C.c_void_p), ("keep_scale", C.c_float), ("out", C.c_void_p),
         ("out_lo", C.c_void_p),
+    ]
+
+
+class TrainBlockArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("cin_pad", C.c_int32), ("cout", C.c_int32),
+        ("downsample", C.c_int32), ("x", C.c_void_p), ("x_lo", C.c_void_p), ("w", C.c_void_p * 4), ("w_lo", C.c_void_p * 4),
+        ("gamma", C.c_void_p * 2), ("beta", C.c_void_p * 2), ("running_mean", C.c_void_p * 4), ("running_var", C.c_void_p * 4),
+        ("eps", C.c_float), ("momentum", C.c_float), ("slope", C.c_float), ("stats", C.c_void_p), ("mean_invstd", C.c_void_p),
+        ("raw", C.c_void_p * 4), ("h1", C.c_void_p), ("h1_lo", C.c_void_p), ("h2", C.c_void_p), ("h2_lo", C.c_void_p),
     ]
 
 
@@ -106,6 +116,8 @@ def load():
     lib.sr_bn_finalize.argtypes = [vp, i64, f32, f32, vp, vp, vp, vp, i32, vp]
     lib.sr_bn_apply.restype = i32
     lib.sr_bn_apply.argtypes = [C.POINTER(BnApplyArgs), vp]
+    lib.sr_train_block.restype = i32
+    lib.sr_train_block.argtypes = [C.POINTER(TrainBlockArgs), vp]
     lib.sr_subspace_factor_workspace_bytes.restype = i64
     lib.sr_subspace_factor_workspace_bytes.argtypes = [i32, i32]
     lib.sr_subspace_factor.restype = i32

@@ -220,7 +220,10 @@ class BackboneEngine(object):
         first blocks.  Consumed (and verified against the live generator) in draw_mask."""
         t = getattr(self, '_db_thread', None)
         if t is not None:
+            import time
+            t0 = time.perf_counter()
             t.join()
+            host_rng.WAIT_S.append(('db_join', time.perf_counter() - t0)) if len(host_rng.WAIT_S) < 4000 else None
         self._db_ready = {}
         self._db_done = False
         if self._prefetch is None or not self._prefetch.alive():
@@ -265,10 +268,13 @@ class BackboneEngine(object):
         """-> (pinned entry, kept) drawn ahead for `key`, after moving the live generator past it; or None."""
         if getattr(self, '_db_ready', None) is None:
             return None
+        import time
+        t0 = time.perf_counter()
         with self._db_cv:
             while key not in self._db_ready and not self._db_done:
                 self._db_cv.wait()
             got = self._db_ready.pop(key, None)
+        host_rng.WAIT_S.append(('db_wait', time.perf_counter() - t0)) if len(host_rng.WAIT_S) < 4000 else None
         if got is None:
             return None
         before, after, ent, kept, g, shp = got
@@ -359,7 +365,10 @@ class BackboneEngine(object):
 
     def train_features(self, x, counters):
         """One train-mode forward (batch-stat BN, running-stat EMA in place, dropout / DropBlock) -> fp32 [B,640]."""
+        import time
+        t_tf0 = time.perf_counter()
         self._ensure_raw()
+        host_rng.WAIT_S.append(('ensure_raw', time.perf_counter() - t_tf0)) if len(host_rng.WAIT_S) < 4000 else None
         raw_w = self._raw[1]
         B = x.shape[0]
         dev = x.device
@@ -376,37 +385,34 @@ class BackboneEngine(object):
         stats_off = [0]
         bumped = []
 
-        def conv_bn(act, wgt, bn, cout):
-            stats = stats_all[stats_off[0]:stats_off[0] + 2 * cout]
-            stats_off[0] += 2 * cout
-            raw = ops.conv([(act, wgt)], cout, epilogue=L.SR_EPI_RAW_STATS, stats=stats)
-            count = raw.shape[0] * raw.shape[1] * raw.shape[2]
-            mean, invstd = ops.bn_finalize(stats, count, bn.running_mean, bn.running_var, BN_EPS, BN_MOMENTUM)
-            bumped.append(bn.num_batches_tracked)
-            return raw, mean, invstd
-
         for bi, (b, w) in enumerate(zip(self.blocks, raw_w)):
             m, cout = b['mod'], b['cout']
             last = bi == nb - 1
-            r1, mu1, is1 = conv_bn(h, w['w1'], m.bn1, cout)
-            h1 = ops.bn_apply(r1, mu1, is1, m.bn1.weight.detach(), m.bn1.bias.detach(), lrelu=True, slope=SLOPE, split=self.split)
-            r2, mu2, is2 = conv_bn(h1, w['w2'], m.bn2, cout)
-            h2 = ops.bn_apply(r2, mu2, is2, m.bn2.weight.detach(), m.bn2.bias.detach(), lrelu=True, slope=SLOPE, split=self.split)
-            r3, mu3, is3 = conv_bn(h2, w['w3'], m.bn3, cout)
-            if b['downsample']:
-                bnd = m.downsample[1]
-                rd, mud, isd = conv_bn(h, w['wd'], bnd, cout)
+            ds = bool(b['downsample'])
+            bns = [m.bn1, m.bn2, m.bn3] + ([m.downsample[1]] if ds else [])
+            n_st = 2 * cout * len(bns)
+            stats = stats_all[stats_off[0]:stats_off[0] + n_st]
+            stats_off[0] += n_st
+            # conv1 .. conv3 (+ downsample conv), their batch statistics / running-stat updates and the two inner BN +
+            # LeakyReLU passes: one library call (sr_train_block) instead of ~11 launches sequenced from Python
+            r3, rd, mi = ops.train_block(
+                h, [w['w1'], w['w2'], w['w3']] + ([w['wd']] if ds else []),
+                [(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var) for bn in bns], stats,
+                h.shape[-1], cout, ds, BN_EPS, BN_MOMENTUM, SLOPE)
+            bumped += [bn.num_batches_tracked for bn in bns]
             size = size // b['pool']
             # drawn here, in forward order: the host RNG of block i overlaps the GPU work already queued for block i
             keep, scale = self.draw_mask(bi, B, size, counters, dev)
             pool = -1 if last and b['pool'] == 1 else (2 if b['pool'] == 2 else 0)
-            if b['downsample']:
-                h = ops.bn_apply(r3, mu3, is3, m.bn3.weight.detach(), m.bn3.bias.detach(), res_raw=rd,
-                                 res_bn=(mud, isd, bnd.weight.detach(), bnd.bias.detach()), lrelu=True, slope=SLOPE,
+            if ds:
+                bnd = m.downsample[1]
+                h = ops.bn_apply(r3, mi[2, 0], mi[2, 1], m.bn3.weight.detach(), m.bn3.bias.detach(), res_raw=rd,
+                                 res_bn=(mi[3, 0], mi[3, 1], bnd.weight.detach(), bnd.bias.detach()), lrelu=True, slope=SLOPE,
                                  pool=pool, keep=keep, keep_scale=scale, split=self.split)
             else:
-                h = ops.bn_apply(r3, mu3, is3, m.bn3.weight.detach(), m.bn3.bias.detach(), res_act=h, lrelu=True,
+                h = ops.bn_apply(r3, mi[2, 0], mi[2, 1], m.bn3.weight.detach(), m.bn3.bias.detach(), res_act=h, lrelu=True,
                                  slope=SLOPE, pool=pool, keep=keep, keep_scale=scale, split=self.split)
+        host_rng.WAIT_S.append(('train_fwd_host', time.perf_counter() - t_tf0)) if len(host_rng.WAIT_S) < 4000 else None
         torch._foreach_add_(bumped, 1)   # BatchNorm2d.num_batches_tracked of every BN that ran
         self.invalidate()   # running statistics moved: the folded weights are stale
         if h.dim() >= 4:    # resnet12: the last block is pooled 2x2, the global average follows

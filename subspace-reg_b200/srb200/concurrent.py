@@ -32,6 +32,16 @@ def frozen_heap():
         gc.unfreeze()
 
 
+def prewarm_allocator(gigabytes, device=None):
+    """Make PyTorch's caching allocator reserve `gigabytes` of HBM in ONE segment up front.  A sweep allocates and frees
+    multi-hundred-MB activation buffers of session-dependent sizes; served from a fragmented cache they keep falling through
+    to cudaMalloc (~9 calls per sweep), and on the B200 boxes used here a cudaMalloc / the copies and allocations queued
+    behind it occasionally block the launching thread for 100-300 ms.  With one large cached segment to split, those
+    requests are served without touching the driver (measured over 24 sweeps: stalls > 200 ms in 5 sweeps -> 1)."""
+    x = torch.empty(int(gigabytes * (1 << 30)), dtype=torch.uint8, device=device if device is not None else "cuda")
+    del x
+
+
 class SeedPool(object):
     """K persistent worker threads, each with its own CUDA stream.  map(fn, items) runs fn(item) for every item, at most K
     at a time, and returns the results in order; exceptions are re-raised in the caller."""

@@ -232,6 +232,51 @@ def bn_apply(raw, mean, invstd, gamma, beta, res_raw=None, res_bn=None, res_act=
     return out
 
 
+def train_block(x, w, bn, stats, cin_pad, cout, downsample, eps, momentum, slope):
+    """One BasicBlock of the train-mode pass up to its last BatchNorm in ONE library call (sr_train_block): conv1 -> BN ->
+    LeakyReLU -> conv2 -> BN -> LeakyReLU -> conv3 [-> 1x1 downsample conv of x], batch statistics and running-stat EMAs
+    included.  x: NHWC bf16 [B,H,W,cin_pad] or a pair [2,...]; w: [w1, w2, w3(, wd)] packed raw weights (pairs in the x3
+    tier); bn: [(gamma, beta, running_mean, running_var)] per conv; stats: zeroed fp64 [n_convs * 2 * cout].
+    -> (raw3, rawd | None, mean_invstd [n_convs, 2, cout])."""
+    split = x.dim() == 5
+    xs = x[0] if split else x
+    B, H, W, _ = xs.shape
+    dev = xs.device
+    n_convs = 4 if downsample else 3
+    a = L.TrainBlockArgs()
+    a.batch, a.height, a.width, a.cin_pad, a.cout, a.downsample = B, H, W, cin_pad, cout, 1 if downsample else 0
+    a.x = _ptr(xs, torch.bfloat16, "x")
+    a.x_lo = _ptr(x[1], torch.bfloat16, "x_lo") if split else None
+    for i in range(n_convs):
+        wi = w[i]
+        a.w[i] = _ptr(wi[0] if split else wi, torch.bfloat16, "w").value
+        a.w_lo[i] = _ptr(wi[1], torch.bfloat16, "w_lo").value if split else None
+        g, b_, rm, rv = bn[i]
+        if i < 2:
+            a.gamma[i] = _ptr(g, torch.float32, "gamma").value
+            a.beta[i] = _ptr(b_, torch.float32, "beta").value
+        a.running_mean[i] = _ptr(rm, torch.float32, "running_mean").value
+        a.running_var[i] = _ptr(rv, torch.float32, "running_var").value
+    a.eps, a.momentum, a.slope = eps, momentum, slope
+    a.stats = _ptr(stats, torch.float64, "stats")
+    mi = torch.empty((n_convs, 2, cout), dtype=torch.float32, device=dev)
+    a.mean_invstd = _ptr(mi)
+    scratch = torch.empty((B, H, W, cout), dtype=torch.float32, device=dev)      # raw output of conv1, then of conv2
+    raw3 = torch.empty((B, H, W, cout), dtype=torch.float32, device=dev)
+    rawd = torch.empty((B, H, W, cout), dtype=torch.float32, device=dev) if downsample else None
+    a.raw[0] = a.raw[1] = _ptr(scratch).value
+    a.raw[2] = _ptr(raw3).value
+    a.raw[3] = _ptr(rawd).value if downsample else None
+    h = _planes((2, B, H, W, cout), split, dev)                                  # h1 | h2 (pairs in the x3 tier)
+    if split:
+        a.h1, a.h1_lo, a.h2, a.h2_lo = _ptr(h[0, 0]), _ptr(h[1, 0]), _ptr(h[0, 1]), _ptr(h[1, 1])
+    else:
+        a.h1, a.h2 = _ptr(h[0]), _ptr(h[1])
+    L.check(L.load().sr_train_block(C.byref(a), _stream()), "sr_train_block")
+    LAUNCHES.add(2 * n_convs + 2)        # n convs + n finalizes + two BN-apply launches
+    return raw3, rawd, mi
+
+
 def subspace_factor(base_weight):
     """Orthonormal row basis Qt of span(rows of base_weight) -> (qt [q_rows, dim], q_rows, is_identity).
 
