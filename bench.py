@@ -84,53 +84,93 @@ def world_bytes(world):
 
 
 class ClockSampler(object):
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of one GPU DURING the timed region, through NVML in-process (pynvml, three cheap calls
+    every 200 ms).  The `nvidia-smi --query-gpu ... -lms 250` loop used before takes driver-wide locks for tens of
+    milliseconds per sample: measured, it stalled the launching thread by 200-350 ms in 3-4 of 12 timed sweeps (the e2e arm,
+    run without it, had none).  Falls back to nvidia-smi at a 1 s period if pynvml is unavailable."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
-        self.rows = []
-        self.proc = None
         self.idx = gpu_index
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.stop_flag = False
+        self.th = None
+        self.proc = None
+        self.source = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.idx])
+            except (ValueError, IndexError):
+                pass
+        return self.idx
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("SRB_BENCH_SMI_MS", "250")], stdout=subprocess.PIPE, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)))
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        for name, bit in self.REASONS:
+                            if mask & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    time.sleep(0.2)
+            self.th = threading.Thread(target=loop, daemon=True)
             self.th.start()
+            self.source = "nvml"
+            return
+        except Exception:
+            pass
+        try:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "1000"], stdout=subprocess.PIPE, text=True)
+
+            def read():
+                for line in self.proc.stdout:
+                    f = [x.strip() for x in line.split(",")]
+                    if len(f) < 6:
+                        continue
+                    try:
+                        self.sm.append(float(f[0]))
+                        self.mx.append(float(f[1]))
+                    except ValueError:
+                        continue
+                    for (name, _), v in zip(self.REASONS, f[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
+            self.th = threading.Thread(target=read, daemon=True)
+            self.th.start()
+            self.source = "nvidia-smi"
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nme, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        sm.sort()
-        busy = [c for c in sm if c > 0]
-        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if self.th is not None:
+            self.th.join(timeout=2)
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        busy = sorted(c for c in self.sm if c > 0)
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 def prepare(world):

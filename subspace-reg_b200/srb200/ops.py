@@ -232,6 +232,27 @@ def bn_apply(raw, mean, invstd, gamma, beta, res_raw=None, res_bn=None, res_act=
     return out
 
 
+_SCRATCH = {}
+
+
+def scratch(tag, shape, dtype, device):
+    """Grow-only device scratch buffer per (host thread, tag): the large temporaries of the train-mode pass are handed out
+    from here instead of being allocated and freed on every call.  Their sizes change from forward to forward (support vs
+    memory batches), which keeps a per-call allocation falling through PyTorch's cache to cudaMalloc - and on the GPU boxes
+    used here an allocation that reaches the driver occasionally blocks the launching thread for 100-300 ms.  Stream-ordered
+    reuse: a buffer is only ever written and read by launches on the calling thread's stream."""
+    n = 1
+    for v in shape:
+        n *= int(v)
+    nbytes = n * torch.empty((), dtype=dtype).element_size()
+    key = (threading.get_ident(), tag, str(device))
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _SCRATCH[key] = buf
+    return buf[:nbytes].view(dtype).view(shape)
+
+
 def train_block(x, w, bn, stats, cin_pad, cout, downsample, eps, momentum, slope):
     """One BasicBlock of the train-mode pass up to its last BatchNorm in ONE library call (sr_train_block): conv1 -> BN ->
     LeakyReLU -> conv2 -> BN -> LeakyReLU -> conv3 [-> 1x1 downsample conv of x], batch statistics and running-stat EMAs
@@ -261,13 +282,13 @@ def train_block(x, w, bn, stats, cin_pad, cout, downsample, eps, momentum, slope
     a.stats = _ptr(stats, torch.float64, "stats")
     mi = torch.empty((n_convs, 2, cout), dtype=torch.float32, device=dev)
     a.mean_invstd = _ptr(mi)
-    scratch = torch.empty((B, H, W, cout), dtype=torch.float32, device=dev)      # raw output of conv1, then of conv2
-    raw3 = torch.empty((B, H, W, cout), dtype=torch.float32, device=dev)
-    rawd = torch.empty((B, H, W, cout), dtype=torch.float32, device=dev) if downsample else None
-    a.raw[0] = a.raw[1] = _ptr(scratch).value
+    raw12 = scratch('tb_raw12', (B, H, W, cout), torch.float32, dev)            # raw output of conv1, then of conv2
+    raw3 = scratch('tb_raw3', (B, H, W, cout), torch.float32, dev)
+    rawd = scratch('tb_rawd', (B, H, W, cout), torch.float32, dev) if downsample else None
+    a.raw[0] = a.raw[1] = _ptr(raw12).value
     a.raw[2] = _ptr(raw3).value
     a.raw[3] = _ptr(rawd).value if downsample else None
-    h = _planes((2, B, H, W, cout), split, dev)                                  # h1 | h2 (pairs in the x3 tier)
+    h = scratch('tb_h', ((2, 2) if split else (2,)) + (B, H, W, cout), torch.bfloat16, dev)   # h1 | h2 (pairs in the x3 tier)
     if split:
         a.h1, a.h1_lo, a.h2, a.h2_lo = _ptr(h[0, 0]), _ptr(h[1, 0]), _ptr(h[0, 1]), _ptr(h[1, 1])
     else:
