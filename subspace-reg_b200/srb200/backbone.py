@@ -6,6 +6,7 @@ sr_bn_apply); this module only owns buffers and launch order.  Reference semanti
 """
 import os
 import threading
+import time
 
 import torch
 import torch.nn.functional as F
@@ -220,10 +221,7 @@ class BackboneEngine(object):
         first blocks.  Consumed (and verified against the live generator) in draw_mask."""
         t = getattr(self, '_db_thread', None)
         if t is not None:
-            import time
-            t0 = time.perf_counter()
             t.join()
-            host_rng.WAIT_S.append(('db_join', time.perf_counter() - t0)) if len(host_rng.WAIT_S) < 4000 else None
         self._db_ready = {}
         self._db_done = False
         if self._prefetch is None or not self._prefetch.alive():
@@ -268,13 +266,12 @@ class BackboneEngine(object):
         """-> (pinned entry, kept) drawn ahead for `key`, after moving the live generator past it; or None."""
         if getattr(self, '_db_ready', None) is None:
             return None
-        import time
         t0 = time.perf_counter()
         with self._db_cv:
             while key not in self._db_ready and not self._db_done:
                 self._db_cv.wait()
             got = self._db_ready.pop(key, None)
-        host_rng.WAIT_S.append(('db_wait', time.perf_counter() - t0)) if len(host_rng.WAIT_S) < 4000 else None
+        host_rng.WAIT_S[0] += time.perf_counter() - t0
         if got is None:
             return None
         before, after, ent, kept, g, shp = got
@@ -365,10 +362,7 @@ class BackboneEngine(object):
 
     def train_features(self, x, counters):
         """One train-mode forward (batch-stat BN, running-stat EMA in place, dropout / DropBlock) -> fp32 [B,640]."""
-        import time
-        t_tf0 = time.perf_counter()
         self._ensure_raw()
-        host_rng.WAIT_S.append(('ensure_raw', time.perf_counter() - t_tf0)) if len(host_rng.WAIT_S) < 4000 else None
         raw_w = self._raw[1]
         B = x.shape[0]
         dev = x.device
@@ -412,7 +406,6 @@ class BackboneEngine(object):
             else:
                 h = ops.bn_apply(r3, mi[2, 0], mi[2, 1], m.bn3.weight.detach(), m.bn3.bias.detach(), res_act=h, lrelu=True,
                                  slope=SLOPE, pool=pool, keep=keep, keep_scale=scale, split=self.split)
-        host_rng.WAIT_S.append(('train_fwd_host', time.perf_counter() - t_tf0)) if len(host_rng.WAIT_S) < 4000 else None
         torch._foreach_add_(bumped, 1)   # BatchNorm2d.num_batches_tracked of every BN that ran
         self.invalidate()   # running statistics moved: the folded weights are stale
         if h.dim() >= 4:    # resnet12: the last block is pooled 2x2, the global average follows

@@ -28,8 +28,11 @@ def init(backend=None):
             cores = os.cpu_count() or 1
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
         per_rank = cores // max(local_world, 1)
-        # main thread + prefetch thread + DropBlock thread come first; walkers get what is left, at most 4
-        os.environ["SRB_RNG_THREADS"] = str(max(0, min(4, per_rank - 3)))
+        # The launching thread and the (mostly waiting) prefetch / DropBlock threads share two cores; the generator walkers
+        # get the rest, between 2 and 4: one walker tempers + compares ~1.1 G generator words per sweep at ~0.35 ns each,
+        # i.e. needs as long as the GPU needs for the sweep - with a single walker (8 ranks on 32 cores under the old
+        # `per_rank - 3` rule) the train-mode passes waited for their masks and the 8-GPU efficiency dropped to 0.92.
+        os.environ["SRB_RNG_THREADS"] = str(max(2, min(4, per_rank - 2)))
     if world > 1 and not dist.is_initialized():
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"

@@ -8,6 +8,7 @@ crosses several generator blocks; otherwise every call goes to torch.
 """
 import ctypes as C
 import threading
+import time
 
 import torch
 
@@ -15,7 +16,8 @@ from . import _lib as L
 from . import rng
 
 _replay_ok = None
-WAIT_S = [0.0, 0.0, 0]   # diagnostics: seconds the consumer waited for pre-drawn masks / spent drawing inline, inline draws
+WAIT_S = [0.0, 0.0, 0]   # diagnostics (tools/one_sweep.py): seconds the run's thread waited for pre-drawn masks, seconds it spent
+                         # drawing masks itself, number of such in-line draws
 
 
 def _torch_draw(shape, p, kind):
@@ -79,7 +81,6 @@ def bernoulli_u8(shape, p, kind, out=None):
     """uint8 CPU tensor of draws (1 with probability p) + number of ones, consuming torch's CPU generator exactly like
     kind 0: tensor.bernoulli_(p)   kind 1: torch.bernoulli(torch.tensor(p).expand(shape))."""
     if replay_available():
-        import time
         t0 = time.perf_counter()
         r = _replay_draw(shape, p, kind, out)
         WAIT_S[1] += time.perf_counter() - t0
@@ -192,7 +193,6 @@ class MaskPrefetch(object):
         """-> (uint8 buffer, ones) or None.  Advances torch's live generator exactly as the draw would have."""
         if self.thread is None or self.dead:
             return None
-        import time
         t0 = time.perf_counter()
         with self._cv:
             while key not in self.results and not self.finished and not self.dead:

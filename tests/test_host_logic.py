@@ -222,7 +222,11 @@ def test_rng_thread_share_between_local_ranks(monkeypatch):
     monkeypatch.setenv("WORLD_SIZE", "1")
     monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(32)), raising=False)
     sdist.init()
-    assert os.environ["SRB_RNG_THREADS"] == "1"          # 32 cores / 8 ranks = 4 per rank, 3 of them spoken for
+    assert os.environ["SRB_RNG_THREADS"] == "2"          # 32 cores / 8 ranks = 4 per rank: two walkers, never fewer
+    monkeypatch.delenv("SRB_RNG_THREADS", raising=False)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    sdist.init()
+    assert os.environ["SRB_RNG_THREADS"] == "4"          # a rank with the whole host still uses at most four
     monkeypatch.setenv("SRB_RNG_THREADS", "3")
     sdist.init()
     assert os.environ["SRB_RNG_THREADS"] == "3"          # an explicit setting wins
