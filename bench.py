@@ -156,6 +156,10 @@ class ClockSampler(object):
         except Exception:
             self.proc = None
 
+    def reset(self):
+        """Forget the samples taken so far (warm-up): only the timed region is reported."""
+        self.sm, self.reasons = [], set()
+
     def stop(self):
         self.stop_flag = True
         if self.proc is not None:
@@ -377,14 +381,15 @@ def main():
     # warm-up is then at least the timed region's, whatever --steps / --warmup are)
     worlds = [prepare(place_world(mk(s), 'gpu')) for s in timed_seeds]
     warm = [prepare(place_world(w, 'gpu')) for w in warm]
+    sampler = ClockSampler(local)
+    sampler.start()          # NVML initialisation happens here, outside the timed region; samples are reset below
     run_sweeps(warm, pool)
     del warm
 
     # ---- value: inputs already resident in HBM ----
-    sampler = ClockSampler(local)
     torch.cuda.synchronize()
     l0 = ops.LAUNCHES[0]
-    sampler.start()
+    sampler.reset()
     ms, recs = timed_sweeps(worlds, device, pool)
     clocks = sampler.stop()
     launches = ops.LAUNCHES[0] - l0
@@ -508,10 +513,12 @@ def main():
             return synthetic.make_world(seed, n_sessions=args.sessions, n_base_batch=args.base_batch, word_embed_path=wdir,
                                         conv_precision="bf16x3")
         run_sweeps([prepare(place_world(mk_x3(3000), 'gpu'))], None)                       # warm-up (packs the weight pairs)
-        r3 = run_sweeps([prepare(place_world(mk_x3(1), 'gpu'))], None)[0]
+        r3s = run_sweeps([prepare(place_world(mk_x3(sd), 'gpu')) for sd in (1, 2, 3)], None)
+        r3 = sorted(r3s, key=lambda r_: r_['wall_ms'])[1]                                   # the median sweep of three
         ep3 = sum(s_['epochs'] for s_ in r3['sessions'])
         parity_tier = {"conv_precision": "bf16x3", "ms_per_step": r3['wall_ms'], "value": ep3 / (r3['wall_ms'] * 1e-3),
-                       "unit": "steps/s", "note": "one sweep (seed 1) run alone, host wall time; this is the tier whose class "
+                       "unit": "steps/s", "sweep_wall_ms": [round(r_['wall_ms'], 1) for r_ in r3s],
+                       "note": "median of three sweeps (seeds 1-3) run alone, host wall time; this is the tier whose class "
                        "predictions are identical to the fp32 oracle's (tests/test_gpu_config2.py)"}
 
     # ---- BASELINE config 5: head / regulariser stress shapes (1000 base + 100 novel classes, 100-shot, 512-d) ----

@@ -13,7 +13,7 @@
 //                                                      S x (Cp/256) x (d/256) CTAs fill the machine; the S partial
 //                                                      products are summed in a fixed order by the update kernel.
 //
-// One epoch = seven launches enqueued back to back by the host loop below (no host synchronisation; a device flag turns the
+// One epoch = six launches enqueued back to back by the host loop below (no host synchronisation; a device flag turns the
 // launches after the stopping rule has fired into no-ops):
 //   conv(Z) -> row statistics (lse, CE, hits) -> dZ^T as hi / lo planes -> pullers -> conv(dW partials) -> loss + rule
 //   -> update (regulariser gradients, optimiser, new W in fp32 and as hi / lo planes, drift norms of the new W).
@@ -39,6 +39,7 @@ struct TcGeom {
 struct TcStart {
     int epoch0, step0, stable_count0;
     float prev_loss;
+    int stopflag[2];   // [e & 1] = the stopping rule has fired by the end of epoch e (read by the update CTAs of epoch e + 1)
 };
 
 bool tc_geometry(const sr_head_args* a, TcGeom* g) {
@@ -72,8 +73,8 @@ bool tc_geometry(const sr_head_args* a, TcGeom* g) {
     g->rowpart = take((int64_t)g->n_rowctas * 4 * 8);
     g->pull_sq = take((int64_t)std::max(a->n_new, 1) * 8);
     g->gpull = take((int64_t)std::max(a->n_new, 1) * g->d * 4);
-    g->nbp = take((int64_t)g->n_upd * 8);
-    g->nnp = take((int64_t)g->n_upd * 8);
+    g->nbp = take(2ll * g->n_upd * 8);   // [2][n_upd]: parity e & 1 holds the partials of W_e
+    g->nnp = take(2ll * g->n_upd * 8);
     g->total = off;
     return true;
 }
@@ -104,6 +105,7 @@ __global__ void tc_init_kernel(const TcParams p) {
     p.start->stable_count0 = st.stable_count0;
     p.start->prev_loss = st.prev_loss;
     p.ctrl->stop = st.already_stopped ? 1 : 0;
+    p.start->stopflag[0] = p.start->stopflag[1] = st.already_stopped ? 1 : 0;
     p.ctrl->epochs_done = 0;
     p.ctrl->stable_count = st.stable_count0;
     p.ctrl->prev_loss = st.prev_loss;
@@ -364,9 +366,9 @@ __global__ void __launch_bounds__(kT) tc_pull_kernel(const TcParams p) {
     if (tid == 0) p.pull_sq[i] = tot;
 }
 
-// Loss of epoch e (pre-update weights) + the reference's stopping rule (language_eval.py:298-318).  One CTA.
-__global__ void __launch_bounds__(kT) tc_loss_kernel(const TcParams p, int e) {
-    if (p.ctrl->stop) return;
+// Loss of epoch e (pre-update weights) + the reference's stopping rule (language_eval.py:298-318).  One CTA (the extra
+// CTA of the update kernel: it runs next to the update CTAs instead of in a launch of its own).
+__device__ void tc_assemble_loss(const TcParams& p, int e) {
     const sr_head_args& a = p.a;
     const int tid = threadIdx.x;
     const bool has_base = a.base_weight != nullptr;
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(kT) tc_loss_kernel(const TcParams p, int e) {
         h1 += p.rowpart[(int64_t)i * 4 + 2];
         h5 += p.rowpart[(int64_t)i * 4 + 3];
     }
-    for (int i = tid; i < p.g.n_upd; i += kT) { nb += p.nbp[i]; nn += p.nnp[i]; }
+    for (int i = tid; i < p.g.n_upd; i += kT) { nb += p.nbp[(e & 1) * p.g.n_upd + i]; nn += p.nnp[(e & 1) * p.g.n_upd + i]; }
     for (int i = tid; i < n_pull; i += kT) ps += p.pull_sq[i];
     {   // the seven sums in one pass: warp shuffles, then warp totals added in warp order (deterministic)
         __shared__ double s7[kT / 32][7];
@@ -427,15 +429,22 @@ __global__ void __launch_bounds__(kT) tc_loss_kernel(const TcParams p, int e) {
         p.ctrl->stable_count = sc;
         p.ctrl->prev_loss = loss;
         p.ctrl->epochs_done = e + 1;
-        __threadfence();
-        p.ctrl->stop = stop;
+        p.start->stopflag[e & 1] = stop;   // for the update CTAs of epoch e + 1 (this epoch's read the other slot)
+        p.ctrl->stop = stop;               // for every other kernel of the later epochs (launched after this one ends)
     }
 }
 
 // dW = sum of the S split-K partials (fixed order) + regulariser gradients + weight decay -> optimiser step; the new W
 // in fp32, as hi / lo planes for the next logits GEMM, and the drift-norm partials of the new W.
 __global__ void __launch_bounds__(kT) tc_update_kernel(const TcParams p, int e) {
-    if (p.ctrl->epochs_done != e + 1) return;   // this epoch's loss kernel did not run: the rule fired in an earlier epoch
+    if (p.start->stopflag[(e + 1) & 1]) {   // the rule fired in an earlier epoch (slot written by epoch e - 1 / init)
+        if ((int)blockIdx.x == p.g.n_upd && threadIdx.x == 0) p.start->stopflag[e & 1] = 1;   // keep it set for epoch e + 1
+        return;
+    }
+    if ((int)blockIdx.x == p.g.n_upd) {            // the extra CTA: loss of this epoch + stopping rule
+        tc_assemble_loss(p, e);
+        return;
+    }
     __shared__ double red[32];
     const sr_head_args& a = p.a;
     const int d = p.g.d, C = p.g.C, Cp = p.g.Cp;
@@ -443,8 +452,15 @@ __global__ void __launch_bounds__(kT) tc_update_kernel(const TcParams p, int e) 
     const bool has_base = a.base_weight != nullptr;
     const bool has_prev = a.reserve_weight != nullptr && a.n_prev_novel > 0;
     const int n_pull = a.pull_mode == SR_PULL_NONE ? 0 : a.n_new;
-    const float nb = has_base ? (float)sqrt(p.ctrl->norm_base_sq) : 0.f;
-    const float np_ = has_prev ? (float)sqrt(p.ctrl->norm_prev_sq) : 0.f;
+    // drift norms of W_e: every CTA adds the same partials in the same order (no dependency on the loss CTA)
+    double nbs = 0.0, nns = 0.0, unused0 = 0.0;
+    for (int t = threadIdx.x; t < p.g.n_upd; t += kT) {
+        nbs += p.nbp[(e & 1) * p.g.n_upd + t];
+        nns += p.nnp[(e & 1) * p.g.n_upd + t];
+    }
+    block_sum3(nbs, nns, unused0, red);
+    const float nb = has_base ? (float)sqrt(nbs) : 0.f;
+    const float np_ = has_prev ? (float)sqrt(nns) : 0.f;
     const float sb = nb > 0.f ? a.lmbd_base / nb : 0.f;    // d||x||/dx = x/||x||, 0 at x = 0 (as torch)
     const float sn = np_ > 0.f ? a.lmbd_novel / np_ : 0.f;
     const int step = p.start->step0 + e;
@@ -522,7 +538,10 @@ __global__ void __launch_bounds__(kT) tc_update_kernel(const TcParams p, int e) 
             for (int j = 0; j < 4; ++j) { const float dl = wn[j] - wr[j]; nnp += (double)dl * dl; }
     }
     block_sum3(nbp, nnp, unused, red);
-    if (threadIdx.x == 0) { p.nbp[blockIdx.x] = nbp; p.nnp[blockIdx.x] = nnp; }
+    if (threadIdx.x == 0) {
+        p.nbp[((e + 1) & 1) * p.g.n_upd + blockIdx.x] = nbp;
+        p.nnp[((e + 1) & 1) * p.g.n_upd + blockIdx.x] = nnp;
+    }
 }
 
 __global__ void tc_finish_kernel(const TcParams p) {
@@ -669,8 +688,7 @@ int32_t head_tc_run(const sr_head_args* a, cudaStream_t stream) {
         if (n_pull) tc_pull_kernel<<<n_pull, kT, 3 * g.d * sizeof(float), stream>>>(p);
         rc = sr_conv(&gw, stream);
         if (rc != SR_OK) return rc;
-        tc_loss_kernel<<<1, kT, 0, stream>>>(p, e);
-        tc_update_kernel<<<g.n_upd, kT, 0, stream>>>(p, e);
+        tc_update_kernel<<<g.n_upd + 1, kT, 0, stream>>>(p, e);   // n_upd update CTAs + the loss / stopping-rule CTA
         SR_CUDA_OK(cudaGetLastError());
     }
     tc_finish_kernel<<<1, 1, 0, stream>>>(p);
