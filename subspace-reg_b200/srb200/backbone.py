@@ -53,6 +53,8 @@ class BackboneEngine(object):
         self._db_cv = threading.Condition()
         self._pf_fwd = 0          # index of the next train-mode forward relative to the prefetch plan
         self._pool_owner = threading.get_ident()   # staging buffers are pooled per run thread (helper threads use the owner's)
+        self._mask_read = {}      # device mask buffer -> event after its last reader on the run's stream
+        self._mask_pending = None
 
     # ---------------------------------------------------------------- weight packing
     def _bn_key(self):
@@ -351,13 +353,22 @@ class BackboneEngine(object):
         cs = getattr(self, '_copy_stream', None)
         if cs is None:
             cs = self._copy_stream = torch.cuda.Stream(device=device)
+        # The device copy lives in a grow-only buffer per (block, forward parity) instead of a fresh allocation: mask sizes
+        # change with every forward (support / memory batches), so fresh allocations on the copy stream kept reaching
+        # cudaMalloc, where the launching thread was seen to block for 100-300 ms.  The buffer's previous reader (the
+        # sr_bn_apply of two forwards ago, on the run's stream) is fenced with an event before the copy overwrites it.
+        dkey = ('mask', bi, self._cur_fwd & 1)
+        keep = ops.scratch(dkey, shape, torch.uint8, device)
+        last_read = self._mask_read.get(dkey)
         with torch.cuda.stream(cs):
-            keep = ent[0].to(device, non_blocking=True)
+            if last_read is not None:
+                cs.wait_event(last_read)
+            keep.copy_(ent[0], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(cs)
         ent[1] = ev                    # the staging buffer may be rewritten once this copy has finished
         main.wait_event(ev)            # consumers on the run's stream (sr_bn_apply) wait for the copy only
-        keep.record_stream(main)
+        self._mask_pending = dkey      # train_features records the reader's event after the consuming launch
         return keep, scale
 
     def train_features(self, x, counters):
@@ -406,6 +417,11 @@ class BackboneEngine(object):
             else:
                 h = ops.bn_apply(r3, mi[2, 0], mi[2, 1], m.bn3.weight.detach(), m.bn3.bias.detach(), res_act=h, lrelu=True,
                                  slope=SLOPE, pool=pool, keep=keep, keep_scale=scale, split=self.split)
+            if self._mask_pending is not None:      # the mask buffer of this block has been read: fence its next overwrite
+                ev = torch.cuda.Event()
+                ev.record()
+                self._mask_read[self._mask_pending] = ev
+                self._mask_pending = None
         torch._foreach_add_(bumped, 1)   # BatchNorm2d.num_batches_tracked of every BN that ran
         self.invalidate()   # running statistics moved: the folded weights are stale
         if h.dim() >= 4:    # resnet12: the last block is pooled 2x2, the global average follows
