@@ -181,6 +181,34 @@ typedef struct sr_train_block_args {
 
 int32_t sr_train_block(const sr_train_block_args* a, void* stream);
 
+/* The whole eval-mode backbone (ResNet.forward up to `feat`, resnet_language.py:170-181, on folded-BN weights) behind ONE
+ * call: 3 convolutions per BasicBlock (the 1x1 downsample conv rides as a second K panel of conv3), LeakyReLU, residual,
+ * MaxPool2d(2), and the final AdaptiveAvgPool2d(1) fused into the last epilogue (a pooled last block - resnet12 - gets
+ * sr_global_avg).  18 launches for resnet18.  `blocks` is a HOST array. */
+typedef struct sr_eval_block {
+    int32_t cout;
+    int32_t pool;            /* MaxPool2d stride of the block: 1 or 2                                      */
+    int32_t downsample;      /* 1: wd is the 1x1 downsample conv of the residual branch (BN folded in)      */
+    int32_t reserved;
+    const void *w1, *w2, *w3, *wd;             /* packed weights with the BN scale folded in (sr_pack_weight) */
+    const void *w1_lo, *w2_lo, *w3_lo, *wd_lo; /* low planes (error-compensated tier) or NULL                 */
+    const float *s1, *s2, *s3;                 /* folded shifts; s3 already holds bn3 + downsample-BN shifts   */
+} sr_eval_block;
+
+typedef struct sr_backbone_eval_args {
+    int32_t n_blocks;
+    const sr_eval_block* blocks;
+    int32_t batch, height, width, cin_pad;     /* of the packed input                                         */
+    const void *x, *x_lo;                      /* NHWC bf16 [batch,height,width,cin_pad] (+ low plane)         */
+    float slope;
+    void* workspace;                           /* sr_backbone_eval_workspace_bytes(...) bytes, 256-byte aligned */
+    int64_t workspace_bytes;
+    float* features;                           /* out: fp32 [batch, cout of the last block]                    */
+} sr_backbone_eval_args;
+
+int64_t sr_backbone_eval_workspace_bytes(const sr_backbone_eval_args* a);
+int32_t sr_backbone_eval(const sr_backbone_eval_args* a, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Subspace regulariser: orthonormal factor of span(base weights)
  * Replaces torch.qr(base_weight^T, some=True) in LangPuller.get_projected_weight

@@ -316,8 +316,7 @@ __global__ void __launch_bounds__(kT, 1) head_cluster_kernel(const ClParams p) {
     grid_barrier(p.ctrl, bar_target);
 
     constexpr int CG = CP / 4;          // 4-class groups (16 or 32)
-    constexpr int RGN = kT / CG;        // row groups (16 or 8)
-    const int cg4 = tid % CG, rg = tid / CG;
+    const int cg4 = tid % CG, rg = tid / CG;   // 4-class group, row group (kT / CG of them)
     const uint32_t w_bytes = (uint32_t)(KB * cw * 4), d_bytes = (uint32_t)(SB * cw * 4);
     int e = 0;
     bool stopped = false;

@@ -1,6 +1,7 @@
 // Data-layout and train-mode BatchNorm kernels around the tcgen05 convolution (HBM-bound elementwise work:
 // coalesced 128-bit accesses, grids sized from the element count).
 #include <cuda_bf16.h>
+#include <algorithm>
 #include "common.h"
 
 namespace {
@@ -370,6 +371,90 @@ extern "C" int32_t sr_bn_finalize(const double* stats, int64_t count, float eps,
 }
 
 extern "C" int32_t sr_bn_apply(const sr_bn_apply_args* a, void* stream_v);
+
+// ---- whole eval-mode backbone pass -------------------------------------------------------------------------------
+namespace {
+// Four activation buffers (conv1 out, conv2 out, and two alternating block outputs: a block's input stays live until its
+// conv3 has read it as residual / downsample panel), each sized for the largest layer, x2 in the error-compensated tier.
+int64_t eval_buffer_bytes(const sr_backbone_eval_args* a) {
+    int64_t mx = 0;
+    int h = a->height, w = a->width;
+    for (int i = 0; i < a->n_blocks; ++i) {
+        mx = std::max<int64_t>(mx, (int64_t)a->batch * h * w * a->blocks[i].cout * 2);
+        if (a->blocks[i].pool == 2) { h /= 2; w /= 2; }
+    }
+    return align_up(mx * (a->x_lo ? 2 : 1), 256);
+}
+}  // namespace
+
+extern "C" int64_t sr_backbone_eval_workspace_bytes(const sr_backbone_eval_args* a) {
+    if (!a || !a->blocks || a->n_blocks < 1 || a->batch < 1) return 0;
+    return 4 * eval_buffer_bytes(a);
+}
+
+extern "C" int32_t sr_backbone_eval(const sr_backbone_eval_args* a, void* stream_v) {
+    if (!a || !a->blocks || a->n_blocks < 1 || !a->x || !a->features || !a->workspace)
+        return fail(SR_E_ARG, "sr_backbone_eval: null pointer");
+    if (reinterpret_cast<uintptr_t>(a->workspace) & 255) return fail(SR_E_ARG, "sr_backbone_eval: workspace must be 256-byte aligned");
+    const int64_t buf = eval_buffer_bytes(a);
+    if (a->workspace_bytes < 4 * buf) return fail(SR_E_SMALLWS, "sr_backbone_eval: workspace %lld < %lld", (long long)a->workspace_bytes, (long long)(4 * buf));
+    const bool precise = a->x_lo != nullptr;
+    uint8_t* ws = static_cast<uint8_t*>(a->workspace);
+    // plane pointers of buffer k: hi at the start, lo in the second half
+    auto hi = [&](int k) { return static_cast<void*>(ws + k * buf); };
+    auto lo = [&](int k) { return precise ? static_cast<void*>(ws + k * buf + buf / 2) : nullptr; };
+    const void* in = a->x;
+    const void* in_lo = a->x_lo;
+    int cin_pad = a->cin_pad, h = a->height, w = a->width;
+    for (int i = 0; i < a->n_blocks; ++i) {
+        const sr_eval_block& b = a->blocks[i];
+        const bool last = i == a->n_blocks - 1;
+        if (!b.w1 || !b.w2 || !b.w3 || (b.downsample && !b.wd)) return fail(SR_E_ARG, "sr_backbone_eval: block %d lacks weights", i);
+        sr_conv_args c;
+        auto conv = [&](const void* act, const void* act_lo, int cin, const void* wgt, const void* wgt_lo, const float* shift,
+                        int out_k, int epi, const void* res, const void* res_lo, const void* ds_act, const void* ds_act_lo,
+                        int ds_cin) -> int32_t {
+            memset(&c, 0, sizeof(c));
+            c.batch = a->batch; c.height = h; c.width = w; c.cout = b.cout;
+            c.n_panels = ds_act ? 2 : 1;
+            c.panel[0].act = act; c.panel[0].act_lo = precise ? act_lo : nullptr;
+            c.panel[0].wgt = wgt; c.panel[0].wgt_lo = precise ? wgt_lo : nullptr;
+            c.panel[0].cin_pad = cin; c.panel[0].taps = 9;
+            if (ds_act) {
+                c.panel[1].act = ds_act; c.panel[1].act_lo = precise ? ds_act_lo : nullptr;
+                c.panel[1].wgt = b.wd; c.panel[1].wgt_lo = precise ? b.wd_lo : nullptr;
+                c.panel[1].cin_pad = ds_cin; c.panel[1].taps = 1;
+            }
+            c.shift = shift; c.residual = res; c.residual_lo = precise ? res_lo : nullptr;
+            c.slope = a->slope; c.epilogue = epi;
+            if (epi == SR_EPI_ACT_AVG) {
+                c.out = a->features;
+            } else {
+                c.out = hi(out_k); c.out_lo = lo(out_k);
+            }
+            return sr_conv(&c, stream_v);
+        };
+        int32_t rc = conv(in, in_lo, cin_pad, b.w1, b.w1_lo, b.s1, 0, SR_EPI_ACT, nullptr, nullptr, nullptr, nullptr, 0);
+        if (rc != SR_OK) return rc;
+        rc = conv(hi(0), lo(0), b.cout, b.w2, b.w2_lo, b.s2, 1, SR_EPI_ACT, nullptr, nullptr, nullptr, nullptr, 0);
+        if (rc != SR_OK) return rc;
+        const int out_k = 2 + (i & 1);
+        int epi = b.pool == 2 ? SR_EPI_ACT_POOL2 : SR_EPI_ACT;
+        const bool fused_avg = last && b.pool != 2;      // resnet18: the last block averages inside the conv epilogue
+        if (fused_avg) epi = SR_EPI_ACT_AVG;
+        if (b.downsample)
+            rc = conv(hi(1), lo(1), b.cout, b.w3, b.w3_lo, b.s3, out_k, epi, nullptr, nullptr, in, in_lo, cin_pad);
+        else
+            rc = conv(hi(1), lo(1), b.cout, b.w3, b.w3_lo, b.s3, out_k, epi, in, in_lo, nullptr, nullptr, 0);
+        if (rc != SR_OK) return rc;
+        if (b.pool == 2) { h /= 2; w /= 2; }
+        if (last && !fused_avg) return sr_global_avg(hi(out_k), lo(out_k), a->features, a->batch, h, w, b.cout, stream_v);
+        in = hi(out_k);
+        in_lo = lo(out_k);
+        cin_pad = b.cout;
+    }
+    return SR_OK;
+}
 
 extern "C" int32_t sr_train_block(const sr_train_block_args* a, void* stream_v) {
     if (!a || !a->x || !a->stats || !a->mean_invstd || !a->h1 || !a->h2) return fail(SR_E_ARG, "sr_train_block: null pointer");

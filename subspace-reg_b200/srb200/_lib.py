@@ -18,7 +18,7 @@ EXPORTS = [
     "sr_last_error", "sr_version", "sr_check_device", "sr_pack_input", "sr_bn_fold", "sr_pack_weight", "sr_conv",
     "sr_bn_finalize", "sr_bn_apply", "sr_subspace_factor_workspace_bytes", "sr_subspace_factor",
     "sr_head_workspace_bytes", "sr_head_run", "sr_eval_logits", "sr_semantic_pullers", "sr_linear_fwd",
-    "sr_linear_bwd", "sr_sqdist", "sr_diff_scale", "sr_project_rows", "sr_score_logits", "sr_host_bernoulli", "sr_host_dropblock", "sr_conv_plan", "sr_pack_input_u8", "sr_global_avg", "sr_mse_grad", "sr_sgd_update", "sr_eval_workspace_bytes", "sr_train_block",
+    "sr_linear_bwd", "sr_sqdist", "sr_diff_scale", "sr_project_rows", "sr_score_logits", "sr_host_bernoulli", "sr_host_dropblock", "sr_conv_plan", "sr_pack_input_u8", "sr_global_avg", "sr_mse_grad", "sr_sgd_update", "sr_eval_workspace_bytes", "sr_train_block", "sr_backbone_eval_workspace_bytes", "sr_backbone_eval",
 ]
 
 
@@ -56,6 +56,19 @@ class TrainBlockArgs(C.Structure):
         ("eps", C.c_float), ("momentum", C.c_float), ("slope", C.c_float), ("stats", C.c_void_p), ("mean_invstd", C.c_void_p),
         ("raw", C.c_void_p * 4), ("h1", C.c_void_p), ("h1_lo", C.c_void_p), ("h2", C.c_void_p), ("h2_lo", C.c_void_p),
     ]
+
+
+class EvalBlock(C.Structure):
+    _fields_ = [("cout", C.c_int32), ("pool", C.c_int32), ("downsample", C.c_int32), ("reserved", C.c_int32),
+                ("w1", C.c_void_p), ("w2", C.c_void_p), ("w3", C.c_void_p), ("wd", C.c_void_p),
+                ("w1_lo", C.c_void_p), ("w2_lo", C.c_void_p), ("w3_lo", C.c_void_p), ("wd_lo", C.c_void_p),
+                ("s1", C.c_void_p), ("s2", C.c_void_p), ("s3", C.c_void_p)]
+
+
+class BackboneEvalArgs(C.Structure):
+    _fields_ = [("n_blocks", C.c_int32), ("blocks", C.POINTER(EvalBlock)), ("batch", C.c_int32), ("height", C.c_int32),
+                ("width", C.c_int32), ("cin_pad", C.c_int32), ("x", C.c_void_p), ("x_lo", C.c_void_p), ("slope", C.c_float),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("features", C.c_void_p)]
 
 
 class HeadArgs(C.Structure):
@@ -116,6 +129,10 @@ def load():
     lib.sr_bn_finalize.argtypes = [vp, i64, f32, f32, vp, vp, vp, vp, i32, vp]
     lib.sr_bn_apply.restype = i32
     lib.sr_bn_apply.argtypes = [C.POINTER(BnApplyArgs), vp]
+    lib.sr_backbone_eval_workspace_bytes.restype = i64
+    lib.sr_backbone_eval_workspace_bytes.argtypes = [C.POINTER(BackboneEvalArgs)]
+    lib.sr_backbone_eval.restype = i32
+    lib.sr_backbone_eval.argtypes = [C.POINTER(BackboneEvalArgs), vp]
     lib.sr_train_block.restype = i32
     lib.sr_train_block.argtypes = [C.POINTER(TrainBlockArgs), vp]
     lib.sr_subspace_factor_workspace_bytes.restype = i64

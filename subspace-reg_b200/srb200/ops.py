@@ -232,6 +232,40 @@ def bn_apply(raw, mean, invstd, gamma, beta, res_raw=None, res_bn=None, res_act=
     return out
 
 
+def backbone_eval(h, blocks, folded, slope=0.1):
+    """The whole eval-mode backbone on a packed input in ONE library call (sr_backbone_eval): h NHWC bf16 [B,H,W,cin_pad]
+    (or a pair [2,...]), blocks = the engine's block descriptors, folded = their folded-BN packed weights / shifts.
+    -> fp32 [B, cout_last]."""
+    split = h.dim() == 5
+    hs = h[0] if split else h
+    B, H, W, cin_pad = hs.shape
+    dev = hs.device
+    arr = (L.EvalBlock * len(blocks))()
+    for i, (b, w) in enumerate(zip(blocks, folded)):
+        e = arr[i]
+        e.cout, e.pool, e.downsample = b['cout'], b['pool'], 1 if b['downsample'] else 0
+        for k in ('w1', 'w2', 'w3') + (('wd',) if b['downsample'] else ()):
+            t = w[k]
+            setattr(e, k, _ptr(t[0] if split else t, torch.bfloat16, k).value)
+            if split:
+                setattr(e, k + '_lo', _ptr(t[1], torch.bfloat16, k + '_lo').value)
+        e.s1, e.s2, e.s3 = (_ptr(w[k], torch.float32, k).value for k in ('s1', 's2', 's3'))
+    a = L.BackboneEvalArgs()
+    a.n_blocks, a.blocks = len(blocks), arr
+    a.batch, a.height, a.width, a.cin_pad = B, H, W, cin_pad
+    a.x = _ptr(hs, torch.bfloat16, "x")
+    a.x_lo = _ptr(h[1], torch.bfloat16, "x_lo") if split else None
+    a.slope = slope
+    ws_bytes = int(L.load().sr_backbone_eval_workspace_bytes(C.byref(a)))
+    ws = scratch('backbone_eval', (ws_bytes,), torch.uint8, dev)
+    a.workspace, a.workspace_bytes = _ptr(ws), ws_bytes
+    feat = torch.empty((B, blocks[-1]['cout']), dtype=torch.float32, device=dev)
+    a.features = _ptr(feat)
+    L.check(L.load().sr_backbone_eval(C.byref(a), _stream()), "sr_backbone_eval")
+    LAUNCHES.add(3 * len(blocks) + (1 if blocks[-1]['pool'] == 2 else 0))
+    return feat
+
+
 _SCRATCH = {}
 
 

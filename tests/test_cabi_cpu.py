@@ -45,9 +45,10 @@ def test_struct_layouts_match_c(tmp_path):
     from srb200 import _lib
     prog = tmp_path / "sizes.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "srb200.h"\nint main(void){'
-                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(sr_conv_panel), sizeof(sr_conv_args), sizeof(sr_bn_apply_args),'
+                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu ", sizeof(sr_conv_panel), sizeof(sr_conv_args), sizeof(sr_bn_apply_args),'
                     'sizeof(sr_head_args), sizeof(sr_eval_args), offsetof(sr_head_args, convergence_epsilon),'
                     'offsetof(sr_head_args, workspace_bytes), sizeof(sr_train_block_args), offsetof(sr_train_block_args, stats));'
+                    'printf("%zu %zu %zu\\n", sizeof(sr_eval_block), sizeof(sr_backbone_eval_args), offsetof(sr_backbone_eval_args, features));'
                     ' return 0;}\n')
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
@@ -60,6 +61,8 @@ def test_struct_layouts_match_c(tmp_path):
     assert out[5] == _lib.HeadArgs.convergence_epsilon.offset
     assert out[6] == _lib.HeadArgs.workspace_bytes.offset
     assert out[7] == ctypes.sizeof(_lib.TrainBlockArgs) and out[8] == _lib.TrainBlockArgs.stats.offset
+    assert out[9] == ctypes.sizeof(_lib.EvalBlock) and out[10] == ctypes.sizeof(_lib.BackboneEvalArgs)
+    assert out[11] == _lib.BackboneEvalArgs.features.offset
 
 
 def test_argument_validation_without_gpu(lib):
