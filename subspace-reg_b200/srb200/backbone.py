@@ -22,6 +22,7 @@ BN_MOMENTUM = 0.1
 
 
 _PINNED_POOL = {}
+_MASK_POOL = {}     # device copies of the keep-masks: (run thread, 'mask', block, forward parity) -> grow-only uint8 buffer
 _SCRATCH_POOL = {}
 
 
@@ -361,9 +362,19 @@ class BackboneEngine(object):
         # cudaMalloc, where the launching thread was seen to block for 100-300 ms.  The buffer's previous reader (the
         # sr_bn_apply of two forwards ago, on the run's stream) is fenced with an event before the copy overwrites it.
         dkey = ('mask', bi, self._cur_fwd & 1)
-        keep = ops.scratch(dkey, shape, torch.uint8, device)
+        pkey = (self._pool_owner,) + dkey
+        n_el = ent[0].numel()
+        buf = _MASK_POOL.get(pkey)
         last_read = self._mask_read.get(dkey)
         with torch.cuda.stream(cs):
+            if buf is None or buf.numel() < n_el:
+                # (allocated with the COPY stream current: the block then comes from that stream's pool, i.e. nothing still
+                # queued on the run's stream can be using its memory when the copy below overwrites it)
+                if buf is not None:
+                    buf.record_stream(main)        # its last reader runs on the run's stream
+                buf = torch.empty(1 << max(int(n_el - 1).bit_length(), 12), dtype=torch.uint8, device=device)
+                _MASK_POOL[pkey] = buf
+            keep = buf[:n_el].view(shape)
             if last_read is not None:
                 cs.wait_event(last_read)
             keep.copy_(ent[0], non_blocking=True)
