@@ -286,6 +286,11 @@ typedef struct sr_head_args {
     float* logits_support;    /* optional [n_support, n_classes]: logits of the LAST epoch (pre-update W)  */
     void* workspace;
     int64_t workspace_bytes;
+    int32_t cta_budget;       /* 0 = the fastest shape for a run that has the GPU to itself (82-98 CTAs at paper  */
+                              /*   sizes).  > 0: the paper-size kernel uses at most this many CTAs (fatter row /  */
+                              /*   column CTAs, ~10-20 % slower per epoch) so that the cooperative launches of      */
+                              /*   several runs sharing the GPU are resident together (3 runs: 148 / 3 = 49).       */
+    int32_t reserved0;
 } sr_head_args;
 
 int64_t sr_head_workspace_bytes(const sr_head_args* a);

@@ -25,7 +25,10 @@ namespace {
 using namespace srb;
 
 constexpr int kT = 256;
-constexpr int DC = 8;     // feature columns per column CTA (16 measured slower: the update and the tile arithmetic double)
+// feature columns per column CTA (template parameter DC): 8 by default (16 measured ~10 % slower per epoch: the update and
+// the tile arithmetic double); 16 when the caller caps the launch (sr_head_args.cta_budget) so that several runs' head
+// loops are co-resident on one GPU - a cooperative launch needs all its CTAs resident at once, and two 82-92-CTA launches do
+// not fit on 148 SMs, three 47-CTA launches do.
 constexpr int KC = 64;    // k-chunk of the W^T stream (phase 1) / n-chunk of the DL stream (phase 2): KC rows of CP floats
 constexpr int NS = 4;     // stages of the W^T / DL stream ring (one region, the two phases never overlap in a CTA).  Measured on
                           // B200: a runtime depth of 6-8 stages, 128-row chunks, 512 threads per CTA, 16 columns per column CTA,
@@ -124,7 +127,7 @@ __device__ void assemble_loss(const SmallParams& p, const HeadStart& st, int e, 
     __syncthreads();
 }
 
-template <int R, int CP>
+template <int R, int CP, int DC>
 __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) {
     extern __shared__ __align__(16) uint8_t dyn[];
     __shared__ double red[32];
@@ -562,12 +565,27 @@ __global__ void __launch_bounds__(kT, 1) head_small_kernel(const SmallParams p) 
 
 // Rows of X per row CTA: as few as keeps the grid within one wave (every row CTA streams all of W each epoch, so
 // fewer rows per CTA buy parallelism with L2 traffic).
-int pick_rows(int nt) {
+int pick_rows(int nt, int budget) {
     if (const char* e = getenv("SRB_HEAD_ROWS")) {   // A/B timing only
         const int v = atoi(e);
         if (v == 4 || v == 8 || v == 16) return v;
     }
-    return nt <= 384 ? 4 : (nt <= 768 ? 8 : 16);
+    int r = nt <= 384 ? 4 : (nt <= 768 ? 8 : 16);
+    if (budget > 0)
+        while (r < 16 && (nt + r - 1) / r + 2 > budget) r *= 2;
+    return r;
+}
+// Feature columns per column CTA: 8 unless the caller's CTA budget asks for fewer, fatter CTAs.
+int pick_cols(int d, int budget) {
+    int dc = 8;
+    if (budget > 0)
+        while (dc < 16 && d / dc + 2 > budget) dc *= 2;
+    return dc;
+}
+// SRB_HEAD_CTAS overrides sr_head_args.cta_budget (A/B timing).
+int cta_budget(const sr_head_args* a) {
+    if (const char* e = getenv("SRB_HEAD_CTAS")) return atoi(e);
+    return a->cta_budget;
 }
 
 struct SmallLayout {
@@ -593,19 +611,24 @@ SmallLayout small_layout(const sr_head_args* a, int GC) {
     return L;
 }
 
-template <int R, int CP>
+template <int R, int CP, int DC>
 int32_t launch_small(const SmallParams& p, size_t dyn, cudaStream_t stream) {
     static PerDeviceOnce once;
     once_per_device(once, [] {
-        cudaFuncSetAttribute(head_small_kernel<R, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaFuncSetAttribute(head_small_kernel<R, CP, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     });
     void* args[] = {const_cast<SmallParams*>(&p)};
-    SR_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(head_small_kernel<R, CP>), dim3(p.G), dim3(kT), args, dyn,
-                                           stream));
+    SR_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(head_small_kernel<R, CP, DC>), dim3(p.G), dim3(kT), args,
+                                           dyn, stream));
     return SR_OK;
 }
+template <int CP, int DC>
+int32_t launch_rows(const SmallParams& p, size_t dyn, cudaStream_t stream) {
+    if (p.R == 4) return launch_small<4, CP, DC>(p, dyn, stream);
+    return p.R == 8 ? launch_small<8, CP, DC>(p, dyn, stream) : launch_small<16, CP, DC>(p, dyn, stream);
+}
 
-size_t small_smem_bytes(const sr_head_args* a, int R, int CP, int ldn, bool pull_cta) {
+size_t small_smem_bytes(const sr_head_args* a, int R, int CP, int DC, int ldn, bool pull_cta) {
     const int C = a->n_classes, d = a->dim;
     const bool proj = a->pull_mode == SR_PULL_PROJECT && a->q_rows < d;
     const bool fixed = a->pull_mode == SR_PULL_FIXED;
@@ -626,27 +649,39 @@ namespace srb {
 bool head_small_applicable(const sr_head_args* a) {
     const int nt = a->n_support + a->n_memory;
     if (a->logits_support != nullptr) return false;
-    if (a->n_classes > 128 || a->dim % 64 != 0 || a->dim > 1024 || a->dim / DC > 146 || nt > 1024) return false;
+    if (a->n_classes > 128 || a->dim % 64 != 0 || a->dim > 1024 || nt > 1024) return false;
     if (a->pull_mode == SR_PULL_PROJECT && a->q_rows < a->dim && (a->q_rows > 256 || a->n_new > 16)) return false;
-    const int R = pick_rows(nt);
+    const int budget = cta_budget(a);
+    int R = pick_rows(nt, budget), DC = pick_cols(a->dim, budget);
     const int CP = a->n_classes <= 64 ? 64 : 128;
     const int ldn = (int)align_up(nt, KC);
-    if ((nt + R - 1) / R > 146) return false;
-    return small_smem_bytes(a, R, CP, ldn, true) <= 200 * 1024;
+    if (small_smem_bytes(a, R, CP, DC, ldn, true) > 200 * 1024) {   // the budget's shape does not fit: the default one decides
+        R = pick_rows(nt, 0);
+        DC = pick_cols(a->dim, 0);
+    }
+    if ((nt + R - 1) / R > 146 || a->dim / DC > 146) return false;
+    return small_smem_bytes(a, R, CP, DC, ldn, true) <= 200 * 1024;
 }
 
-int64_t head_small_workspace_bytes(const sr_head_args* a) { return small_layout(a, a->dim / DC).total; }
+// (sized for the widest grid: 8 columns per column CTA)
+int64_t head_small_workspace_bytes(const sr_head_args* a) { return small_layout(a, a->dim / 8).total; }
 
 int32_t head_small_run(const sr_head_args* a, cudaStream_t stream) {
     SmallParams p;
     p.a = *a;
     p.n_total = a->n_support + a->n_memory;
     p.ldn = (int)align_up(p.n_total, KC);
-    p.R = pick_rows(p.n_total);
+    p.CP = a->n_classes <= 64 ? 64 : 128;
+    const int budget = cta_budget(a);
+    p.R = pick_rows(p.n_total, budget);
+    int DC = pick_cols(a->dim, budget);
+    if (small_smem_bytes(a, p.R, p.CP, DC, p.ldn, true) > 200 * 1024) {   // as in head_small_applicable
+        p.R = pick_rows(p.n_total, 0);
+        DC = pick_cols(a->dim, 0);
+    }
     p.GA = (p.n_total + p.R - 1) / p.R;
     p.GC = a->dim / DC;
     p.G = std::max(p.GA, p.GC) + 2;   // + one CTA for the loss / stopping rule, one for the projection coefficients
-    p.CP = a->n_classes <= 64 ? 64 : 128;
     const SmallLayout L = small_layout(a, p.GC);
     if (a->workspace_bytes < L.total) return fail(SR_E_SMALLWS, "sr_head_run: workspace %lld < %lld",
                                                   (long long)a->workspace_bytes, (long long)L.total);
@@ -661,13 +696,11 @@ int32_t head_small_run(const sr_head_args* a, cudaStream_t stream) {
     p.pull_part = reinterpret_cast<double*>(ws + L.pull);
     p.u = reinterpret_cast<float*>(ws + L.u);
     SR_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)L.total, stream));   // control block, DL / W^T padding, partials
-    const size_t dyn = small_smem_bytes(a, p.R, p.CP, p.ldn, true);
+    const size_t dyn = small_smem_bytes(a, p.R, p.CP, DC, p.ldn, true);
     if (p.CP == 64) {
-        if (p.R == 4) return launch_small<4, 64>(p, dyn, stream);
-        return p.R == 8 ? launch_small<8, 64>(p, dyn, stream) : launch_small<16, 64>(p, dyn, stream);
+        return DC == 8 ? launch_rows<64, 8>(p, dyn, stream) : launch_rows<64, 16>(p, dyn, stream);
     }
-    if (p.R == 4) return launch_small<4, 128>(p, dyn, stream);
-    return p.R == 8 ? launch_small<8, 128>(p, dyn, stream) : launch_small<16, 128>(p, dyn, stream);
+    return DC == 8 ? launch_rows<128, 8>(p, dyn, stream) : launch_rows<128, 16>(p, dyn, stream);
 }
 
 }  // namespace srb

@@ -291,6 +291,8 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         b_row0 = q_row0 + n_query
 
         # ---- epochs 2.. on the device until the stopping rule fires (chained to epoch 1 on the device) ----
+        ops.align_runs()     # (several runs sharing this GPU start their head loops together; no-op for a run alone)
+        tp3h = _mark()
         head.run(max(opt.max_novel_epochs - 1, 1), feat=cache, support_row0=0, memory_row0=n_sup, defer=True)
         tp4 = _mark()
 
@@ -301,7 +303,7 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         scored = ops.eval_logits(cache[q_row0:b_row0 + base_x.shape[0]], net.classifier.weight.detach(), labels_all, confusion)
         confusion_run += confusion
         tp5 = _mark()
-        phase_events += [('train_pass', tp0, tp1), ('head1', tp1, tp2), ('cache', tp2, tp3), ('head', tp3, tp4),
+        phase_events += [('train_pass', tp0, tp1), ('head1', tp1, tp2), ('cache', tp2, tp3), ('head', tp3h, tp4),
                          ('score', tp4, tp5)]
 
         # ---- the session's one host synchronisation: epoch counts, loss trace, predictions ----

@@ -85,7 +85,7 @@ class HeadArgs(C.Structure):
         ("stable_count0", C.c_int32), ("min_novel_epochs", C.c_int32), ("max_novel_epochs", C.c_int32),
         ("convergence_epsilon", C.c_double), ("target_train_loss", C.c_double), ("prev_loss", C.c_float),
         ("loss_trace", C.c_void_p), ("status", C.c_void_p), ("resume_status", C.c_void_p), ("logits_support", C.c_void_p),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("cta_budget", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 

@@ -15,6 +15,7 @@ import threading
 import torch
 
 from . import host_rng
+from . import ops
 from . import rng
 
 
@@ -42,14 +43,54 @@ def prewarm_allocator(gigabytes, device=None):
     del x
 
 
+class Lockstep(object):
+    """Rendezvous of the n runs of one group (see ops.align_runs): align() returns once all n threads have called it, with
+    the calling thread's CUDA stream waiting for everything the other n - 1 streams had queued at that point.  A run that
+    fails or finishes early leaves the group with leave(); the others carry on unaligned."""
+
+    def __init__(self, n):
+        self.n = n
+        self.broken = n <= 1
+        self._events = [None] * n
+        self._barrier = threading.Barrier(n) if n > 1 else None
+
+    def align(self):
+        if self.broken:
+            return
+        slot = getattr(_slot, "i", None)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._events[slot] = ev
+        try:
+            self._barrier.wait(timeout=120.0)           # every run has recorded its event
+            mine = torch.cuda.current_stream()
+            for i, e in enumerate(self._events):
+                if i != slot and e is not None:
+                    mine.wait_event(e)
+            self._barrier.wait(timeout=120.0)           # every run has read the list (it is reused by the next align)
+        except threading.BrokenBarrierError:
+            self.broken = True
+
+    def leave(self):
+        self.broken = True
+        if self._barrier is not None:
+            self._barrier.abort()
+
+
+_slot = threading.local()
+
+
 class SeedPool(object):
     """K persistent worker threads, each with its own CUDA stream.  map(fn, items) runs fn(item) for every item, at most K
-    at a time, and returns the results in order; exceptions are re-raised in the caller."""
+    at a time, and returns the results in order; exceptions are re-raised in the caller.  With lockstep=True (default) the
+    items are run in groups of K whose session drivers rendezvous before every head loop (ops.align_runs)."""
 
-    def __init__(self, workers, device=None):
+    def __init__(self, workers, device=None, lockstep=True):
         self.workers = max(1, int(workers))
+        self.lockstep = bool(lockstep) and self.workers > 1
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         host_rng.replay_available()              # the generator self-check touches the global generator: do it here, once
+        ops.set_gpu_share(self.workers)           # head launches of the K runs must fit on the device together
         self._q = queue.Queue()
         self._threads = [threading.Thread(target=self._work, daemon=True) for _ in range(self.workers)]
         for t in self._threads:
@@ -62,13 +103,19 @@ class SeedPool(object):
             job = self._q.get()
             if job is None:
                 return
-            fn, item, out, idx, done = job
+            fn, item, out, idx, done, group, slot = job
+            _slot.i = slot
+            ops.bind_lockstep(group)
             try:
                 with torch.cuda.stream(stream), rng.scope():
                     out[idx] = (True, fn(item))
-                    stream.synchronize()
+                    ops.wait_stream_blocking()
             except BaseException as e:            # noqa: BLE001 - handed to the caller
                 out[idx] = (False, e)
+            finally:
+                ops.bind_lockstep(None)
+                if group is not None:
+                    group.leave()                 # a finished (or failed) run must not keep the others waiting
             done.release()
 
     def map(self, fn, items):
@@ -76,10 +123,19 @@ class SeedPool(object):
         out = [None] * len(items)
         done = threading.Semaphore(0)
         torch.cuda.current_stream().synchronize()     # inputs prepared on the caller's stream are complete
-        for i, it in enumerate(items):
-            self._q.put((fn, it, out, i, done))
-        for _ in items:
-            done.acquire()
+        if self.lockstep:
+            for g0 in range(0, len(items), self.workers):       # one group of <= K runs at a time
+                chunk = items[g0:g0 + self.workers]
+                group = Lockstep(len(chunk))
+                for j, it in enumerate(chunk):
+                    self._q.put((fn, it, out, g0 + j, done, group, j))
+                for _ in chunk:
+                    done.acquire()
+        else:
+            for i, it in enumerate(items):
+                self._q.put((fn, it, out, i, done, None, 0))
+            for _ in items:
+                done.acquire()
         res = []
         for ok, v in out:
             if not ok:
@@ -92,3 +148,4 @@ class SeedPool(object):
             self._q.put(None)
         for t in self._threads:
             t.join()
+        ops.set_gpu_share(1)

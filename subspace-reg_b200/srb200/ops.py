@@ -353,6 +353,51 @@ def subspace_factor(base_weight):
     return qt, info_h[0], bool(info_h[1])
 
 
+_GPU_SHARE = [1]
+
+
+def set_gpu_share(runs):
+    """Tell the ops how many independent runs share this process's GPU (srb200.concurrent.SeedPool does).  With more than
+    one, the paper-size head kernel is capped at SMs // runs CTAs (sr_head_args.cta_budget) so that the cooperative
+    launches of all runs are resident together instead of queueing behind one another."""
+    _GPU_SHARE[0] = max(1, int(runs))
+
+
+def head_cta_budget():
+    k = _GPU_SHARE[0]
+    if k <= 1:
+        return 0
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count // k
+
+
+_share_tls = threading.local()
+
+
+def bind_lockstep(ls):
+    """Bind (or clear, with None) the rendezvous object of the calling thread's run (srb200.concurrent.Lockstep)."""
+    _share_tls.lockstep = ls
+
+
+def align_runs():
+    """Called by the session driver right before it queues a head loop.  With several runs in flight on this GPU, wait
+    until every run of the group has reached the same point and make this run's stream wait for the others' queued work:
+    the K budgeted cooperative head launches then start together and are co-resident (3 x 47 CTAs), while the
+    convolution phases - persistent kernels that want all 148 SMs - never run beside a head loop.  Free-running groups lose
+    what the budget buys: a conv kernel next to ONE head loop runs its 148 CTAs in two waves on 101 SMs (measured: 365 ms
+    per sweep with 3 free-running sweeps in flight, the same as one sweep alone).  No-op for a run that is alone."""
+    ls = getattr(_share_tls, "lockstep", None)
+    if ls is not None:
+        ls.align()
+
+
+def wait_stream_blocking():
+    """Sleep (not spin) until everything queued on the current stream is done.  A plain .cpu() / synchronize() busy-waits on
+    the launching thread - one host core per run for most of a sweep, which the mask generator threads of 8 ranks need."""
+    ev = torch.cuda.Event(blocking=True)
+    ev.record()
+    ev.synchronize()
+
+
 class HeadSession(object):
     """Device state of one session's fine-tuning (weight, optimiser state, counters) around sr_head_run."""
 
@@ -360,7 +405,7 @@ class HeadSession(object):
                  memory_row0=0, labels_memory=None, base_weight=None, reserve_weight=None, pull_mode=L.SR_PULL_NONE,
                  pull=None, q_rows=0, lmbd_base=0.0, lmbd_novel=0.0, gamma=0.0, adam=False, lr=0.002, momentum=0.9,
                  weight_decay=5e-4, stable=True, convergence_epsilon=1e-4, stable_epochs=10, target_train_loss=0.0,
-                 min_novel_epochs=20, max_novel_epochs=1000, want_logits=False):
+                 min_novel_epochs=20, max_novel_epochs=1000, want_logits=False, cta_budget=None):
         dev = feat.device
         self.feat, self.weight = feat, weight
         self.labels_support, self.labels_memory = labels_support, labels_memory
@@ -389,6 +434,7 @@ class HeadSession(object):
         a.min_novel_epochs, a.max_novel_epochs = min_novel_epochs, max_novel_epochs
         a.convergence_epsilon, a.target_train_loss = convergence_epsilon, target_train_loss
         a.logits_support = _ptr(self.logits)
+        a.cta_budget = head_cta_budget() if cta_budget is None else int(cta_budget)
         ws_bytes = int(L.load().sr_head_workspace_bytes(C.byref(a)))
         self.workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         a.workspace, a.workspace_bytes = _ptr(self.workspace), ws_bytes
@@ -437,6 +483,7 @@ class HeadSession(object):
         """Read back every pending launch (the one host sync): -> concatenated trace of the epochs they ran."""
         if not self._pending:
             return torch.zeros((0, L.SR_TRACE_COLS), dtype=torch.float32)
+        wait_stream_blocking()
         sts = torch.stack([st for st, _ in self._pending]).cpu().tolist()
         out = []
         for st, (_, trace) in zip(sts, self._pending):
