@@ -152,6 +152,7 @@ typedef struct sr_bn_apply_args {
     float keep_scale;       /* multiplier for kept elements (1/(1-p) for dropout, numel/kept for DropBlock) */
     void* out;              /* bf16 NHWC [B,Ho,Wo,C], or fp32 [B,C] when pool == -1                      */
     void* out_lo;           /* optional: low plane of the bf16 output (error-compensated mode)           */
+    const float* keep_scale_dev; /* optional DEVICE scalar used instead of keep_scale (sr_dropblock_keep's output) */
 } sr_bn_apply_args;
 
 int32_t sr_bn_apply(const sr_bn_apply_args* a, void* stream);
@@ -367,6 +368,43 @@ int64_t sr_host_bernoulli(void* state_blob, int64_t blob_bytes, int32_t kind, do
  * bs x bs block anchored at a seed covers the pixel, 1 elsewhere (= 1 - padded mask).  Returns the number of ones in
  * `keep` (count_ones of :321), or -1 on bad arguments. */
 int64_t sr_host_dropblock(const uint8_t* seeds, int64_t planes, int32_t hs, int32_t ws, int32_t bs, uint8_t* keep);
+
+/* ------------------------------------------------------------------------------------------------
+ * Jump-ahead for PyTorch's CPU generator (mt19937): what lets the keep-masks be drawn ON THE DEVICE from the host
+ * generator's state (sr_device_bernoulli below) while the host generator is moved past them without drawing anything.
+ * table: n_polys polynomials of 624 uint32 (19937 coefficient bits each), entry w-1 = t^(w * SR_MT_JUMP_WORDS) mod the
+ * generator's characteristic polynomial; computed on the host (cached inside the library, ~4 ms per entry the first time).
+ * ---------------------------------------------------------------------------------------------- */
+#define SR_MT_JUMP_WORDS (1 << 19)
+int64_t sr_mt_jump_table_bytes(int32_t n_polys);
+int32_t sr_mt_jump_table(uint32_t* table_host, int32_t n_polys);
+/* state_blob (bytes of torch.get_rng_state(), HOST) is advanced by n_words 32-bit draws; the result is byte-identical to
+ * torch's own state after that many draws.  Needs n_polys >= n_words / SR_MT_JUMP_WORDS table entries (HOST pointer). */
+int32_t sr_host_mt_advance(void* state_blob, int64_t blob_bytes, int64_t n_words, const uint32_t* table_host,
+                           int32_t n_polys);
+
+/* Device replay of the generator's Bernoulli stream: the keep-masks of one train-mode forward (resnet_language.py:292-299,
+ * 311-325) drawn on the GPU, bit-identical to what torch's CPU generator would produce from `state_blob`, in region
+ * order.  kind 0: tensor.bernoulli_(double p), two words per element; kind 1: torch.bernoulli(float32 p tensor), one word;
+ * kind 2: n words skipped.  out: DEVICE uint8[n] (1 = drawn one), NCHW order = draw order.  Every region but the last must
+ * use an even number of words.  state_blob (HOST) is advanced in place past all regions, like sr_host_bernoulli does.
+ * table_dev / table_host: the same sr_mt_jump_table on the device and on the host, n_polys >= total words / SR_MT_JUMP_WORDS. */
+typedef struct sr_mask_region {
+    int32_t kind;
+    int32_t reserved;
+    double p;
+    int64_t n;
+    uint8_t* out;
+} sr_mask_region;
+int64_t sr_device_bernoulli_workspace_bytes(int64_t total_words);
+int32_t sr_device_bernoulli(void* state_blob, int64_t blob_bytes, const sr_mask_region* regions, int32_t n_regions,
+                            const uint32_t* table_dev, const uint32_t* table_host, int32_t n_polys, void* workspace,
+                            int64_t workspace_bytes, void* stream);
+/* DropBlock._compute_block_mask (resnet_language.py:327-352) + the numel / kept scale (:321-323) on the device.
+ * seeds: DEVICE uint8 [planes, hs, ws]; keep: DEVICE uint8 [planes, hs+bs-1, ws+bs-1]; scale_out: DEVICE, 16 bytes, 16-byte
+ * aligned: [0] = fp32(numel) / fp32(kept) as the reference computes it (the rest is scratch). */
+int32_t sr_dropblock_keep(const uint8_t* seeds, int64_t planes, int32_t hs, int32_t ws, int32_t bs, uint8_t* keep,
+                          float* scale_out, void* stream);
 
 #ifdef __cplusplus
 }

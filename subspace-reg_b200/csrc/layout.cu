@@ -227,10 +227,11 @@ __global__ void bn_apply_kernel(const BnApplyParams p) {
         bn_pixel(a, pix, c0, al, be, ral, rbe, y);
     }
     if (a.keep) {
+        const float ks = a.keep_scale_dev ? __ldg(a.keep_scale_dev) : a.keep_scale;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const uint8_t k = a.keep[(((int64_t)n * a.channels + c0 + j) * p.Ho + ho) * p.Wo + wo];
-            y[j] = k ? y[j] * a.keep_scale : 0.f;
+            y[j] = k ? y[j] * ks : 0.f;
         }
     }
     const int64_t o_off = (((int64_t)n * p.Ho + ho) * p.Wo + wo) * a.channels + c0;
@@ -253,6 +254,7 @@ __global__ void bn_apply_avg_kernel(const BnApplyParams p) {
     if (a.res_raw) bn_coeffs(a.res_mean, a.res_invstd, a.res_gamma, a.res_beta, c0, ral, rbe);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const int HW = a.height * a.width;
+    const float ks = (a.keep && a.keep_scale_dev) ? __ldg(a.keep_scale_dev) : a.keep_scale;
     for (int q = 0; q < HW; ++q) {
         float y[8];
         bn_pixel(a, (int64_t)n * HW + q, c0, al, be, ral, rbe, y);
@@ -260,7 +262,7 @@ __global__ void bn_apply_avg_kernel(const BnApplyParams p) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const uint8_t k = a.keep[((int64_t)n * a.channels + c0 + j) * HW + q];
-                y[j] = k ? y[j] * a.keep_scale : 0.f;
+                y[j] = k ? y[j] * ks : 0.f;
             }
         }
 #pragma unroll

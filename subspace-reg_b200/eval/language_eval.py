@@ -143,8 +143,21 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         iter_num = getattr(opt, 'n_sessions_override', 8)   # 8 sessions for miniImageNet (reference literal)
         basec_map = ckpt['training_classes']
 
+    # A session's accuracy bookkeeping is finished one session late (finish_session below), while the device is busy with
+    # the next session; whatever the next session prints before that point is held back so that the log keeps the
+    # reference's order.
+    pending_finish = None
+    held_prints = []
+
+    def say(*args):
+        line = " ".join(str(a) for a in args) + "\n"
+        if pending_finish is not None:
+            held_prints.append(line)
+        else:
+            sys.stdout.write(line)
+
     for idx in range(iter_num):
-        print("\n**** Iteration {}/{} ****\n".format(idx + 1, opt.neval_episodes))
+        say("\n**** Iteration {}/{} ****\n".format(idx + 1, opt.neval_episodes))
         support_xs, support_ys, query_xs, query_ys = drop_a_dim(next(meta_valloader_it))
         if base_support_loader is not None:
             # (concatenating on the host would turn pinned loader tensors into a pageable one: a host memcpy plus a
@@ -155,8 +168,8 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
             prev_vocab_base = vocab_base
             prev_vocab_novel = vocab_novel
         vocab_base, vocab_all, vocab_novel, orig2id = get_vocabs(base_val_loader, meta_valloader, query_ys)
-        print("Vocab base: ", vocab_base)
-        print("Vocab novel: ", vocab_novel)
+        say("Vocab base: ", vocab_base)
+        say("Vocab novel: ", vocab_novel)
         if idx == 0:
             orig_base_num = len(vocab_base)
         if idx > 0:
@@ -165,14 +178,14 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         # Previous sessions' novel weights as they were when their session ended (reglossnovel anchors).
         if idx == 1:
             novel_weight_to_reserve = net.classifier.weight.clone().detach()[-opt.n_ways:, :].requires_grad_(False)
-            print(f"Novel weight to reserve is of shape {novel_weight_to_reserve.shape} at session {idx+1}.")
+            say(f"Novel weight to reserve is of shape {novel_weight_to_reserve.shape} at session {idx+1}.")
         if idx > 1:
             new_novel_set = net.classifier.weight.clone().detach()[-opt.n_ways:, :].requires_grad_(False)
             novel_weight_to_reserve = torch.cat((novel_weight_to_reserve, new_novel_set), 0)
-            print(f"Novel weight to reserve is of shape {novel_weight_to_reserve.shape} at session {idx+1}.")
+            say(f"Novel weight to reserve is of shape {novel_weight_to_reserve.shape} at session {idx+1}.")
 
         novel_labels = np.sort(np.unique(query_ys))
-        print("Novel labels: ", novel_labels)
+        say("Novel labels: ", novel_labels)
         for k, v in orig2id.items():
             orig2id[k] = v + idx * opt.n_ways
         query_ys_id = torch.LongTensor([orig2id[y] for y in query_ys])
@@ -280,43 +293,59 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         net.eval()                                  # validate()'s side effect after epoch 1
         tp2 = _mark()
 
-        # ---- eval-mode feature cache: support | memory | queries of sessions 1..idx+1 | base batch ----
-        parts = [support_xs_d] + ([memory.data] if has_mem else []) + novel_query_collection + [base_x]
+        # ---- eval-mode feature cache, part A: the rows the head trains on (support | memory) ----
         with torch.no_grad():
-            cache = net.engine().eval_features(torch.cat(parts, 0))
+            cache = net.engine().eval_features(torch.cat([support_xs_d] + ([memory.data] if has_mem else []), 0))
         tm['backbone_imgs'] += cache.shape[0]
         tp3 = _mark()
-        q_row0 = n_sup + n_mem
-        n_query = sum(q.shape[0] for q in novel_query_collection)
-        b_row0 = q_row0 + n_query
 
         # ---- epochs 2.. on the device until the stopping rule fires (chained to epoch 1 on the device) ----
         ops.align_runs()     # (several runs sharing this GPU start their head loops together; no-op for a run alone)
         tp3h = _mark()
         head.run(max(opt.max_novel_epochs - 1, 1), feat=cache, support_row0=0, memory_row0=n_sup, defer=True)
+        head.post()          # status / trace copies are queued HERE: the host reads them while part B below still runs
         tp4 = _mark()
 
-        # ---- scoring of the last epoch: validate (:321-326) + eval_base (:362-367) on cached features, ONE launch over
-        # the queries of every session so far and the base batch (contiguous rows of the cache) ----
+        # ---- part B, queued behind the head loop: features of the queries of every session so far | base batch, and the
+        # scoring of the last epoch - validate (:321-326) + eval_base (:362-367) - in ONE launch over those rows.  Nothing
+        # of the next session's set-up depends on it, so it is not waited for here: the host reads the epoch count as soon
+        # as the head loop ends and prepares session idx+2 while the device works through part B (finish_session below).
+        n_query = sum(q.shape[0] for q in novel_query_collection)
+        with torch.no_grad():
+            cache_q = net.engine().eval_features(torch.cat(novel_query_collection + [base_x], 0))
+        tm['backbone_imgs'] += cache_q.shape[0]
+        tp4b = _mark()
         labels_all = torch.cat(novel_query_collection_id + [base_y])
         confusion = torch.zeros((100, 100), dtype=torch.int64, device=dev)   # (gold id, predicted id) of this session
-        scored = ops.eval_logits(cache[q_row0:b_row0 + base_x.shape[0]], net.classifier.weight.detach(), labels_all, confusion)
+        scored = ops.eval_logits(cache_q, net.classifier.weight.detach(), labels_all, confusion)
         confusion_run += confusion
         tp5 = _mark()
         phase_events += [('train_pass', tp0, tp1), ('head1', tp1, tp2), ('cache', tp2, tp3), ('head', tp3h, tp4),
-                         ('score', tp4, tp5)]
+                         ('cache', tp4, tp4b), ('score', tp4b, tp5)]
 
-        # ---- the session's one host synchronisation: epoch counts, loss trace, predictions ----
+        # the previous session's scores have long been computed: finish its bookkeeping (and its prints, in the reference's
+        # order) before this session's own results are read
+        if pending_finish is not None:
+            pending_finish()
+            pending_finish = None
+            sys.stdout.write("".join(held_prints))
+            held_prints.clear()
+
+        # ---- the session's one wait: for the head loop (epoch counts, loss trace) ----
         head.collect()
+        rescored = False
         while not head.stopped:                     # (only if the chained launch ran out of epochs before the rule fired)
             head.run(max(opt.max_novel_epochs - head.epochs, 1))
-            scored = None
-        if scored is None:
+            rescored = True
+        if rescored:
             confusion_run -= confusion
             confusion.zero_()
-            scored = ops.eval_logits(cache[q_row0:b_row0 + base_x.shape[0]], net.classifier.weight.detach(), labels_all, confusion)
+            scored = ops.eval_logits(cache_q, net.classifier.weight.detach(), labels_all, confusion)
             confusion_run += confusion
-        pred_all = scored["pred"].cpu().numpy().astype(np.int64)
+        pred_host = torch.empty(scored["pred"].shape, dtype=torch.int32, pin_memory=True)
+        pred_host.copy_(scored["pred"], non_blocking=True)
+        scored_ev = torch.cuda.Event(blocking=True)
+        scored_ev.record()
         trace = torch.cat(head.traces, 0).numpy()
         epoch = head.epochs + 1
         tm['train_s'] += time.perf_counter() - t_train0
@@ -340,21 +369,7 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
         done = next(iter(net.block_counters().values())) - counters0
         net.advance_block_counters(n_calls - done)
 
-        test_acc, query_ys_pred, query_logits = [], [], []
-        r0 = 0
-        for qx, qy_h in zip(novel_query_collection, query_ids_host):
-            nq = qx.shape[0]
-            pred = pred_all[r0:r0 + nq]
-            test_acc.append(percent(int((pred == qy_h).sum()), nq)[0])
-            query_ys_pred.append(pred)
-            query_logits.append(scored["logits"][r0:r0 + nq])
-            r0 += nq
-        base_pred = pred_all[r0:r0 + base_x.shape[0]]
-        acc_base_ = np.mean([percent(int((base_pred == base_y_host).sum()), base_x.shape[0])[0].item()])
-        record['confusion_last'] = confusion
-        record['confusion'] = confusion_run
-        tm['images_scored'] += n_query + base_x.shape[0]
-
+        inds = None
         if opt.memory_replay:
             inds = rng.np_random().choice(opt.n_shots, opt.memory_replay)
             margin = 5 * np.arange(5)
@@ -364,33 +379,61 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
             inds_d = torch.from_numpy(inds).to(dev)
             memory.additems(support_xs_d[inds_d, :], support_ys_d[inds_d])
 
-        test_acc = [round(i.item(), 2) for i in test_acc]
-        print("Novel session accuracies: ", test_acc)
-        novel_session_acc = list(test_acc)
-        test_acc = np.array(test_acc).mean()
+        def finish_session(scored=scored, scored_ev=scored_ev, pred_host=pred_host, n_queries=[q.shape[0] for q in
+                           novel_query_collection], query_ids=list(query_ids_host), confusion=confusion, trace=trace,
+                           epoch=epoch, epochs=head.epochs, novel_labels=novel_labels, vocab_base=list(vocab_base),
+                           vocab_novel=list(vocab_novel), inds=inds, n_query=n_query, cache=cache, f_train=f_train,
+                           W_snap=None if getattr(opt, 'light_record', False) else net.classifier.weight.detach().clone(),
+                           bn_snap=None if getattr(opt, 'light_record', False) else {
+                               k: v.detach().clone() for k, v in net.state_dict().items()
+                               if 'running_' in k or 'num_batches_tracked' in k}):
+            """Accuracy bookkeeping of a session once its scores are on the host (language_eval.py:321-404)."""
+            scored_ev.synchronize()
+            pred_all = pred_host.numpy().astype(np.int64)
+            test_acc, query_ys_pred, query_logits = [], [], []
+            r0 = 0
+            for nq, qy_h in zip(n_queries, query_ids):
+                pred = pred_all[r0:r0 + nq]
+                test_acc.append(percent(int((pred == qy_h).sum()), nq)[0])
+                query_ys_pred.append(pred)
+                query_logits.append(scored["logits"][r0:r0 + nq])
+                r0 += nq
+            base_pred = pred_all[r0:r0 + base_x.shape[0]]
+            acc_base_ = np.mean([percent(int((base_pred == base_y_host).sum()), base_x.shape[0])[0].item()])
+            record['confusion_last'] = confusion
+            record['confusion'] = confusion_run
+            tm['images_scored'] += n_query + base_x.shape[0]
 
-        acc_base.update(acc_base_)
-        acc_novel.update(test_acc)
-        w1 = 60 if opt.dataset == "miniImageNet" else 200
-        w2 = len(vocab_base) + len(vocab_novel) - 60
-        weighted_avg = (w1 * acc_base_ + w2 * test_acc) / (w1 + w2)
-        weighted_avg_l.append(round(weighted_avg, 2))
-        acc_novel_list.append(round(test_acc, 2))
-        acc_base_list.append(round(acc_base_, 2))
-        print(f"***Running weighted avg: {weighted_avg}")
-        log_episode(novel_labels, vocab_novel, epoch, test_acc, acc_base_, acc_base.avg, acc_novel.avg)
+            test_acc = [round(i.item(), 2) for i in test_acc]
+            print("Novel session accuracies: ", test_acc)
+            novel_session_acc = list(test_acc)
+            test_acc = np.array(test_acc).mean()
 
-        sess = dict(
-            epochs=head.epochs, terms=trace.astype(np.float64),
-            novel_session_acc=novel_session_acc, query_pred=[torch.from_numpy(p) for p in query_ys_pred],
-            query_logits=query_logits, base_pred=torch.from_numpy(base_pred), acc_base=float(acc_base_),
-            memory_inds=inds.copy() if opt.memory_replay else None, vocab_novel=list(vocab_novel))
-        if not getattr(opt, 'light_record', False):   # snapshots for the parity tests (~100 small device copies per session)
-            sess.update(W=net.classifier.weight.detach().clone(), probe_feat=cache[:8].clone(), train_feat=f_train[:8].clone(),
-                        bn={k: v.detach().clone() for k, v in net.state_dict().items()
-                            if 'running_' in k or 'num_batches_tracked' in k})
-        record['sessions'].append(sess)
+            acc_base.update(acc_base_)
+            acc_novel.update(test_acc)
+            w1 = 60 if opt.dataset == "miniImageNet" else 200
+            w2 = len(vocab_base) + len(vocab_novel) - 60
+            weighted_avg = (w1 * acc_base_ + w2 * test_acc) / (w1 + w2)
+            weighted_avg_l.append(round(weighted_avg, 2))
+            acc_novel_list.append(round(test_acc, 2))
+            acc_base_list.append(round(acc_base_, 2))
+            print(f"***Running weighted avg: {weighted_avg}")
+            log_episode(novel_labels, vocab_novel, epoch, test_acc, acc_base_, acc_base.avg, acc_novel.avg)
 
+            sess = dict(
+                epochs=epochs, terms=trace.astype(np.float64),
+                novel_session_acc=novel_session_acc, query_pred=[torch.from_numpy(p) for p in query_ys_pred],
+                query_logits=query_logits, base_pred=torch.from_numpy(base_pred), acc_base=float(acc_base_),
+                memory_inds=inds.copy() if inds is not None else None, vocab_novel=list(vocab_novel))
+            if W_snap is not None:   # snapshots for the parity tests (~100 small device copies per session)
+                sess.update(W=W_snap, probe_feat=cache[:8].clone(), train_feat=f_train[:8].clone(), bn=bn_snap)
+            record['sessions'].append(sess)
+
+        pending_finish = finish_session
+
+    if pending_finish is not None:
+        pending_finish()
+        sys.stdout.write("".join(held_prints))
     torch.cuda.current_stream().synchronize()
     for name, e0, e1 in phase_events:
         ph[name] += e0.elapsed_time(e1) * 1e-3

@@ -19,6 +19,8 @@ EXPORTS = [
     "sr_bn_finalize", "sr_bn_apply", "sr_subspace_factor_workspace_bytes", "sr_subspace_factor",
     "sr_head_workspace_bytes", "sr_head_run", "sr_eval_logits", "sr_semantic_pullers", "sr_linear_fwd",
     "sr_linear_bwd", "sr_sqdist", "sr_diff_scale", "sr_project_rows", "sr_score_logits", "sr_host_bernoulli", "sr_host_dropblock", "sr_conv_plan", "sr_pack_input_u8", "sr_global_avg", "sr_mse_grad", "sr_sgd_update", "sr_eval_workspace_bytes", "sr_train_block", "sr_backbone_eval_workspace_bytes", "sr_backbone_eval",
+    "sr_mt_jump_table_bytes", "sr_mt_jump_table", "sr_host_mt_advance", "sr_device_bernoulli_workspace_bytes",
+    "sr_device_bernoulli", "sr_dropblock_keep",
 ]
 
 
@@ -44,8 +46,12 @@ class BnApplyArgs(C.Structure):
         ("res_raw", C.c_void_p), ("res_mean", C.c_void_p), ("res_invstd", C.c_void_p), ("res_gamma", C.c_void_p),
         ("res_beta", C.c_void_p), ("res_act", C.c_void_p), ("res_act_lo", C.c_void_p), ("lrelu", C.c_int32),
         ("slope", C.c_float), ("pool", C.c_int32), ("keep", C.c_void_p), ("keep_scale", C.c_float), ("out", C.c_void_p),
-        ("out_lo", C.c_void_p),
+        ("out_lo", C.c_void_p), ("keep_scale_dev", C.c_void_p),
     ]
+
+
+class MaskRegion(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("p", C.c_double), ("n", C.c_int64), ("out", C.c_void_p)]
 
 
 class TrainBlockArgs(C.Structure):
@@ -161,6 +167,18 @@ def load():
     lib.sr_conv_plan.argtypes = [C.POINTER(ConvArgs), C.POINTER(C.c_int32)]
     lib.sr_host_dropblock.restype = i64
     lib.sr_host_dropblock.argtypes = [vp, i64, i32, i32, i32, vp]
+    lib.sr_mt_jump_table_bytes.restype = i64
+    lib.sr_mt_jump_table_bytes.argtypes = [i32]
+    lib.sr_mt_jump_table.restype = i32
+    lib.sr_mt_jump_table.argtypes = [vp, i32]
+    lib.sr_host_mt_advance.restype = i32
+    lib.sr_host_mt_advance.argtypes = [vp, i64, i64, vp, i32]
+    lib.sr_device_bernoulli_workspace_bytes.restype = i64
+    lib.sr_device_bernoulli_workspace_bytes.argtypes = [i64]
+    lib.sr_device_bernoulli.restype = i32
+    lib.sr_device_bernoulli.argtypes = [vp, i64, C.POINTER(MaskRegion), i32, vp, vp, i32, vp, i64, vp]
+    lib.sr_dropblock_keep.restype = i32
+    lib.sr_dropblock_keep.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp]
     lib.sr_score_logits.restype = i32
     lib.sr_score_logits.argtypes = [C.POINTER(EvalArgs), vp]
     lib.sr_semantic_pullers.restype = i32

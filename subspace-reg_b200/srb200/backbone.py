@@ -12,6 +12,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib as L
+from . import device_rng
 from . import host_rng
 from . import rng
 from . import ops
@@ -56,6 +57,9 @@ class BackboneEngine(object):
         self._pool_owner = threading.get_ident()   # staging buffers are pooled per run thread (helper threads use the owner's)
         self._mask_read = {}      # device mask buffer -> event after its last reader on the run's stream
         self._mask_pending = None
+        self._dev_masks = None    # this forward's keep-masks when they are drawn on the device: block -> (keep, scale tensor | float)
+        self._dev_fwd_done = {}   # forward parity -> event after that forward's last mask reader (buffer reuse fence)
+        self._dev_ws = None       # workspace of sr_device_bernoulli (only ever used on the mask stream)
 
     # ---------------------------------------------------------------- weight packing
     def _bn_key(self):
@@ -189,11 +193,88 @@ class BackboneEngine(object):
         return h
 
     # ---------------------------------------------------------------- train-mode pass (epoch 1 of a session)
+    def device_masks(self, device=None):
+        """True if this engine draws its keep-masks on the GPU (srb200.device_rng; SRB_MASKS=host or a failed self-check
+        select the host generator threads below instead)."""
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        return device_rng.available(device)
+
+    def _draw_masks_on_device(self, B, size, counters, device):
+        """All keep-masks of one train-mode forward, drawn on the device in forward order from the CPU generator's current
+        state (which is moved past them): block index -> (keep uint8 NCHW, scale).  Runs on a side stream, so the ~0.3 ms of
+        generator kernels overlap the first block's convolutions; returns None if a region layout is not supported."""
+        plan = []
+        for bi, b in enumerate(self.blocks):
+            size = size // b['pool']
+            dr = b.get('drop_rate', 0.1)
+            if not dr > 0:
+                continue
+            shape = (B, b['cout'], size, size)
+            if b['drop_block']:
+                bs = b['block_size']
+                gamma = self._dropblock_gamma(counters[b['prefix']], bs, size, dr)
+                plan.append((bi, 1, gamma, (B, b['cout'], size - (bs - 1), size - (bs - 1)), shape, bs))
+            else:
+                plan.append((bi, 0, 1 - dr, shape, shape, 0))
+        for k, (bi, kind, p, dshape, shape, bs) in enumerate(plan[:-1]):
+            n = 1
+            for d_ in dshape:
+                n *= d_
+            if device_rng.region_words(kind, n) & 1:
+                return None
+        main = torch.cuda.current_stream()
+        cs = getattr(self, '_copy_stream', None)
+        if cs is None:
+            cs = self._copy_stream = torch.cuda.Stream(device=device)
+        par = self._cur_fwd & 1
+        out = {}
+        with torch.cuda.stream(cs):
+            prev = self._dev_fwd_done.get(par)
+            if prev is not None:
+                cs.wait_event(prev)            # the readers of these buffers two forwards ago
+            regions = []
+            post = []
+            for bi, kind, p, dshape, shape, bs in plan:
+                keep = self._dev_buf(('keep', bi, par), shape, device)
+                if kind == 0:
+                    regions.append((0, p, keep))
+                    out[bi] = (keep, float(torch.ones(1).div_(p)))      # noise.div_(1 - drop_rate)
+                else:
+                    seeds = self._dev_buf(('seeds', bi, par), dshape, device)
+                    scale = self._dev_buf(('scale', bi, par), (16,), device).view(torch.float32)
+                    regions.append((1, p, seeds))
+                    post.append((seeds, bs, keep, scale))
+                    out[bi] = (keep, scale)
+            self._dev_ws = device_rng.draw(regions, self._dev_ws)
+            for seeds, bs, keep, scale in post:
+                device_rng.dropblock_keep(seeds, bs, keep, scale)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        ops.LAUNCHES.add(3 + 3 * len(post))
+        self._dev_ready = ev
+        return out
+
+    def _dev_buf(self, key, shape, device):
+        """Grow-only device uint8 buffer per (run thread, key), allocated on the mask stream's pool."""
+        n = 1
+        for d_ in shape:
+            n *= int(d_)
+        pkey = (self._pool_owner, 'dev') + tuple(key)
+        buf = _MASK_POOL.get(pkey)
+        if buf is None or buf.numel() < n:
+            # (the old block returns to the mask stream's pool; that stream has already waited for its last readers)
+            buf = torch.empty(1 << max(int(n - 1).bit_length(), 12), dtype=torch.uint8, device=device)
+            _MASK_POOL[pkey] = buf
+        return buf[:n].view(shape)
+
     def start_mask_prefetch(self, forwards):
         """Begin drawing, on a host thread, the dropout masks of the next len(forwards) train-mode forwards.
         forwards: [(skip_words_before, batch), ...] in the order they will run; `skip_words_before` generator draws are
         assumed to happen before that forward (the session's nn.Linear init).  DropBlock draws are skipped over (their
         gamma is not known yet) and made later from the live generator.  May cover every remaining session of a run."""
+        if self.device_masks():
+            return
         steps = []
         for f, (skip, batch) in enumerate(forwards):
             if skip:
@@ -225,6 +306,8 @@ class BackboneEngine(object):
         prefetch thread keeps the generator state in front of every DropBlock region ('hold'), and from that state the
         seeds can be drawn off the live generator as soon as gamma is known - while the main thread is busy launching the
         first blocks.  Consumed (and verified against the live generator) in draw_mask."""
+        if self.device_masks():
+            return
         t = getattr(self, '_db_thread', None)
         if t is not None:
             t.join()
@@ -287,7 +370,7 @@ class BackboneEngine(object):
         return ent, kept
 
     def mask_prefetch_alive(self):
-        return self._prefetch is not None and self._prefetch.alive()
+        return self.device_masks() or (self._prefetch is not None and self._prefetch.alive())
 
     def _scratch(self, key, shape):
         """Reusable pageable uint8 host buffer (process-wide pool, power-of-two capacity)."""
@@ -327,6 +410,11 @@ class BackboneEngine(object):
         drop_rate = b.get('drop_rate', 0.1)
         if not drop_rate > 0:                                                  # `if self.drop_rate > 0` (:292): no draw at all
             return None, 1.0
+        if self._dev_masks is not None:                                        # drawn on the device at the top of the forward
+            if self._dev_ready is not None:
+                torch.cuda.current_stream().wait_event(self._dev_ready)
+                self._dev_ready = None
+            return self._dev_masks[bi]
         if not b['drop_block']:
             scale = float(torch.ones(1).div_(1 - drop_rate))                   # noise.div_(1 - p)
             got = self._prefetch.take((self._cur_fwd, bi), shape) if self._prefetch is not None else None
@@ -394,6 +482,7 @@ class BackboneEngine(object):
         size = x.shape[2] if x.dtype != torch.uint8 else x.shape[1]
         self._cur_fwd = self._pf_fwd
         self._pf_fwd += 1
+        self._dev_masks = self._draw_masks_on_device(B, size, counters, dev) if self.device_masks(dev) else None
         h = self.pack(x)
         nb = len(self.blocks)
 
@@ -436,6 +525,11 @@ class BackboneEngine(object):
                 ev.record()
                 self._mask_read[self._mask_pending] = ev
                 self._mask_pending = None
+        if self._dev_masks is not None:             # fence for the mask buffers of this parity (rewritten two forwards on)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._dev_fwd_done[self._cur_fwd & 1] = ev
+            self._dev_masks = None
         torch._foreach_add_(bumped, 1)   # BatchNorm2d.num_batches_tracked of every BN that ran
         self.invalidate()   # running statistics moved: the folded weights are stale
         if h.dim() >= 4:    # resnet12: the last block is pooled 2x2, the global average follows

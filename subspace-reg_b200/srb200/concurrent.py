@@ -14,6 +14,7 @@ import threading
 
 import torch
 
+from . import device_rng
 from . import host_rng
 from . import ops
 from . import rng
@@ -89,7 +90,8 @@ class SeedPool(object):
         self.workers = max(1, int(workers))
         self.lockstep = bool(lockstep) and self.workers > 1
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
-        host_rng.replay_available()              # the generator self-check touches the global generator: do it here, once
+        host_rng.replay_available()              # the generator self-checks touch the global generator: do them here, once
+        device_rng.available(self.device)
         ops.set_gpu_share(self.workers)           # head launches of the K runs must fit on the device together
         self._q = queue.Queue()
         self._threads = [threading.Thread(target=self._work, daemon=True) for _ in range(self.workers)]

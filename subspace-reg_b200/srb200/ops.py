@@ -216,7 +216,11 @@ def bn_apply(raw, mean, invstd, gamma, beta, res_raw=None, res_bn=None, res_act=
     a.slope = slope
     a.pool = pool
     a.keep = _ptr(keep, torch.uint8, "keep")
-    a.keep_scale = keep_scale
+    if torch.is_tensor(keep_scale):          # device scalar (DropBlock's numel / kept from sr_dropblock_keep)
+        a.keep_scale = 1.0
+        a.keep_scale_dev = _ptr(keep_scale, torch.float32, "keep_scale")
+    else:
+        a.keep_scale = keep_scale
     if pool == -1:
         out = torch.empty((B, Cc), dtype=torch.float32, device=raw.device)
     elif pool == 2:
@@ -413,6 +417,7 @@ class HeadSession(object):
         Cn, d = weight.shape
         self.opt_state = torch.zeros((2 if adam else 1, Cn, d), dtype=torch.float32, device=dev)
         self._pending = []       # [(status, trace)] of launches whose results have not been read back yet
+        self._posted = None      # (pinned status, pinned traces, event, #launches) queued by post()
         self.logits = torch.empty((n_support, Cn), dtype=torch.float32, device=dev) if want_logits else None
         a = L.HeadArgs()
         a.feat, a.dim = _ptr(feat, torch.float32, "feat"), d
@@ -479,14 +484,43 @@ class HeadSession(object):
             return None
         return self.collect()
 
+    def post(self):
+        """Queue the device->host copies of every pending launch's status / trace NOW (pinned buffers, one event), so that
+        collect() waits for the head loop only - not for whatever the caller queues on the stream after this point (the
+        session driver queues the query cache build and the scoring behind the head loop and reads the epoch count while
+        they run)."""
+        if not self._pending or self._posted is not None:
+            return
+        sts = torch.stack([st for st, _ in self._pending])
+        sts_h = torch.empty(sts.shape, dtype=sts.dtype, pin_memory=True)
+        sts_h.copy_(sts, non_blocking=True)
+        traces_h = []
+        for _, trace in self._pending:
+            th = torch.empty(trace.shape, dtype=trace.dtype, pin_memory=True)
+            th.copy_(trace, non_blocking=True)
+            traces_h.append(th)
+        ev = torch.cuda.Event(blocking=True)
+        ev.record()
+        self._posted = (sts_h, traces_h, ev, len(self._pending))
+
     def collect(self):
         """Read back every pending launch (the one host sync): -> concatenated trace of the epochs they ran."""
         if not self._pending:
             return torch.zeros((0, L.SR_TRACE_COLS), dtype=torch.float32)
-        wait_stream_blocking()
-        sts = torch.stack([st for st, _ in self._pending]).cpu().tolist()
+        if self._posted is not None and self._posted[3] != len(self._pending):
+            self._posted = None                      # launches were queued after post(): read everything the plain way
+        if self._posted is not None:
+            sts_h, traces_h, ev, _ = self._posted
+            ev.synchronize()
+            sts = sts_h.tolist()
+            traces = traces_h
+        else:
+            wait_stream_blocking()
+            sts = torch.stack([st for st, _ in self._pending]).cpu().tolist()
+            traces = [trace for _, trace in self._pending]
+        self._posted = None
         out = []
-        for st, (_, trace) in zip(sts, self._pending):
+        for st, trace in zip(sts, traces):
             if st[3] != 0:
                 raise RuntimeError("srb200: head kernel reported a grid-barrier timeout")
             n = st[0]
@@ -494,7 +528,7 @@ class HeadSession(object):
             self.stopped = bool(st[1])
             self.stable_count = st[2]
             if n > 0:
-                tr = trace[:n].cpu()
+                tr = trace[:n].cpu().clone() if trace.is_cuda else trace[:n].clone()
                 self.prev_loss = float(tr[-1, 0])
                 self.traces.append(tr)
                 out.append(tr)
