@@ -354,16 +354,13 @@ def main():
         return synthetic.make_world(seed, n_sessions=args.sessions, n_base_batch=args.base_batch, word_embed_path=wdir,
                                     conv_precision=args.precision)
 
-    # sweeps in flight per GPU: each needs a host thread for its launches plus the mask threads, so the number follows the
-    # host cores this rank can use (SRB_RNG_THREADS is set by dist.init from the node's core count)
+    # sweeps in flight per GPU (srb200.concurrent.SeedPool): groups of three seeds run in lockstep - their convolution
+    # phases take turns on the whole device, their head loops (capped at 47 CTAs each, sr_head_args.cta_budget) run side by
+    # side.  Measured on one B200: 270-285 ms per sweep against 350-365 ms for one sweep at a time.  The host side is light
+    # since the keep-masks are drawn on the device (0.2 s of CPU per sweep), so the same setting is used at every --gpus.
     conc = args.concurrency
     if conc <= 0:
-        try:
-            cores = len(os.sched_getaffinity(0))
-        except AttributeError:
-            cores = os.cpu_count() or 1
-        cores = max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world_size))))
-        conc = 1   # measured on one B200 (16 host cores): 2 / 3 in flight change a sweep by -10..+5 % - inside the run-to-run spread
+        conc = 3
     conc = max(1, min(conc, args.steps))
     from srb200.concurrent import SeedPool
     pool = SeedPool(conc, device) if conc > 1 else None

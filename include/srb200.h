@@ -375,7 +375,7 @@ int64_t sr_host_dropblock(const uint8_t* seeds, int64_t planes, int32_t hs, int3
  * table: n_polys polynomials of 624 uint32 (19937 coefficient bits each), entry w-1 = t^(w * SR_MT_JUMP_WORDS) mod the
  * generator's characteristic polynomial; computed on the host (cached inside the library, ~4 ms per entry the first time).
  * ---------------------------------------------------------------------------------------------- */
-#define SR_MT_JUMP_WORDS (1 << 19)
+#define SR_MT_JUMP_WORDS (1 << 18)
 int64_t sr_mt_jump_table_bytes(int32_t n_polys);
 int32_t sr_mt_jump_table(uint32_t* table_host, int32_t n_polys);
 /* state_blob (bytes of torch.get_rng_state(), HOST) is advanced by n_words 32-bit draws; the result is byte-identical to

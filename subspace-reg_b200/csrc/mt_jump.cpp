@@ -7,7 +7,7 @@
 // window (x[n] .. x[n+623]) at an arbitrary distance n.  The state transition is linear over GF(2) with a primitive
 // characteristic polynomial phi of degree 19937, hence with  t^n mod phi(t) = sum_k g_k t^k  (k < 19937)
 //     window(n) = XOR over { k : g_k = 1 } of window(k),
-// i.e. a window 2^19 * w words ahead is an XOR of ~10^4 of the first 19937 windows - 6 M word operations, done by one
+// i.e. a window 2^18 * w words ahead is an XOR of ~10^4 of the first 19937 windows - 6 M word operations, done by one
 // CTA per walker (csrc/mask.cu) or by sr_host_mt_advance below (which keeps torch's HOST generator in step without
 // drawing anything).  This file computes phi (Berlekamp-Massey on the generator's own output, so nothing is taken on
 // faith), the polynomials g^(wJ) for J = SR_MT_JUMP_WORDS, and the host-side advance.
@@ -36,10 +36,19 @@ inline uint32_t twist(uint32_t u, uint32_t v) {
 }
 
 // next window: out[0..623] = x[k+624 .. k+1247] from in[0..623] = x[k .. k+623] (only the top bit of in[0] is used)
-void next_window(const uint32_t* in, uint32_t* out) {
+// (in and out never alias; the second loop reads out[] 227 words behind the one it writes: safe for any vector width <= 227)
+__attribute__((target_clones("arch=skylake-avx512", "avx2", "default"))) void next_window(const uint32_t* __restrict__ in,
+                                                                                         uint32_t* __restrict__ out) {
+#pragma GCC ivdep
     for (int j = 0; j < N - M; ++j) out[j] = in[j + M] ^ twist(in[j], in[j + 1]);
+#pragma GCC ivdep
     for (int j = N - M; j < N - 1; ++j) out[j] = out[j + M - N] ^ twist(in[j], in[j + 1]);
     out[N - 1] = out[M - 1] ^ twist(in[N - 1], out[0]);
+}
+
+__attribute__((target_clones("arch=skylake-avx512", "avx2", "default"))) void xor_window(uint32_t* __restrict__ acc,
+                                                                                        const uint32_t* __restrict__ src) {
+    for (int j = 0; j < N; ++j) acc[j] ^= src[j];
 }
 
 using Poly = std::vector<uint64_t>;   // PW words
@@ -210,8 +219,7 @@ void jump_window(uint32_t* win, const uint32_t* poly32) {
             gw &= gw - 1;
             const int64_t k = (int64_t)wi * 32 + b;
             if (k >= DEG) break;
-            const uint32_t* src = &y[(size_t)k];
-            for (int j = 0; j < N; ++j) acc[j] ^= src[j];
+            xor_window(acc, &y[(size_t)k]);
         }
     }
     memcpy(win, acc, sizeof(acc));

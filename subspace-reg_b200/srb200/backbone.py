@@ -25,6 +25,9 @@ BN_MOMENTUM = 0.1
 _PINNED_POOL = {}
 _MASK_POOL = {}     # device copies of the keep-masks: (run thread, 'mask', block, forward parity) -> grow-only uint8 buffer
 _SCRATCH_POOL = {}
+_SIDE_POOL = {}     # (run thread, device index) -> [mask side stream, sr_device_bernoulli workspace]: one per run thread for
+                    # the life of the process - every new stream brings its own allocator pool, i.e. cudaMalloc calls (and
+                    # the host stalls that come with them) in whatever sweep first uses it
 
 
 def _pad16(c):
@@ -58,8 +61,9 @@ class BackboneEngine(object):
         self._mask_read = {}      # device mask buffer -> event after its last reader on the run's stream
         self._mask_pending = None
         self._dev_masks = None    # this forward's keep-masks when they are drawn on the device: block -> (keep, scale tensor | float)
+        self._dev_plan = None     # (batch, input size, block counters, device) of a forward whose masks are not drawn yet
+        self._dev_ready = None
         self._dev_fwd_done = {}   # forward parity -> event after that forward's last mask reader (buffer reuse fence)
-        self._dev_ws = None       # workspace of sr_device_bernoulli (only ever used on the mask stream)
 
     # ---------------------------------------------------------------- weight packing
     def _bn_key(self):
@@ -224,9 +228,8 @@ class BackboneEngine(object):
             if device_rng.region_words(kind, n) & 1:
                 return None
         main = torch.cuda.current_stream()
-        cs = getattr(self, '_copy_stream', None)
-        if cs is None:
-            cs = self._copy_stream = torch.cuda.Stream(device=device)
+        side = self._side(device)
+        cs = side[0]
         par = self._cur_fwd & 1
         out = {}
         with torch.cuda.stream(cs):
@@ -246,7 +249,7 @@ class BackboneEngine(object):
                     regions.append((1, p, seeds))
                     post.append((seeds, bs, keep, scale))
                     out[bi] = (keep, scale)
-            self._dev_ws = device_rng.draw(regions, self._dev_ws)
+            side[1] = device_rng.draw(regions, side[1])
             for seeds, bs, keep, scale in post:
                 device_rng.dropblock_keep(seeds, bs, keep, scale)
             ev = torch.cuda.Event()
@@ -254,6 +257,14 @@ class BackboneEngine(object):
         ops.LAUNCHES.add(3 + 3 * len(post))
         self._dev_ready = ev
         return out
+
+    def _side(self, device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        key = (self._pool_owner, idx)
+        ent = _SIDE_POOL.get(key)
+        if ent is None:
+            ent = _SIDE_POOL[key] = [torch.cuda.Stream(device=device), None]
+        return ent
 
     def _dev_buf(self, key, shape, device):
         """Grow-only device uint8 buffer per (run thread, key), allocated on the mask stream's pool."""
@@ -410,7 +421,13 @@ class BackboneEngine(object):
         drop_rate = b.get('drop_rate', 0.1)
         if not drop_rate > 0:                                                  # `if self.drop_rate > 0` (:292): no draw at all
             return None, 1.0
-        if self._dev_masks is not None:                                        # drawn on the device at the top of the forward
+        if self._dev_plan is not None:
+            # All masks of this forward are drawn on the device NOW, i.e. after the first block's convolutions have been
+            # queued: the generator kernels (side stream) and the host-side jump of the CPU generator (~0.3 ms) then
+            # overlap that block's device work instead of preceding it.
+            self._dev_masks = self._draw_masks_on_device(*self._dev_plan)
+            self._dev_plan = None
+        if self._dev_masks is not None:
             if self._dev_ready is not None:
                 torch.cuda.current_stream().wait_event(self._dev_ready)
                 self._dev_ready = None
@@ -442,9 +459,7 @@ class BackboneEngine(object):
         # Upload on a side stream: the 20-40 MB mask copy then overlaps the convolutions of this block that are already
         # queued on the run's stream instead of sitting between them (43 MB per support forward, ~26 ms of copies per sweep).
         main = torch.cuda.current_stream()
-        cs = getattr(self, '_copy_stream', None)
-        if cs is None:
-            cs = self._copy_stream = torch.cuda.Stream(device=device)
+        cs = self._side(device)[0]
         # The device copy lives in a grow-only buffer per (block, forward parity) instead of a fresh allocation: mask sizes
         # change with every forward (support / memory batches), so fresh allocations on the copy stream kept reaching
         # cudaMalloc, where the launching thread was seen to block for 100-300 ms.  The buffer's previous reader (the
@@ -482,7 +497,8 @@ class BackboneEngine(object):
         size = x.shape[2] if x.dtype != torch.uint8 else x.shape[1]
         self._cur_fwd = self._pf_fwd
         self._pf_fwd += 1
-        self._dev_masks = self._draw_masks_on_device(B, size, counters, dev) if self.device_masks(dev) else None
+        self._dev_masks = None
+        self._dev_plan = (B, size, counters, dev) if self.device_masks(dev) else None
         h = self.pack(x)
         nb = len(self.blocks)
 

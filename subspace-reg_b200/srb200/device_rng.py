@@ -15,7 +15,7 @@ import torch
 from . import _lib as L
 from . import rng
 
-JUMP_WORDS = 1 << 19
+JUMP_WORDS = 1 << 18
 _lock = threading.Lock()
 _host_table = None          # int32 [n, 624] (CPU), grows
 _dev_tables = {}            # device index -> CUDA copy of (a prefix of) the host table
@@ -100,7 +100,7 @@ def _self_check(device):
             torch.manual_seed(4321)
             torch.rand(5)
             s0 = torch.get_rng_state()
-            n0, n1 = 300000, 5001
+            n0, n1 = 300000, 5001            # 600 k words: crosses two jump boundaries
             a0 = torch.empty(n0, dtype=torch.uint8).bernoulli_(0.9)
             a1 = torch.bernoulli(torch.tensor(0.0123).expand(n1)).to(torch.uint8)
             sa = torch.get_rng_state()

@@ -45,7 +45,7 @@ def test_forward_masks_equal_torch(batch, pre):
 
 
 def test_long_stream_crosses_many_jump_boundaries():
-    """9 M words = 18 walkers; checked against the host replay of the same stream (itself pinned to torch)."""
+    """9 M words = 35 walkers; checked against the host replay of the same stream (itself pinned to torch)."""
     from srb200 import host_rng
     if not host_rng.replay_available():
         pytest.skip("host replay unavailable")

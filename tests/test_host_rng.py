@@ -133,20 +133,23 @@ def test_held_regions_can_be_drawn_off_the_live_generator():
     assert pf.take('b', shape_b) is not None
 
 
-@pytest.mark.parametrize("pre,n", [(0, 5), (7, 617), (7, 618), (100, 624 * 3 + 1), (623, (1 << 19) - 1), (1, 1 << 19),
-                                   (300, (1 << 19) + 77), (17, 3 * (1 << 19) + 12345)])
+JW = 1 << 18   # SR_MT_JUMP_WORDS
+
+
+@pytest.mark.parametrize("pre,n", [(0, 5), (7, 617), (7, 618), (100, 624 * 3 + 1), (623, JW - 1), (1, JW), (300, JW + 77),
+                                   (17, 3 * JW + 12345), (5, 8 * JW - 3)])
 def test_jump_ahead_equals_drawing(pre, n):
     """sr_host_mt_advance (polynomial jump-ahead, csrc/mt_jump.cpp) leaves the generator byte-identical to drawing n words
     one by one: against torch itself for short distances, against the replay's skip for long ones."""
     lib = L.load()
-    table = torch.zeros((4, 624), dtype=torch.int32)
-    assert lib.sr_mt_jump_table(C.c_void_p(table.data_ptr()), 4) == 0
+    table = torch.zeros((8, 624), dtype=torch.int32)
+    assert lib.sr_mt_jump_table(C.c_void_p(table.data_ptr()), 8) == 0
     torch.manual_seed(11 + pre)
     if pre:
         torch.empty(pre, dtype=torch.int32).random_()
     s0 = torch.get_rng_state()
     a = s0.clone()
-    assert lib.sr_host_mt_advance(C.c_void_p(a.data_ptr()), a.numel(), n, C.c_void_p(table.data_ptr()), 4) == 0
+    assert lib.sr_host_mt_advance(C.c_void_p(a.data_ptr()), a.numel(), n, C.c_void_p(table.data_ptr()), 8) == 0
     b = s0.clone()
     assert lib.sr_host_bernoulli(C.c_void_p(b.data_ptr()), b.numel(), 2, 0.0, n, None) == 0
     assert torch.equal(a, b)
@@ -155,4 +158,4 @@ def test_jump_ahead_equals_drawing(pre, n):
         assert torch.equal(torch.get_rng_state(), a)
     # a distance the table does not cover is refused, not approximated
     c = s0.clone()
-    assert lib.sr_host_mt_advance(C.c_void_p(c.data_ptr()), c.numel(), 6 * (1 << 19), C.c_void_p(table.data_ptr()), 4) != 0
+    assert lib.sr_host_mt_advance(C.c_void_p(c.data_ptr()), c.numel(), 10 * JW, C.c_void_p(table.data_ptr()), 8) != 0
