@@ -347,8 +347,7 @@ def main():
     wdir = word_embed_dir()
     from srb200.concurrent import prewarm_allocator
     # one large cached segment for the caching allocator to split (see prewarm_allocator: fewer cudaMalloc stalls)
-    prewarm_allocator(16 + 0.8 * (args.steps + args.warmup), device)
-    config["allocator_prewarm_gb"] = 16 + 0.8 * (args.steps + args.warmup)
+    prewarm_gb = 16 + 0.8 * (args.steps + args.warmup)
 
     def mk(seed):
         return synthetic.make_world(seed, n_sessions=args.sessions, n_base_batch=args.base_batch, word_embed_path=wdir,
@@ -363,7 +362,10 @@ def main():
         conc = 3
     conc = max(1, min(conc, args.steps))
     from srb200.concurrent import SeedPool
-    pool = SeedPool(conc, device) if conc > 1 else None
+    # (the resident worlds live on the caller's stream; every sweep's temporaries on the stream of the thread that runs it)
+    prewarm_allocator(prewarm_gb if conc == 1 else 0.8 * (args.steps + args.warmup) + 2, device)
+    pool = SeedPool(conc, device, prewarm_gb=12.0, group=3 if conc > 3 else None) if conc > 1 else None
+    config["allocator_prewarm_gb"] = prewarm_gb if conc == 1 else 12.0 * conc
     config["sweeps_in_flight_per_gpu"] = conc
     config["conv_precision"] = args.precision
 
@@ -387,9 +389,11 @@ def main():
     torch.cuda.synchronize()
     l0 = ops.LAUNCHES[0]
     sampler.reset()
+    mallocs0 = torch.cuda.memory_stats(device).get('num_device_alloc', 0)
     ms, recs = timed_sweeps(worlds, device, pool)
     clocks = sampler.stop()
     launches = ops.LAUNCHES[0] - l0
+    config["cudaMalloc_calls_in_timed_region"] = int(torch.cuda.memory_stats(device).get('num_device_alloc', 0) - mallocs0)
     del worlds
     epochs = sum(sum(s['epochs'] for s in r['sessions']) for r in recs)
     ms_max = sdist.max_over_ranks(ms, device)

@@ -86,13 +86,19 @@ class SeedPool(object):
     at a time, and returns the results in order; exceptions are re-raised in the caller.  With lockstep=True (default) the
     items are run in groups of K whose session drivers rendezvous before every head loop (ops.align_runs)."""
 
-    def __init__(self, workers, device=None, lockstep=True):
+    def __init__(self, workers, device=None, lockstep=True, prewarm_gb=0.0, group=None):
         self.workers = max(1, int(workers))
         self.lockstep = bool(lockstep) and self.workers > 1
+        # runs per lockstep group (default: all workers form one group).  With workers = 2 x group two groups are in flight:
+        # while one group's head loops spin on their grid barriers the other group's convolutions queue behind them.
+        self.group = self.workers if not group else max(1, min(int(group), self.workers))
+        # PyTorch's caching allocator keeps one pool PER STREAM: a segment reserved on the caller's stream (prewarm_allocator)
+        # is of no use to the workers' streams, so each worker reserves its own before its first run
+        self.prewarm_gb = float(prewarm_gb)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         host_rng.replay_available()              # the generator self-checks touch the global generator: do them here, once
         device_rng.available(self.device)
-        ops.set_gpu_share(self.workers)           # head launches of the K runs must fit on the device together
+        ops.set_gpu_share(self.group)             # head launches of the runs of a group must fit on the device together
         self._q = queue.Queue()
         self._threads = [threading.Thread(target=self._work, daemon=True) for _ in range(self.workers)]
         for t in self._threads:
@@ -101,6 +107,9 @@ class SeedPool(object):
     def _work(self):
         torch.cuda.set_device(self.device)
         stream = torch.cuda.Stream(device=self.device)
+        if self.prewarm_gb > 0:
+            with torch.cuda.stream(stream):
+                prewarm_allocator(self.prewarm_gb, self.device)
         while True:
             job = self._q.get()
             if job is None:
@@ -126,12 +135,19 @@ class SeedPool(object):
         done = threading.Semaphore(0)
         torch.cuda.current_stream().synchronize()     # inputs prepared on the caller's stream are complete
         if self.lockstep:
-            for g0 in range(0, len(items), self.workers):       # one group of <= K runs at a time
-                chunk = items[g0:g0 + self.workers]
+            in_flight = []                                      # sizes of the groups dispatched and not yet finished
+            max_groups = max(1, self.workers // self.group)
+            for g0 in range(0, len(items), self.group):         # groups of <= `group` runs, at most workers / group at a time
+                chunk = items[g0:g0 + self.group]
+                if len(in_flight) == max_groups:
+                    for _ in range(in_flight.pop(0)):           # (approximation: ANY `size` finished runs make room)
+                        done.acquire()
                 group = Lockstep(len(chunk))
                 for j, it in enumerate(chunk):
                     self._q.put((fn, it, out, g0 + j, done, group, j))
-                for _ in chunk:
+                in_flight.append(len(chunk))
+            for n in in_flight:
+                for _ in range(n):
                     done.acquire()
         else:
             for i, it in enumerate(items):
