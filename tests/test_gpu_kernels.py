@@ -225,3 +225,30 @@ def test_support_augmentation_on_device_matches_torchvision():
     want = ops.pack_input(want_f.cuda().contiguous(), 16)
     got = ops.pack_input_u8(x8.cuda(), transform_cfg.mean, transform_cfg.std, 16, crop_ij=ij.cuda(), flip=flip.cuda(), pad=8)
     assert torch.equal(want.view(torch.int16), got.view(torch.int16))
+
+
+def test_head_cta_budget_is_bit_identical():
+    """sr_head_args.cta_budget (fewer, fatter CTAs so that several runs' cooperative head launches are co-resident) changes
+    the launch shape only: loss trace and weights equal the unconstrained kernel's bit for bit, for SGD and Adam."""
+    from srb200 import ops, _lib as L
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(5)
+    for adam in (False, True):
+        Ns, Nm, nb, npv, nn_, d = 185, 175, 60, 35, 5, 640
+        Cn = nb + npv + nn_
+        feat = (torch.randn(Ns + Nm, d, device=dev, generator=g) * 0.45 + 0.53).clamp_min(-0.11)
+        ys = torch.randint(0, Cn, (Ns,), device=dev, generator=g)
+        ym = torch.randint(0, Cn, (Nm,), device=dev, generator=g)
+        W = (torch.rand(Cn, d, device=dev, generator=g) * 2 - 1) / d ** 0.5
+        base, reserve = W[:nb].clone(), W[nb:nb + npv].clone()
+        qt, q, _ = ops.subspace_factor(base.contiguous())
+        got = []
+        for budget in (0, 74, 49):
+            hs = ops.HeadSession(feat, Ns, 0, ys, W.clone(), nb, nn_, n_memory=Nm, memory_row0=Ns, labels_memory=ym,
+                                 base_weight=base, reserve_weight=reserve, pull_mode=L.SR_PULL_PROJECT, pull=qt, q_rows=q,
+                                 lmbd_base=0.2, lmbd_novel=0.1, gamma=1.0, adam=adam, stable=False, target_train_loss=-1.0,
+                                 min_novel_epochs=0, max_novel_epochs=10 ** 6, cta_budget=budget)
+            tr = hs.run(200)
+            got.append((tr.clone(), hs.weight.clone()))
+        for tr, w in got[1:]:
+            assert torch.equal(tr, got[0][0]) and torch.equal(w, got[0][1])
