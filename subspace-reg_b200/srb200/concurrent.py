@@ -40,8 +40,13 @@ def prewarm_allocator(gigabytes, device=None):
     to cudaMalloc (~9 calls per sweep), and on the B200 boxes used here a cudaMalloc / the copies and allocations queued
     behind it occasionally block the launching thread for 100-300 ms.  With one large cached segment to split, those
     requests are served without touching the driver (measured over 24 sweeps: stalls > 200 ms in 5 sweeps -> 1)."""
-    x = torch.empty(int(gigabytes * (1 << 30)), dtype=torch.uint8, device=device if device is not None else "cuda")
+    dev = device if device is not None else "cuda"
+    x = torch.empty(int(gigabytes * (1 << 30)), dtype=torch.uint8, device=dev)
     del x
+    # Requests of <= 1 MB come from a separate pool of 2 MB segments (status blocks, traces, labels, statistics: a few
+    # hundred per sweep); reserve some of those too, so that the small pool does not grow inside a sweep either.
+    small = [torch.empty(1 << 19, dtype=torch.uint8, device=dev) for _ in range(256)]
+    del small
 
 
 class Lockstep(object):
