@@ -259,7 +259,7 @@ REFERENCE_SAMPLE = ("%d x (session 1 of the config-2 sweep, capped at %d epochs,
                     "sample's")
 
 
-def head_stress(device, hbm_gbs, steps=5):
+def head_stress(device, hbm_gbs, steps=20):
     """Fine-tune steps of the fused head at the config-5 shapes; algorithmic bytes / FLOPs per step from SURVEY 8d."""
     import torch
     from srb200 import ops, _lib as L
@@ -280,9 +280,10 @@ def head_stress(device, hbm_gbs, steps=5):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        hs.run(steps)
+        hs.run(steps, defer=True)      # (queued only: the result read-back is not part of a fine-tune step)
         e1.record()
         torch.cuda.synchronize()
+        hs.collect()
         ms = e0.elapsed_time(e1) / steps
         qr = min(n_base, d)
         bytes_step = 4 * N * d + 8 * N + 4 * Cn * d * 4 + 4 * n_base * d + 4 * qr * d
