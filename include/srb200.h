@@ -343,6 +343,15 @@ int32_t sr_linear_bwd(const float* dy, const float* x, int32_t n, int32_t k, int
  * loss[0] += mean((y-target)^2) (caller zeroes it); dy = 2 (y - target) / n;  param -= lr * (grad + weight_decay * param). */
 int32_t sr_mse_grad(const float* y, const float* target, int64_t n, float* dy, float* loss, void* stream);
 int32_t sr_sgd_update(float* param, const float* grad, int64_t n, float lr, float weight_decay, void* stream);
+/* learn_mapping.py:41-67 in ONE launch: `epochs` full-batch SGD steps (lr, weight_decay, no momentum) on nn.MSELoss(mean)
+ * of y = x weight^T + bias against target.  x [n,e], target [n,d], weight [d,e] and bias [d] updated in place,
+ * loss_trace [epochs] (optional) = the loss BEFORE each step.  Output dimensions are independent, so every CTA fits its own
+ * rows of `weight` out of shared memory without any exchange.  sr_fit_linear_map_workspace_bytes returns 0 when n x e does
+ * not fit in shared memory (use the per-op entry points above then). */
+int64_t sr_fit_linear_map_workspace_bytes(int32_t n, int32_t e, int32_t d, int32_t epochs);
+int32_t sr_fit_linear_map(const float* x, const float* target, float* weight, float* bias, int32_t n, int32_t e, int32_t d,
+                          int32_t epochs, float lr, float weight_decay, float* loss_trace, void* workspace,
+                          int64_t workspace_bytes, void* stream);
 /* out[0] = sum((a-b)^2)  (torch.norm(a-b)**2, :90,232,239). */
 int32_t sr_sqdist(const float* a, const float* b, int64_t n, float* out, void* stream);
 /* out = (a-b) * scale * gout[0] * (sq ? 1/sqrt(sq[0]), 0 when sq[0]==0 : 1): backward of s*||a-b||^2 (sq NULL,

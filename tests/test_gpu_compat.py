@@ -130,13 +130,30 @@ def test_fit_linear_map_matches_learn_mapping_recipe(word_embed_dir):
     T = torch.randn(60, 640, generator=g) * 0.05
     init = {'map.weight': torch.randn(640, 300, generator=g) * 0.02, 'map.bias': torch.zeros(640)}
     import time
-    mapping.fit_linear_map(E.cuda(), T.cuda(), epochs=5, lr=1.0, weight_decay=5e-4, init=init)      # warm-up
+    res = {}
+    for fused in (True, False):
+        mapping.fit_linear_map(E.cuda(), T.cuda(), epochs=5, lr=1.0, weight_decay=5e-4, init=init, fused=fused)      # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res[fused] = mapping.fit_linear_map(E.cuda(), T.cuda(), epochs=200, lr=1.0, weight_decay=5e-4, init=init, fused=fused)
+        torch.cuda.synchronize()
+        print("fit_linear_map (%s): %.1f us per full-batch step (60 x 300 -> 640)" %
+              ("one launch: sr_fit_linear_map" if fused else "5 launches per step, host-bound", (time.perf_counter() - t0) * 1e6 / 200))
+    Ec, Tc = E.cuda(), T.cuda()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    sd, losses = mapping.fit_linear_map(E.cuda(), T.cuda(), epochs=200, lr=1.0, weight_decay=5e-4, init=init)
+    e0.record()
+    mapping.fit_linear_map(Ec, Tc, epochs=1000, lr=1.0, weight_decay=5e-4, init=init)
+    e1.record()
     torch.cuda.synchronize()
-    print("fit_linear_map: %.1f us per full-batch step (60 x 300 -> 640; 5 launches per step, host-bound)" %
-          ((time.perf_counter() - t0) * 1e6 / 200))
+    print("fit_linear_map, the reference's 1000 steps in one launch: %.2f ms of device time (%.2f us per step)" %
+          (e0.elapsed_time(e1), e0.elapsed_time(e1)))
+    sd, losses = res[True]
+    # the one-launch fit against the per-op route (same arithmetic, different summation order)
+    for k in sd:
+        rel = ((sd[k] - res[False][0][k]).norm() / res[False][0][k].norm()).item()
+        assert rel < 1e-5, (k, rel)
+    np.testing.assert_allclose(losses, res[False][1], rtol=1e-5)
     W = init['map.weight'].double().clone().requires_grad_(True)
     b = init['map.bias'].double().clone().requires_grad_(True)
     opt = torch.optim.SGD([W, b], lr=1.0, weight_decay=5e-4)
@@ -148,6 +165,8 @@ def test_fit_linear_map_matches_learn_mapping_recipe(word_embed_dir):
         opt.step()
         ref.append(loss.item())
     np.testing.assert_allclose(losses, ref, rtol=1e-4)
+    assert ((sd['map.weight'].cpu().double() - W.detach()).norm() / W.detach().norm()).item() < 1e-5
+    assert ((sd['map.bias'].cpu().double() - b.detach()).norm() / b.detach().norm()).item() < 1e-4
     assert ((sd['map.weight'].cpu().double() - W.detach()).abs().max() / W.detach().abs().max()).item() < 1e-4
     assert ((sd['map.bias'].cpu().double() - b.detach()).abs().max() / (b.detach().abs().max() + 1e-12)).item() < 1e-3
 
