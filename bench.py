@@ -460,6 +460,11 @@ def main():
     # events on the sweep's stream) over the images they encoded, against the sustained peak
     # (with several sweeps in flight the events of one stream also span the other streams' kernels, so the phases are
     # taken from one extra sweep run alone after the timed region)
+    # (one untimed sweep first: with several sweeps in flight the timed region ran on the workers' streams, so the caller's
+    # stream has not seen a sweep's allocation pattern yet - its first sweep would pay cudaMalloc inside the events)
+    if pool is not None:
+        run_sweeps([prepare(place_world(mk(3000 + rank), 'gpu'))], None)
+        torch.cuda.synchronize()
     solo_prepared = prepare(place_world(mk(2000 + rank), 'gpu'))
     solo_prepared[1].engine().conv_events = []      # CUDA events around the conv launches of every cache-build chunk
     solo = run_sweeps([solo_prepared], None)

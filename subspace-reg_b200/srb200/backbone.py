@@ -42,7 +42,7 @@ class BackboneEngine(object):
 
     def __init__(self, blocks, chunk=1024, precision=None):
         self.blocks = blocks
-        self.chunk = chunk
+        self.chunk = int(os.environ.get("SRB_EVAL_CHUNK", chunk))   # images per eval-mode pass (A/B timing override)
         # 'bf16': one tcgen05 pass on bf16 operands (throughput tier, features ~3e-3 from fp32);
         # 'bf16x3': error-compensated operand pairs, three passes into the same fp32 accumulator (parity tier, ~1e-5)
         self.precision = precision or os.environ.get("SRB_CONV_PRECISION", "bf16")
