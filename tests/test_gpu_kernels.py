@@ -252,3 +252,4 @@ def test_head_cta_budget_is_bit_identical():
             got.append((tr.clone(), hs.weight.clone()))
         for tr, w in got[1:]:
             assert torch.equal(tr, got[0][0]) and torch.equal(w, got[0][1])
+

@@ -27,8 +27,9 @@ hs.run(2)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize()
 e0.record()
-tr = hs.run(steps)
+hs.run(steps, defer=True)      # queued only: the read-back is not part of a step
 e1.record()
 torch.cuda.synchronize()
+tr = hs.collect()
 print("config 5 (n_base %d): %.1f us per step over %d steps, last loss %.6f" % (n_base, e0.elapsed_time(e1) * 1e3 / steps, steps,
                                                                                 float(tr[-1, 0])))
