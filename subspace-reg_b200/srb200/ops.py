@@ -358,6 +358,7 @@ def subspace_factor(base_weight):
 
 
 _GPU_SHARE = [1]
+_share_tls = threading.local()
 
 
 def set_gpu_share(runs):
@@ -369,12 +370,12 @@ def set_gpu_share(runs):
 
 def head_cta_budget():
     k = _GPU_SHARE[0]
+    ls = getattr(_share_tls, "lockstep", None)
+    if ls is not None:
+        k = min(k, ls.n)      # a trailing group of fewer runs (one run: the device is its own again)
     if k <= 1:
         return 0
     return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count // k
-
-
-_share_tls = threading.local()
 
 
 def bind_lockstep(ls):
