@@ -97,7 +97,7 @@ def _self_check(device):
     ok = True
     try:
         with torch.cuda.device(device):
-            torch.manual_seed(4321)
+            torch.default_generator.manual_seed(4321)     # the CPU generator only: torch.manual_seed would reseed CUDA's too
             torch.rand(5)
             s0 = torch.get_rng_state()
             n0, n1 = 300000, 5001            # 600 k words: crosses two jump boundaries

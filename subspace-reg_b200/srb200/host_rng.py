@@ -55,7 +55,7 @@ def _self_check():
     ok = True
     try:
         for kind, p in ((0, 0.9), (1, 0.0123), (0, 0.5), (1, 0.5)):
-            torch.manual_seed(1234 + kind)
+            torch.default_generator.manual_seed(1234 + kind)     # CPU generator only (torch.manual_seed reseeds CUDA's too)
             torch.rand(7)                          # start mid-block
             s0 = torch.get_rng_state()
             a = _torch_draw((3, 1777), p, kind)
