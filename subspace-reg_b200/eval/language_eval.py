@@ -15,7 +15,6 @@ B200-first restructuring of the session loop (same numbers, different schedule):
 """
 from __future__ import print_function
 
-import copy
 import itertools
 import sys
 import time
@@ -105,9 +104,9 @@ def few_shot_finetune_incremental_test(net, ckpt, criterion, meta_valloader, bas
 
     rng.manual_seed(opt.set_seed)          # torch.manual_seed + np.random.seed (of this thread's run, srb200/rng.py)
 
-    basenet = copy.deepcopy(net).cuda()
-    base_weight, base_bias = basenet._get_base_weights()
-    base_weight = base_weight.contiguous()
+    # (the reference deep-copies the whole network - language_eval.py:106-107 - only to read this clone off the copy)
+    base_weight, base_bias = net._get_base_weights()
+    base_weight = base_weight.cuda().contiguous()
     dev = base_weight.device
     n_base_cls = net.num_classes
     W_cols = base_weight.shape[1]
