@@ -75,6 +75,24 @@ def test_argument_validation_without_gpu(lib):
     h = _lib.HeadArgs()
     assert lib.sr_head_run(ctypes.byref(h), None) == -1
     assert lib.sr_pack_input(None, None, None, 1, 3, 84, 84, 16, None) == -1
+    # the entry points added in round 2: mask generator, DropBlock, the one-launch mapping fit
+    import torch
+    state = torch.get_rng_state().clone()
+    regs = (_lib.MaskRegion * 2)()
+    assert lib.sr_device_bernoulli(None, 0, regs, 2, None, None, 0, None, 0, None) == -1
+    regs[0].kind, regs[0].n, regs[0].out = 1, 3, 4096          # an odd word count before the last region is refused
+    regs[1].kind, regs[1].n, regs[1].out = 0, 4, 8192
+    assert lib.sr_device_bernoulli(ctypes.c_void_p(state.data_ptr()), state.numel(), regs, 2, None, None, 0, None, 0, None) == -1
+    assert b"odd word count" in lib.sr_last_error()
+    regs[0].n = 1 << 20                                         # more words than the (empty) jump table covers
+    assert lib.sr_device_bernoulli(ctypes.c_void_p(state.data_ptr()), state.numel(), regs, 2, None, None, 0, None, 0, None) == -1
+    assert b"jump polynomials" in lib.sr_last_error()
+    assert torch.equal(state, torch.get_rng_state())           # a refused call leaves the generator state alone
+    assert lib.sr_dropblock_keep(None, 1, 6, 6, 5, None, None, None) == -1
+    assert lib.sr_fit_linear_map(None, None, None, None, 60, 300, 640, 10, 1.0, 5e-4, None, None, 0, None) == -1
+    assert lib.sr_fit_linear_map_workspace_bytes(60, 300, 640, 1000) > 0
+    assert lib.sr_fit_linear_map_workspace_bytes(4096, 4096, 640, 10) == 0     # does not fit in shared memory: per-op route
+    assert lib.sr_host_mt_advance(None, 0, 5, None, 0) == -1
 
 
 def test_no_cpu_fallback():
