@@ -54,25 +54,37 @@ class Lockstep(object):
     the calling thread's CUDA stream waiting for everything the other n - 1 streams had queued at that point.  A run that
     fails or finishes early leaves the group with leave(); the others carry on unaligned."""
 
-    def __init__(self, n):
+    def __init__(self, n, record=None, wait=None):
+        """record() -> event of the calling thread's stream at this point; wait(event): make the calling thread's stream wait
+        for it.  Defaults: CUDA events on the current stream (the CPU tests pass plain callables)."""
         self.n = n
         self.broken = n <= 1
         self._events = [None] * n
         self._barrier = threading.Barrier(n) if n > 1 else None
+        self._record = record or self._cuda_record
+        self._wait = wait or self._cuda_wait
 
-    def align(self):
-        if self.broken:
-            return
-        slot = getattr(_slot, "i", None)
+    @staticmethod
+    def _cuda_record():
         ev = torch.cuda.Event()
         ev.record()
-        self._events[slot] = ev
+        return ev
+
+    @staticmethod
+    def _cuda_wait(ev):
+        torch.cuda.current_stream().wait_event(ev)
+
+    def align(self, slot=None):
+        if self.broken:
+            return
+        if slot is None:
+            slot = getattr(_slot, "i", None)
+        self._events[slot] = self._record()
         try:
             self._barrier.wait(timeout=120.0)           # every run has recorded its event
-            mine = torch.cuda.current_stream()
             for i, e in enumerate(self._events):
                 if i != slot and e is not None:
-                    mine.wait_event(e)
+                    self._wait(e)
             self._barrier.wait(timeout=120.0)           # every run has read the list (it is reused by the next align)
         except threading.BrokenBarrierError:
             self.broken = True

@@ -299,3 +299,58 @@ def test_reference_format_checkpoint_round_trip(tmp_path):
     import pytest
     with pytest.raises(ValueError):
         load_backbone(synthetic.init_model(create_model, opt_b, 1), ckpt)
+
+
+def test_lockstep_rendezvous_protocol():
+    """srb200.concurrent.Lockstep (the rendezvous that makes the head loops of the runs sharing a GPU start together): every
+    align() returns only after all runs of the group have reached it, each run waits for exactly the events the OTHER runs
+    recorded in that round, a run that leaves (finished or failed) releases the rest, and a group of one never waits."""
+    import threading
+    from srb200.concurrent import Lockstep
+    n, rounds = 3, 5
+    log = [[] for _ in range(n)]          # per run: the events it waited for, round by round
+    counter = [0] * n
+    tls = threading.local()
+
+    def record():
+        counter[tls.i] += 1
+        return (tls.i, counter[tls.i])
+
+    def wait(ev):
+        log[tls.i].append(ev)
+
+    group = Lockstep(n, record=record, wait=wait)
+    arrived = []
+
+    def run(i):
+        tls.i = i
+        for r in range(rounds):
+            arrived.append((r, i))
+            group.align(slot=i)
+            # nobody is past round r before everybody has arrived at round r
+            assert {(r, j) for j in range(n)} <= set(arrived)
+        if i == 0:
+            group.leave()
+
+    ts = [threading.Thread(target=run, args=(i,)) for i in range(n)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=30)
+    assert not any(t.is_alive() for t in ts)
+    for i in range(n):
+        assert log[i] == [(j, r + 1) for r in range(rounds) for j in range(n) if j != i]
+    # after a run has left, the others pass straight through
+    assert group.broken
+    group.align(slot=1)
+    # a failing run must not keep the others waiting: leave() breaks a barrier that is being waited on
+    g2 = Lockstep(2, record=lambda: None, wait=lambda e: None)
+    done = []
+    t = threading.Thread(target=lambda: (g2.align(slot=0), done.append(1)))
+    t.start()
+    g2.leave()
+    t.join(timeout=30)
+    assert done == [1] and g2.broken
+    # a group of one never waits
+    g1 = Lockstep(1, record=lambda: (_ for _ in ()).throw(AssertionError("no event for a single run")), wait=None)
+    g1.align(slot=0)
