@@ -295,6 +295,9 @@ typedef struct sr_head_args {
 } sr_head_args;
 
 int64_t sr_head_workspace_bytes(const sr_head_args* a);
+/* Host only (no device needed): out4 = {kernel sr_head_run picks: 0 fp32 SIMT tiles, 1 paper-size persistent kernel, 2 its
+ * cluster variant, 3 tensor-core head; rows per row CTA; feature columns per column CTA; CTAs of the cooperative launch}. */
+int32_t sr_head_plan(const sr_head_args* a, int32_t* out4);
 /* Persistent kernel: loops epochs on the device until the stopping rule fires or max_epochs is reached. */
 int32_t sr_head_run(const sr_head_args* a, void* stream);
 

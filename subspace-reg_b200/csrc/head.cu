@@ -602,6 +602,24 @@ extern "C" int64_t sr_head_workspace_bytes(const sr_head_args* a) {
     return n;
 }
 
+// Host-only view of the dispatch: which kernel sr_head_run picks for this problem and, for the paper-size kernel, its launch
+// shape under a->cta_budget.  out[0] = kernel (0 = fp32 SIMT head_kernel, 1 = head_small, 2 = head_cluster, 3 = tensor-core
+// head_tc), out[1] = rows per row CTA, out[2] = feature columns per column CTA, out[3] = CTAs of the cooperative launch.
+extern "C" int32_t sr_head_plan(const sr_head_args* a, int32_t* out4) {
+    if (!a || !out4) return fail(SR_E_ARG, "sr_head_plan: null pointer");
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    if (a->dim < 4 || a->dim % 4 || a->n_support < 1 || a->n_classes < 1) return fail(SR_E_ARG, "sr_head_plan: empty problem");
+    if (srb::head_small_applicable(a)) {
+        out4[0] = srb::head_cluster_applicable(a) ? 2 : 1;
+        int r = 0, c = 0, g = 0;
+        srb::head_small_shape(a, &r, &c, &g);
+        out4[1] = r; out4[2] = c; out4[3] = g;
+    } else if (srb::head_tc_applicable(a) && !getenv("SRB_HEAD_SIMT")) {
+        out4[0] = 3;
+    }
+    return SR_OK;
+}
+
 extern "C" int32_t sr_head_run(const sr_head_args* a, void* stream_v) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     if (!a) return fail(SR_E_ARG, "sr_head_run: null args");

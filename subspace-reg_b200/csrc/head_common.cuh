@@ -131,6 +131,7 @@ namespace srb {
 bool head_small_applicable(const sr_head_args* a);
 int64_t head_small_workspace_bytes(const sr_head_args* a);
 int32_t head_small_run(const sr_head_args* a, cudaStream_t stream);
+void head_small_shape(const sr_head_args* a, int* rows_per_cta, int* cols_per_cta, int* ctas);   // host only
 bool head_cluster_applicable(const sr_head_args* a);
 int64_t head_cluster_workspace_bytes(const sr_head_args* a);
 int32_t head_cluster_run(const sr_head_args* a, cudaStream_t stream);

@@ -666,6 +666,22 @@ bool head_small_applicable(const sr_head_args* a) {
 // (sized for the widest grid: 8 columns per column CTA)
 int64_t head_small_workspace_bytes(const sr_head_args* a) { return small_layout(a, a->dim / 8).total; }
 
+// The launch shape head_small_run will use (host only; sr_head_plan).
+void head_small_shape(const sr_head_args* a, int* rows_per_cta, int* cols_per_cta, int* ctas) {
+    const int nt = a->n_support + a->n_memory;
+    const int CP = a->n_classes <= 64 ? 64 : 128;
+    const int ldn = (int)align_up(nt, KC);
+    const int budget = cta_budget(a);
+    int R = pick_rows(nt, budget), DCc = pick_cols(a->dim, budget);
+    if (small_smem_bytes(a, R, CP, DCc, ldn, true) > 200 * 1024) {
+        R = pick_rows(nt, 0);
+        DCc = pick_cols(a->dim, 0);
+    }
+    *rows_per_cta = R;
+    *cols_per_cta = DCc;
+    *ctas = std::max((nt + R - 1) / R, a->dim / DCc) + 2;
+}
+
 int32_t head_small_run(const sr_head_args* a, cudaStream_t stream) {
     SmallParams p;
     p.a = *a;

@@ -20,7 +20,7 @@ EXPORTS = [
     "sr_head_workspace_bytes", "sr_head_run", "sr_eval_logits", "sr_semantic_pullers", "sr_linear_fwd",
     "sr_linear_bwd", "sr_sqdist", "sr_diff_scale", "sr_project_rows", "sr_score_logits", "sr_host_bernoulli", "sr_host_dropblock", "sr_conv_plan", "sr_pack_input_u8", "sr_global_avg", "sr_mse_grad", "sr_sgd_update", "sr_eval_workspace_bytes", "sr_train_block", "sr_backbone_eval_workspace_bytes", "sr_backbone_eval",
     "sr_mt_jump_table_bytes", "sr_mt_jump_table", "sr_host_mt_advance", "sr_device_bernoulli_workspace_bytes",
-    "sr_device_bernoulli", "sr_dropblock_keep", "sr_fit_linear_map_workspace_bytes", "sr_fit_linear_map",
+    "sr_device_bernoulli", "sr_dropblock_keep", "sr_fit_linear_map_workspace_bytes", "sr_fit_linear_map", "sr_head_plan",
 ]
 
 
@@ -147,6 +147,8 @@ def load():
     lib.sr_subspace_factor.argtypes = [vp, i32, i32, vp, vp, vp, i64, vp]
     lib.sr_head_workspace_bytes.restype = i64
     lib.sr_head_workspace_bytes.argtypes = [C.POINTER(HeadArgs)]
+    lib.sr_head_plan.restype = i32
+    lib.sr_head_plan.argtypes = [C.POINTER(HeadArgs), C.POINTER(C.c_int32)]
     lib.sr_head_run.restype = i32
     lib.sr_head_run.argtypes = [C.POINTER(HeadArgs), vp]
     lib.sr_eval_workspace_bytes.restype = i64

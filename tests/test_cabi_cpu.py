@@ -169,3 +169,32 @@ def test_integration_doc_lists_every_entry_point():
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     missing = [f for f in declared_functions() if f not in doc and f.replace("sr_linear_", "sr_linear_") not in doc]
     assert not missing, missing
+
+
+def test_head_plan_for_every_session_shape(lib):
+    """sr_head_plan (host only): every session of BASELINE config 2 runs on the paper-size persistent kernel; without a CTA
+    budget it takes the fastest shape (4 rows / 8 columns per CTA, 82-92 CTAs: two such cooperative launches do NOT fit on 148
+    SMs), with the budget of three runs per GPU (148 // 3 = 49) every session's launch is <= 49 CTAs so that three are
+    resident together; config 5 goes to the tensor-core head, a mid-size problem to the SIMT tiles."""
+    from srb200 import _lib
+
+    def plan(ns, nm, ncls, dim, budget, n_new=5, q=60, n_base=60):
+        a = _lib.HeadArgs()
+        a.n_support, a.n_memory, a.n_classes, a.dim = ns, nm, ncls, dim
+        a.n_base, a.n_new, a.n_prev_novel = n_base, n_new, max(ncls - n_base - n_new, 0)
+        a.pull_mode, a.q_rows, a.optimizer, a.cta_budget = _lib.SR_PULL_PROJECT, q, _lib.SR_OPT_SGD, budget
+        out = (ctypes.c_int32 * 4)()
+        assert lib.sr_head_plan(ctypes.byref(a), out) == 0
+        return list(out)
+
+    for s in range(1, 9):
+        ns, nm, ncls = 185, 25 * (s - 1), 60 + 5 * s
+        kind, rows, cols, ctas = plan(ns, nm, ncls, 640, 0)
+        assert (kind, rows, cols) == (1, 4, 8) and ctas == max((ns + nm + 3) // 4, 80) + 2 and 2 * ctas > 148
+        for budget in (74, 49):
+            kind, rows, cols, ctas = plan(ns, nm, ncls, 640, budget)
+            assert kind == 1 and ctas <= budget and (148 // budget) * ctas <= 148, (s, budget, ctas)
+            assert ctas == max((ns + nm + rows - 1) // rows, 640 // cols) + 2
+    assert plan(10000, 0, 1100, 512, 0, n_new=100, q=512, n_base=1000)[0] == 3      # BASELINE config 5
+    assert plan(9000, 1000, 300, 512, 0, n_new=50, q=256)[0] == 0                   # neither small nor large
+    assert lib.sr_head_plan(None, None) == -1
